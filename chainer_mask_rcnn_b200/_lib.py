@@ -1,0 +1,107 @@
+"""ctypes binding of libcmr_b200.so (declared in include/cmr_b200.h).
+
+There is no CPU fallback: if the library is missing, or a call returns a
+non-zero status, an exception is raised.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libcmr_b200.so')
+
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+c_size_t = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/cmr_b200.h one to one.
+_SIGNATURES = {
+    'cmr_status_string': (ctypes.c_char_p, [c_int]),
+    'cmr_version': (c_int, []),
+    'cmr_last_cuda_error': (ctypes.c_char_p, []),
+    'cmr_roi_align_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                  c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'cmr_roi_align_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'cmr_roi_align_nhwc_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_float, c_int,
+                                       c_void_p, c_void_p]),
+    'cmr_roi_align_nhwc_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, c_int, c_int, c_float, c_int,
+                                       c_void_p, c_void_p]),
+    'cmr_nms_workspace_bytes': (c_size_t, [c_int]),
+    'cmr_nms': (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                        c_size_t, c_void_p]),
+    'cmr_proposals_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'cmr_proposals': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                              c_float, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_size_t, c_void_p]),
+    'cmr_conv_gemm_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p]),
+    'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+
+class ConvDesc(ctypes.Structure):
+    """struct cmr_conv_desc (include/cmr_b200.h)."""
+    _fields_ = [(n, c_int) for n in (
+        'batch', 'in_h', 'in_w', 'in_c', 'in_ld', 'out_h', 'out_w', 'kh', 'kw', 'stride',
+        'pad', 'n', 'd_h', 'd_w', 'd_ld', 'd_stride', 'd_oy', 'd_ox', 'relu', 'round_tf32',
+        'tile_n')]
+
+
+EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))
+
+
+class CmrError(RuntimeError):
+    """A libcmr_b200 entry point returned a non-zero cmr_status."""
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libcmr_b200.so is missing at {} -- run `python -m '
+            'chainer_mask_rcnn_b200.build` (or __graft_entry__.build()). There is no CPU '
+            'fallback.'.format(LIB_PATH))
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        lib = load()
+        msg = lib.cmr_status_string(status).decode()
+        detail = lib.cmr_last_cuda_error().decode() if status == -2 else ''
+        raise CmrError('{} failed: {} ({}) {}'.format(what, msg, status, detail))
+
+
+def call(name, *args):
+    """Call an int-status entry point and raise CmrError on failure."""
+    check(getattr(load(), name)(*args), name)
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream, as a void*."""
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError('tensor must be contiguous')
+    return ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,40 @@
+// Shared helpers for the cmr_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cmr_b200.h"
+
+namespace cmr {
+
+// Records the last CUDA error text for cmr_last_cuda_error().
+void record_cuda_error(cudaError_t e, const char* file, int line);
+
+#define CMR_CUDA_TRY(expr)                                   \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) {                                 \
+      ::cmr::record_cuda_error(_e, __FILE__, __LINE__);      \
+      return CMR_ERR_CUDA;                                   \
+    }                                                        \
+  } while (0)
+
+#define CMR_LAUNCH_CHECK() CMR_CUDA_TRY(cudaGetLastError())
+
+#define CMR_REQUIRE(cond)                 \
+  do {                                    \
+    if (!(cond)) return CMR_ERR_INVALID_ARG; \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Number of SMs of the current device (148 on B200), cached per process.
+int sm_count();
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline long long ceil_div_ll(long long a, long long b) {
+  return (a + b - 1) / b;
+}
+
+}  // namespace cmr

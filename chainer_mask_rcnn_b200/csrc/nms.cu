@@ -1,0 +1,431 @@
+// Greedy NMS (warp-bitmask) and RPN proposal generation for sm_100a.
+//
+// Replaces, on device and without host round trips:
+//   chainercv non_maximum_suppression  (called at models/mask_rcnn.py:193-194 and
+//                                       inside ProposalCreator)
+//   chainercv ProposalCreator.__call__ (models/region_proposal_network.py:135-141)
+//
+// Results are integers (keep lists / proposal indices) and must be bit-exact
+// against the CPU algorithm, so every fp32 expression below is written with
+// explicitly rounded intrinsics in the same order as the NumPy code (no FMA
+// contraction):  area = (y2-y1)*(x2-x1);  inter = (br_y-tl_y)*(br_x-tl_x) when
+// tl < br on both axes, else 0;  iou = inter / ((area_i + area_j) - inter);
+// suppressed iff iou >= thresh.
+#include "common.cuh"
+
+namespace cmr {
+namespace {
+
+__device__ __forceinline__ float box_area(const float4 b) {  // (y1,x1,y2,x2) = (x,y,z,w)
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+__device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float4 b,
+                                       float area_b, float thresh) {
+  const float tl_y = fmaxf(a.x, b.x), tl_x = fmaxf(a.y, b.y);
+  const float br_y = fminf(a.z, b.z), br_x = fminf(a.w, b.w);
+  float inter = __fmul_rn(__fsub_rn(br_y, tl_y), __fsub_rn(br_x, tl_x));
+  if (!(tl_y < br_y && tl_x < br_x)) inter = __fmul_rn(inter, 0.0f);
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return iou >= thresh;
+}
+
+// mask[i][cb] bit k  <=>  j = 64*cb + k > i  and  IoU(i, j) >= thresh.
+// grid = (nb, nb, B); only the upper block triangle does work.
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ n_arr, int n_max,
+                float thresh, unsigned long long* __restrict__ mask, int nb_stride) {
+  const int img = blockIdx.z;
+  const int n = n_arr ? min(n_arr[img], n_max) : n_max;
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+  boxes += (size_t)img * n_max;
+  mask += (size_t)img * n_max * nb_stride;
+  __shared__ float4 cbox[64];
+  __shared__ float carea[64];
+  const int t = threadIdx.x;
+  const int j = cb * 64 + t;
+  if (j < n) {
+    cbox[t] = boxes[j];
+    carea[t] = box_area(cbox[t]);
+  }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i < n) {
+    const float4 b = boxes[i];
+    const float ai = box_area(b);
+    const int ncol = min(64, n - cb * 64);
+    unsigned long long bits = 0ull;
+    for (int k = (rb == cb) ? t + 1 : 0; k < ncol; ++k)
+      if (iou_ge(b, ai, cbox[k], carea[k], thresh)) bits |= (1ull << k);
+    mask[(size_t)i * nb_stride + cb] = bits;
+  }
+}
+
+// One CTA per image resolves the bitmask sequentially in 64-box chunks.
+// Thread 0 resolves the diagonal 64x64 block from registers; all warps then OR
+// the kept rows into the running "removed" mask held in shared memory.
+constexpr int kSweepThreads = 256;  // thread 0 keeps 64 mask words in registers
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ n_arr,
+                 int n_max, int nb_stride, int limit, int32_t* __restrict__ keep,
+                 int32_t* __restrict__ n_keep, int keep_stride) {
+  extern __shared__ unsigned long long remv[];  // nb_stride words
+  __shared__ unsigned long long diag[64];
+  __shared__ int kept_list[64];
+  __shared__ int kept_n, count_s, done_s;
+  const int img = blockIdx.x;
+  const int n = n_arr ? min(n_arr[img], n_max) : n_max;
+  const int nb = (n + 63) / 64;
+  mask += (size_t)img * n_max * nb_stride;
+  keep += (size_t)img * keep_stride;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int w = t; w < nb_stride; w += kSweepThreads) remv[w] = 0ull;
+  if (t == 0) {
+    count_s = 0;
+    done_s = 0;
+  }
+  unsigned long long next_diag = 0ull;
+  if (t < 64 && t < n) next_diag = mask[(size_t)t * nb_stride + 0];
+  __syncthreads();
+  for (int cb = 0; cb < nb; ++cb) {
+    if (t < 64) {
+      diag[t] = next_diag;
+      const int i = (cb + 1) * 64 + t;  // prefetch the next diagonal block
+      next_diag = (cb + 1 < nb && i < n) ? mask[(size_t)i * nb_stride + cb + 1] : 0ull;
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long d[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) d[j] = diag[j];
+      unsigned long long r = remv[cb];
+      int cnt = count_s, nk = 0;
+      const int lim = min(64, n - cb * 64);
+      bool done = false;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        if (j < lim && !done && !((r >> j) & 1ull)) {
+          keep[cnt++] = cb * 64 + j;
+          kept_list[nk++] = j;
+          r |= d[j];
+          if (limit > 0 && cnt >= limit) done = true;
+        }
+      }
+      kept_n = nk;
+      count_s = cnt;
+      if (done) done_s = 1;
+    }
+    __syncthreads();
+    if (done_s) break;
+    const int nk = kept_n;
+    for (int q = warp; q < nk; q += kSweepThreads / 32) {
+      const unsigned long long* row = mask + (size_t)(cb * 64 + kept_list[q]) * nb_stride;
+      for (int w = cb + 1 + lane; w < nb; w += 32) {
+        const unsigned long long v = row[w];
+        if (v) atomicOr(&remv[w], v);
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0) n_keep[img] = count_s;
+}
+
+// --------------------------------------------------------------- proposals --
+__device__ __forceinline__ unsigned int float_to_sortable(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// loc2bbox + clip + min-size filter.  One thread per anchor.
+// key = (sortable(score) << 32 | anchor index) for surviving boxes, 0 otherwise.
+__global__ void __launch_bounds__(256)
+proposal_decode_kernel(const float4* __restrict__ loc, const float* __restrict__ score,
+                       const float4* __restrict__ anchor, int n_anchor, int n_pad,
+                       float img_h, float img_w, float min_size, float4* __restrict__ roi,
+                       unsigned long long* __restrict__ keys, int* __restrict__ n_valid) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_pad) return;
+  unsigned long long key = 0ull;
+  if (k < n_anchor) {
+    const float4 a = __ldg(anchor + k);
+    const float4 l = __ldg(loc + (size_t)img * n_anchor + k);
+    const float h = __fsub_rn(a.z, a.x), w = __fsub_rn(a.w, a.y);
+    const float cy = __fadd_rn(a.x, __fmul_rn(0.5f, h));
+    const float cx = __fadd_rn(a.y, __fmul_rn(0.5f, w));
+    const float ncy = __fadd_rn(__fmul_rn(l.x, h), cy);
+    const float ncx = __fadd_rn(__fmul_rn(l.y, w), cx);
+    // exp evaluated in fp64 and rounded once: the correctly rounded fp32 value.
+    const float nh = __fmul_rn((float)exp((double)l.z), h);
+    const float nw = __fmul_rn((float)exp((double)l.w), w);
+    float y1 = __fsub_rn(ncy, __fmul_rn(0.5f, nh)), x1 = __fsub_rn(ncx, __fmul_rn(0.5f, nw));
+    float y2 = __fadd_rn(ncy, __fmul_rn(0.5f, nh)), x2 = __fadd_rn(ncx, __fmul_rn(0.5f, nw));
+    y1 = fminf(fmaxf(y1, 0.f), img_h);
+    y2 = fminf(fmaxf(y2, 0.f), img_h);
+    x1 = fminf(fmaxf(x1, 0.f), img_w);
+    x2 = fminf(fmaxf(x2, 0.f), img_w);
+    roi[(size_t)img * n_anchor + k] = make_float4(y1, x1, y2, x2);
+    const bool ok = (__fsub_rn(y2, y1) >= min_size) && (__fsub_rn(x2, x1) >= min_size);
+    if (ok) {
+      key = ((unsigned long long)float_to_sortable(__ldg(score + (size_t)img * n_anchor + k))
+             << 32) | (unsigned int)k;
+      atomicAdd(n_valid + img, 1);
+    }
+  }
+  keys[(size_t)img * n_pad + k] = key;
+}
+
+// Descending bitonic sort of n_pad (power of two) 64-bit keys, one CTA per image.
+// Sub-sequences of kSortChunk keys are sorted in shared memory; only the few
+// stages with a partner distance >= kSortChunk touch global (L2-resident) memory.
+constexpr int kSortThreads = 1024;
+constexpr int kSortChunk = 16384;  // 128 KB of 64-bit keys
+
+__device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned long long& b,
+                                              bool desc) {
+  if ((a < b) == desc) {
+    unsigned long long t = a;
+    a = b;
+    b = t;
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+bitonic_sort_desc_kernel(unsigned long long* __restrict__ keys_all, int n_pad) {
+  extern __shared__ unsigned long long sk[];
+  unsigned long long* keys = keys_all + (size_t)blockIdx.x * n_pad;
+  const int t = threadIdx.x;
+  const int chunk = min(n_pad, kSortChunk);
+  // Phase 1: fully sort every chunk in shared memory (alternating directions so
+  // that consecutive chunks form bitonic sequences).
+  for (int base = 0; base < n_pad; base += chunk) {
+    for (int i = t; i < chunk; i += kSortThreads) sk[i] = keys[base + i];
+    __syncthreads();
+    for (int k = 2; k <= chunk; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = t; i < chunk / 2; i += kSortThreads) {
+          const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+          const int hi = lo | j;
+          const bool desc = (((base + lo) & k) == 0);
+          cmp_swap_desc(sk[lo], sk[hi], desc);
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = t; i < chunk; i += kSortThreads) keys[base + i] = sk[i];
+    __syncthreads();
+  }
+  // Phase 2: merge levels above the chunk size.
+  for (int k = chunk << 1; k <= n_pad; k <<= 1) {
+    int j = k >> 1;
+    for (; j >= chunk; j >>= 1) {  // global-memory stages
+      for (int i = t; i < n_pad / 2; i += kSortThreads) {
+        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        const int hi = lo | j;
+        const bool desc = ((lo & k) == 0);
+        unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+    for (int base = 0; base < n_pad; base += chunk) {  // remaining stages in smem
+      for (int i = t; i < chunk; i += kSortThreads) sk[i] = keys[base + i];
+      __syncthreads();
+      for (int jj = chunk >> 1; jj > 0; jj >>= 1) {
+        for (int i = t; i < chunk / 2; i += kSortThreads) {
+          const int lo = ((i & ~(jj - 1)) << 1) | (i & (jj - 1));
+          const int hi = lo | jj;
+          const bool desc = (((base + lo) & k) == 0);
+          cmp_swap_desc(sk[lo], sk[hi], desc);
+        }
+        __syncthreads();
+      }
+      for (int i = t; i < chunk; i += kSortThreads) keys[base + i] = sk[i];
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+proposal_gather_sorted_kernel(const unsigned long long* __restrict__ keys,
+                              const float4* __restrict__ roi, const int* __restrict__ n_valid,
+                              int n_anchor, int n_pad, int n_pre, float4* __restrict__ sorted,
+                              int32_t* __restrict__ sorted_idx, int* __restrict__ n_cand) {
+  const int img = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(n_valid[img], n_pre);
+  if (k == 0) n_cand[img] = n;
+  if (k >= n) return;
+  const int idx = (int)(keys[(size_t)img * n_pad + k] & 0xffffffffull);
+  sorted[(size_t)img * n_pre + k] = roi[(size_t)img * n_anchor + idx];
+  sorted_idx[(size_t)img * n_pre + k] = idx;
+}
+
+__global__ void __launch_bounds__(256)
+proposal_emit_kernel(const float4* __restrict__ sorted, const int32_t* __restrict__ sorted_idx,
+                     const int32_t* __restrict__ keep, const int32_t* __restrict__ n_keep,
+                     int n_pre, int n_post, float4* __restrict__ rois_out,
+                     int32_t* __restrict__ idx_out, int32_t* __restrict__ n_out) {
+  const int img = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(n_keep[img], n_post);
+  if (q == 0) n_out[img] = n;
+  if (q >= n_post) return;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  int idx = -1;
+  if (q < n) {
+    const int s = keep[(size_t)img * n_pre + q];
+    r = sorted[(size_t)img * n_pre + s];
+    idx = sorted_idx[(size_t)img * n_pre + s];
+  }
+  rois_out[(size_t)img * n_post + q] = r;
+  idx_out[(size_t)img * n_post + q] = idx;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int launch_nms(const float4* boxes, const int* n_arr, int n_max, int B, float thresh, int limit,
+               int32_t* keep, int32_t* n_keep, unsigned long long* mask, cudaStream_t st) {
+  const int nb = (n_max + 63) / 64;
+  dim3 grid(nb, nb, B);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(boxes, n_arr, n_max, thresh, mask, nb);
+  CMR_LAUNCH_CHECK();
+  const size_t smem = sizeof(unsigned long long) * nb;
+  nms_sweep_kernel<<<B, kSweepThreads, smem, st>>>(mask, n_arr, n_max, nb, limit, keep, n_keep,
+                                                   n_max);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+}  // namespace
+}  // namespace cmr
+
+using namespace cmr;
+
+extern "C" size_t cmr_nms_workspace_bytes(int n) {
+  if (n <= 0) return 256;
+  const size_t nb = (n + 63) / 64;
+  return align_up(sizeof(unsigned long long) * (size_t)n * nb, 256);
+}
+
+extern "C" int cmr_nms(const float* boxes, int n, float thresh, int limit, int32_t* keep,
+                       int32_t* n_keep, void* workspace, size_t workspace_bytes, void* stream) {
+  CMR_REQUIRE(n >= 0 && n_keep);
+  cudaStream_t st = as_stream(stream);
+  if (n == 0) {
+    CMR_CUDA_TRY(cudaMemsetAsync(n_keep, 0, sizeof(int32_t), st));
+    return CMR_OK;
+  }
+  CMR_REQUIRE(boxes && keep && workspace);
+  CMR_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
+  CMR_REQUIRE(n <= 64 * 2048);  // sweep keeps ceil(n/64) words in shared memory
+  if (workspace_bytes < cmr_nms_workspace_bytes(n)) return CMR_ERR_WORKSPACE;
+  return launch_nms(reinterpret_cast<const float4*>(boxes), nullptr, n, 1, thresh, limit, keep,
+                    n_keep, reinterpret_cast<unsigned long long*>(workspace), st);
+}
+
+namespace {
+struct ProposalWs {
+  size_t roi, keys, n_valid, sorted, sorted_idx, n_cand, keep, n_keep, mask, total;
+  int n_pad;
+};
+ProposalWs proposal_ws(int B, int n_anchor, int n_pre) {
+  ProposalWs w;
+  w.n_pad = next_pow2(n_anchor);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t nb = (n_pre + 63) / 64;
+  w.roi = take(sizeof(float4) * (size_t)B * n_anchor);
+  w.keys = take(sizeof(unsigned long long) * (size_t)B * w.n_pad);
+  w.n_valid = take(sizeof(int) * B);
+  w.sorted = take(sizeof(float4) * (size_t)B * n_pre);
+  w.sorted_idx = take(sizeof(int32_t) * (size_t)B * n_pre);
+  w.n_cand = take(sizeof(int) * B);
+  w.keep = take(sizeof(int32_t) * (size_t)B * n_pre);
+  w.n_keep = take(sizeof(int32_t) * B);
+  w.mask = take(sizeof(unsigned long long) * (size_t)B * n_pre * nb);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t cmr_proposals_workspace_bytes(int B, int n_anchor, int n_pre) {
+  if (B <= 0 || n_anchor <= 0 || n_pre <= 0) return 256;
+  return proposal_ws(B, n_anchor, n_pre).total;
+}
+
+extern "C" int cmr_proposals(const float* loc, const float* score, const float* anchor, int B,
+                             int n_anchor, float img_h, float img_w, float min_size, int n_pre,
+                             int n_post, float nms_thresh, float* rois_out, int32_t* idx_out,
+                             int32_t* n_out, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  CMR_REQUIRE(B > 0 && n_anchor > 0 && n_post > 0);
+  CMR_REQUIRE(loc && score && anchor && rois_out && idx_out && n_out && workspace);
+  if (n_pre <= 0 || n_pre > n_anchor) n_pre = n_anchor;  // "no limit"
+  CMR_REQUIRE(n_pre <= 64 * 2048 && n_anchor <= (1 << 22));
+  const ProposalWs w = proposal_ws(B, n_anchor, n_pre);
+  if (workspace_bytes < w.total) return CMR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  char* ws = reinterpret_cast<char*>(workspace);
+  float4* roi = reinterpret_cast<float4*>(ws + w.roi);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
+  int* n_valid = reinterpret_cast<int*>(ws + w.n_valid);
+  float4* sorted = reinterpret_cast<float4*>(ws + w.sorted);
+  int32_t* sorted_idx = reinterpret_cast<int32_t*>(ws + w.sorted_idx);
+  int* n_cand = reinterpret_cast<int*>(ws + w.n_cand);
+  int32_t* keep = reinterpret_cast<int32_t*>(ws + w.keep);
+  int32_t* n_keep = reinterpret_cast<int32_t*>(ws + w.n_keep);
+  unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + w.mask);
+
+  CMR_CUDA_TRY(cudaMemsetAsync(n_valid, 0, sizeof(int) * B, st));
+  {
+    dim3 grid(ceil_div(w.n_pad, 256), B);
+    proposal_decode_kernel<<<grid, 256, 0, st>>>(
+        reinterpret_cast<const float4*>(loc), score, reinterpret_cast<const float4*>(anchor),
+        n_anchor, w.n_pad, img_h, img_w, min_size, roi, keys, n_valid);
+    CMR_LAUNCH_CHECK();
+  }
+  {
+    const int chunk = w.n_pad < kSortChunk ? w.n_pad : kSortChunk;
+    const size_t smem = sizeof(unsigned long long) * chunk;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CMR_CUDA_TRY(cudaFuncSetAttribute(bitonic_sort_desc_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(unsigned long long) * kSortChunk)));
+      attr_set = true;
+    }
+    bitonic_sort_desc_kernel<<<B, kSortThreads, smem, st>>>(keys, w.n_pad);
+    CMR_LAUNCH_CHECK();
+  }
+  {
+    dim3 grid(ceil_div(n_pre, 256), B);
+    proposal_gather_sorted_kernel<<<grid, 256, 0, st>>>(keys, roi, n_valid, n_anchor, w.n_pad,
+                                                        n_pre, sorted, sorted_idx, n_cand);
+    CMR_LAUNCH_CHECK();
+  }
+  int rc = launch_nms(sorted, n_cand, n_pre, B, nms_thresh, n_post, keep, n_keep, mask, st);
+  if (rc != CMR_OK) return rc;
+  {
+    dim3 grid(ceil_div(n_post, 256), B);
+    proposal_emit_kernel<<<grid, 256, 0, st>>>(sorted, sorted_idx, keep, n_keep, n_pre, n_post,
+                                               reinterpret_cast<float4*>(rois_out), idx_out,
+                                               n_out);
+    CMR_LAUNCH_CHECK();
+  }
+  return CMR_OK;
+}

@@ -1,0 +1,143 @@
+/*
+ * cmr_b200 -- C ABI of the B200-native Mask R-CNN (R50/R101-C4) hot path.
+ *
+ * Plain C entry points: pointers, sizes, a CUDA stream handle, int status.
+ * No torch / C++ types cross this boundary.  All device entry points are
+ * asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ * default stream), re-entrant, and never allocate or free user-visible
+ * memory: the caller owns inputs, outputs and workspaces.
+ *
+ * Every function cites the reference interface (file:line under
+ * wkentaro/chainer-mask-rcnn @ v0.5.24) that it replaces.  INTEGRATION.md
+ * shows the ctypes binding a maintainer of the reference would add.
+ */
+#ifndef CMR_B200_H_
+#define CMR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cmr_status {
+  CMR_OK = 0,
+  CMR_ERR_INVALID_ARG = -1,  /* bad shape / null pointer / unsupported value  */
+  CMR_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed           */
+  CMR_ERR_WORKSPACE = -3,    /* caller's workspace is too small               */
+  CMR_ERR_UNSUPPORTED = -4   /* shape outside what the kernel was built for   */
+} cmr_status;
+
+/* Human-readable text for a status code (static storage). */
+const char* cmr_status_string(int status);
+/* Library ABI version (bumped when a signature changes). */
+int cmr_version(void);
+/* Last CUDA error string recorded by this library on the calling thread. */
+const char* cmr_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------ *
+ * ROIAlign, reference layout (x NCHW fp32, rois (R,5) = b,x1,y1,x2,y2).
+ * Replaces ROIAlign2D.forward_gpu / backward_gpu
+ * (chainer_mask_rcnn/functions/roi_align_2d.py:162-290, 391-524).
+ * y: (R,C,outh,outw).  gx: (N,C,H,W), zero-filled by the callee.
+ * sampling_ratio == 0 selects the adaptive grid ceil(roi/pooled).
+ * ------------------------------------------------------------------------ */
+int cmr_roi_align_fwd(const float* x, int N, int C, int H, int W,
+                      const float* rois, int R, int outh, int outw,
+                      float spatial_scale, int sampling_ratio, float* y,
+                      void* stream);
+int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int N, int C,
+                      int H, int W, int outh, int outw, float spatial_scale,
+                      int sampling_ratio, float* gx, void* stream);
+
+/* Same operator on channels-last tensors, used inside the model
+ * (ResNetRoIHead.__call__, models/mask_rcnn_resnet.py:168-181):
+ * x (N,H,W,C), y (R,outh/bin_stride,outw/bin_stride,C).  Only the bins
+ * (ph, pw) with ph % bin_stride == 0 and pw % bin_stride == 0 are produced:
+ * res5.a's stride-2 1x1 convolutions read no others when roi_size == 14.
+ * C must be a multiple of 4. */
+int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C,
+                           const float* rois, int R, int outh, int outw,
+                           int bin_stride, float spatial_scale,
+                           int sampling_ratio, float* y, void* stream);
+int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N,
+                           int H, int W, int C, int outh, int outw,
+                           int bin_stride, float spatial_scale,
+                           int sampling_ratio, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Greedy NMS on score-sorted boxes (y1,x1,y2,x2), IoU >= thresh suppresses.
+ * Replaces chainercv.utils.non_maximum_suppression as called at
+ * chainer_mask_rcnn/models/mask_rcnn.py:193-194 and inside ProposalCreator
+ * (models/region_proposal_network.py:136-138).
+ * keep: int32[n] (first *n_keep entries valid, ascending = score order);
+ * n_keep: device int32.  limit <= 0 means no limit.  The workspace also
+ * receives the 64-bit suppression bitmask (n x ceil(n/64) words, row i bit j
+ * set iff j > i and IoU(i,j) >= thresh) at offset 0 for the bit-exact test.
+ * ------------------------------------------------------------------------ */
+size_t cmr_nms_workspace_bytes(int n);
+int cmr_nms(const float* boxes, int n, float thresh, int limit, int32_t* keep,
+            int32_t* n_keep, void* workspace, size_t workspace_bytes,
+            void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * RPN proposal generation for a batch of B images: decode (loc2bbox), clip,
+ * min-size filter, descending score sort, top n_pre, NMS, top n_post.
+ * Replaces chainercv ProposalCreator.__call__ as invoked per image at
+ * chainer_mask_rcnn/models/region_proposal_network.py:135-141.
+ * loc (B,n_anchor,4), score (B,n_anchor), anchor (n_anchor,4) fp32.
+ * rois_out (B,n_post,4) fp32, idx_out (B,n_post) int32 = anchor index of each
+ * kept proposal, n_out (B) int32 (device).
+ * ------------------------------------------------------------------------ */
+size_t cmr_proposals_workspace_bytes(int B, int n_anchor, int n_pre);
+int cmr_proposals(const float* loc, const float* score, const float* anchor,
+                  int B, int n_anchor, float img_h, float img_w,
+                  float min_size, int n_pre, int n_post, float nms_thresh,
+                  float* rois_out, int32_t* idx_out, int32_t* n_out,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Implicit-GEMM convolution on the tcgen05 tensor cores (TF32 inputs, fp32
+ * accumulate):  D[m,n] = epilogue(sum_k A[m,k] * W[n,k]).
+ * Replaces the forward / data-gradient of chainer.links.Convolution2D,
+ * Deconvolution2D and Linear as instantiated at
+ * chainer_mask_rcnn/models/region_proposal_network.py:75-80,
+ * models/mask_rcnn_resnet.py:131-143 and inside BuildingBlock
+ * (models/resnet_extractor.py:47-90), with AffineChannel2D
+ * (functions/affine_channel_2d.py:17-20), bias, residual add and ReLU fused.
+ *
+ * a : NHWC activations (batch, in_h, in_w, in_ld) of which in_c channels are
+ *     used (in_c % 32 == 0); rows of the GEMM are output pixels (b, oy, ox),
+ *     oy < out_h, ox < out_w, reading input pixel (oy*stride - pad + fr,
+ *     ox*stride - pad + fs); out-of-image taps read zeros.
+ * w : filter bank (n, kh, kw, in_c) fp32, i.e. K-major.
+ * d : row (b, oy, ox) is written at pixel (oy*d_stride + d_oy, ox*d_stride + d_ox)
+ *     of a (batch, d_h, d_w, d_ld) tensor, channels [0, n).
+ * epilogue, in this order, each optional (NULL / 0 = skip):
+ *     v *= scale[n];  v += bias[n];  v += addend[same address as d];
+ *     v = max(v, 0) if relu;  v = 0 where mask[same address as d] <= 0;
+ *     v = round-to-nearest tf32 if round_tf32.
+ * tile_n: 0 = automatic, else 64 / 128 / 256.
+ * ------------------------------------------------------------------------ */
+typedef struct cmr_conv_desc {
+  int batch, in_h, in_w, in_c, in_ld;
+  int out_h, out_w;
+  int kh, kw, stride, pad;
+  int n;
+  int d_h, d_w, d_ld, d_stride, d_oy, d_ox;
+  int relu, round_tf32;
+  int tile_n;
+} cmr_conv_desc;
+
+int cmr_conv_gemm_tc(const cmr_conv_desc* desc, const float* a, const float* w,
+                     float* d, const float* scale, const float* bias,
+                     const float* addend, const float* mask, void* stream);
+
+/* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
+int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMR_B200_H_ */

@@ -1,0 +1,103 @@
+"""Load the reference's own operator files verbatim (dev container only).
+
+TEST INFRASTRUCTURE.  ``/root/reference`` is read-only and exists only in the
+development container; this loader is used by ``tests/golden/make_golden.py`` to
+produce the committed golden vectors and by CPU tests that re-validate the numpy
+restatement when the reference tree happens to be present.  Nothing on the GPU
+box may call it (it returns ``None`` there).
+
+The reference package cannot be imported as a whole (chainer / chainercv / cupy
+are absent).  ``functions/roi_align_2d.py`` and
+``functions/affine_channel_2d.py`` only need three chainer names on their CPU
+paths, so a stub ``chainer`` package is registered just for the duration of the
+load and the file is executed unmodified from where it lies.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get('CMR_REFERENCE_ROOT', '/root/reference')
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(
+        REFERENCE_ROOT, 'chainer_mask_rcnn', 'functions', 'roi_align_2d.py'))
+
+
+def _stub_chainer():
+    import numpy
+
+    chainer = types.ModuleType('chainer')
+    cuda = types.ModuleType('chainer.cuda')
+    cuda.get_array_module = lambda *a: numpy
+    function = types.ModuleType('chainer.function')
+
+    class Function(object):
+        def retain_inputs(self, indexes):
+            self._retained = indexes
+
+    function.Function = Function
+    functions = types.ModuleType('chainer.functions')
+    utils = types.ModuleType('chainer.utils')
+    type_check = types.ModuleType('chainer.utils.type_check')
+    utils.type_check = type_check
+    chainer.cuda = cuda
+    chainer.function = function
+    chainer.functions = functions
+    chainer.utils = utils
+    chainer.Function = Function
+    return {
+        'chainer': chainer, 'chainer.cuda': cuda, 'chainer.function': function,
+        'chainer.functions': functions, 'chainer.utils': utils,
+        'chainer.utils.type_check': type_check,
+    }
+
+
+def _load(relpath, modname):
+    if not reference_available():
+        return None
+    stubs = _stub_chainer()
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        path = os.path.join(REFERENCE_ROOT, relpath)
+        spec = importlib.util.spec_from_file_location(modname, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def load_roi_align_module():
+    """-> module of chainer_mask_rcnn/functions/roi_align_2d.py, or None."""
+    return _load('chainer_mask_rcnn/functions/roi_align_2d.py', '_ref_roi_align_2d')
+
+
+def load_affine_channel_module():
+    """-> module of chainer_mask_rcnn/functions/affine_channel_2d.py, or None."""
+    return _load('chainer_mask_rcnn/functions/affine_channel_2d.py',
+                 '_ref_affine_channel_2d')
+
+
+def ref_roi_align_forward(x, rois_xy, outh, outw, spatial_scale, sampling_ratio):
+    """Reference ROIAlign2D.forward_cpu (roi_align_2d.py:61-160), run verbatim."""
+    mod = load_roi_align_module()
+    f = mod.ROIAlign2D(outh, outw, spatial_scale, sampling_ratio)
+    y, = f.forward_cpu((x, rois_xy))
+    return y
+
+
+def ref_roi_align_backward(x_shape, rois_xy, gy, outh, outw, spatial_scale,
+                           sampling_ratio):
+    """Reference ROIAlign2D.backward_cpu (roi_align_2d.py:292-389), verbatim."""
+    mod = load_roi_align_module()
+    f = mod.ROIAlign2D(outh, outw, spatial_scale, sampling_ratio)
+    f._bottom_data_shape = tuple(x_shape)
+    gx, _ = f.backward_cpu((None, rois_xy), (gy,))
+    return gx

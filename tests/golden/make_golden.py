@@ -1,0 +1,124 @@
+"""Generate golden vectors by running the reference's own code (dev container only).
+
+Run from the repo root:  python tests/golden/make_golden.py
+
+The reference files are executed verbatim from /root/reference through
+oracle/ref_loader.py (stub ``chainer`` module); nothing is copied.  Outputs are
+small .npz fixtures committed next to this script:
+
+  roi_align_unit.npz    reference unit-test fixture, tests/functions_tests/
+                        test_roi_align_2d.py:20-39 (np.random.seed(0) first; the
+                        reference test is unseeded), sampling_ratio 0, 1, 2
+  roi_align_check.npz   the 8x8 hand-typed map of tests/functions_tests/
+                        check_roi_align_2d.py:24-47, 3 RoIs, 2x2 output
+  roi_align_random.npz  random-normal maps (the unit fixture is a ramp, which
+                        hides sampling-ratio errors): feature-stride-16 boxes,
+                        7x7 and 14x14 outputs, sampling_ratio 0 and 2
+  affine_channel.npz    functions/affine_channel_2d.py forward/backward
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, '..', '..'))
+
+from oracle import ref_loader  # noqa: E402
+
+
+def unit_fixture():
+    np.random.seed(0)
+    N, C = 3, 3
+    x = np.arange(N * C * 12 * 8, dtype=np.float32).reshape((N, C, 12, 8))
+    np.random.shuffle(x)
+    x = 2 * x / x.size - 1
+    rois = np.array([[0, 1, 1, 6, 6], [2, 6, 2, 7, 11], [1, 3, 1, 5, 10],
+                     [0, 3, 3, 3, 3]], dtype=np.float32)
+    outh, outw, scale = 5, 7, 0.6
+    gy = np.random.uniform(-1, 1, (4, C, outh, outw)).astype(np.float32)
+    out = dict(x=x.astype(np.float32), rois=rois, gy=gy, outh=outh, outw=outw,
+               spatial_scale=scale)
+    for ratio in (0, 1, 2):
+        y = ref_loader.ref_roi_align_forward(x, rois, outh, outw, scale, ratio)
+        gx = ref_loader.ref_roi_align_backward(x.shape, rois, gy, outh, outw,
+                                               scale, ratio)
+        out['y_r%d' % ratio] = y
+        out['gx_r%d' % ratio] = gx
+    return out
+
+
+def check_fixture():
+    x = np.array([
+        [0.88, 0.44, 0.14, 0.16, 0.37, 0.77, 0.96, 0.27],
+        [0.19, 0.45, 0.57, 0.16, 0.63, 0.29, 0.71, 0.70],
+        [0.66, 0.26, 0.82, 0.64, 0.54, 0.73, 0.59, 0.26],
+        [0.85, 0.34, 0.76, 0.84, 0.29, 0.75, 0.62, 0.25],
+        [0.32, 0.74, 0.21, 0.39, 0.34, 0.03, 0.33, 0.48],
+        [0.20, 0.14, 0.16, 0.13, 0.73, 0.65, 0.96, 0.32],
+        [0.19, 0.69, 0.09, 0.86, 0.88, 0.07, 0.01, 0.48],
+        [0.83, 0.24, 0.97, 0.04, 0.24, 0.35, 0.50, 0.91],
+    ], dtype=np.float32)[None, None]
+    rois = np.array([[0, 0, 0, 2, 2], [0, 0, 0, 3, 2], [0, 0, 2, 6, 7]],
+                    dtype=np.float32)
+    y = ref_loader.ref_roi_align_forward(x, rois, 2, 2, 1.0, 0)
+    gy = np.ones_like(y)
+    gx = ref_loader.ref_roi_align_backward(x.shape, rois, gy, 2, 2, 1.0, 0)
+    return dict(x=x, rois=rois, y=y, gy=gy, gx=gx)
+
+
+def random_fixture():
+    rs = np.random.RandomState(1234)
+    N, C, H, W = 2, 3, 13, 17
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    img_h, img_w = H * 16, W * 16
+    R = 7
+    hh = np.exp(rs.uniform(np.log(16), np.log(img_h), R))
+    ww = np.exp(rs.uniform(np.log(16), np.log(img_w), R))
+    cy = rs.uniform(0, img_h, R)
+    cx = rs.uniform(0, img_w, R)
+    y1 = np.clip(cy - hh / 2, 0, img_h)
+    y2 = np.clip(cy + hh / 2, 0, img_h)
+    x1 = np.clip(cx - ww / 2, 0, img_w)
+    x2 = np.clip(cx + ww / 2, 0, img_w)
+    b = rs.randint(0, N, R)
+    rois = np.stack([b, x1, y1, x2, y2], axis=1).astype(np.float32)
+    # one RoI covering the whole image (largest adaptive grid, edge clamps)
+    rois[0] = [1, 0, 0, img_w, img_h]
+    out = dict(x=x, rois=rois, spatial_scale=1. / 16)
+    for (oh, ow) in ((7, 7), (14, 14)):
+        gy = rs.standard_normal((R, C, oh, ow)).astype(np.float32)
+        out['gy_%d' % oh] = gy
+        for ratio in (0, 2):
+            y = ref_loader.ref_roi_align_forward(x, rois, oh, ow, 1. / 16, ratio)
+            gx = ref_loader.ref_roi_align_backward(x.shape, rois, gy, oh, ow,
+                                                   1. / 16, ratio)
+            out['y_%d_r%d' % (oh, ratio)] = y
+            out['gx_%d_r%d' % (oh, ratio)] = gx
+    return out
+
+
+def affine_fixture():
+    mod = ref_loader.load_affine_channel_module()
+    rs = np.random.RandomState(7)
+    x = rs.standard_normal((2, 5, 4, 3)).astype(np.float32)
+    W = rs.uniform(0.5, 1.5, (1, 5, 1, 1)).astype(np.float32)
+    b = rs.standard_normal((1, 5, 1, 1)).astype(np.float32)
+    gy = rs.standard_normal(x.shape).astype(np.float32)
+    f = mod.AffineChannel2DFunction()
+    y, = f.forward((x, W, b))
+    gx, gW, gb = f.backward((x, W, b), (gy,))
+    return dict(x=x, W=W, b=b, gy=gy, y=y, gx=gx, gW=gW, gb=gb)
+
+
+def main():
+    assert ref_loader.reference_available(), 'needs /root/reference'
+    np.savez_compressed(os.path.join(HERE, 'roi_align_unit.npz'), **unit_fixture())
+    np.savez_compressed(os.path.join(HERE, 'roi_align_check.npz'), **check_fixture())
+    np.savez_compressed(os.path.join(HERE, 'roi_align_random.npz'), **random_fixture())
+    np.savez_compressed(os.path.join(HERE, 'affine_channel.npz'), **affine_fixture())
+    print('golden vectors written to', HERE)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,50 @@
+"""Seeded synthetic inputs shared by the oracle-vs-CUDA tests and bench.py
+(SURVEY.md 8d).  Pure NumPy; no reference or oracle code."""
+import numpy as np
+
+
+def random_boxes(rs, n, img_h, img_w, lo=16., hi=512.):
+    """(n, 4) float32 (y1, x1, y2, x2): log-uniform sizes, uniform centres, clipped."""
+    h = np.exp(rs.uniform(np.log(lo), np.log(hi), n))
+    w = np.exp(rs.uniform(np.log(lo), np.log(hi), n))
+    cy = rs.uniform(0, img_h, n)
+    cx = rs.uniform(0, img_w, n)
+    b = np.stack([cy - h / 2, cx - w / 2, cy + h / 2, cx + w / 2], axis=1)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, img_h)
+    b[:, 1::2] = np.clip(b[:, 1::2], 0, img_w)
+    return b.astype(np.float32)
+
+
+def clustered_boxes(rs, n, img_h, img_w, n_centers=40):
+    """Boxes jittered around a few objects, so that NMS has real work to do."""
+    centers = random_boxes(rs, n_centers, img_h, img_w, 32., 400.)
+    pick = rs.randint(0, n_centers, n)
+    b = centers[pick].astype(np.float64)
+    size = np.stack([b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]], axis=1)
+    jitter = rs.normal(0, 0.12, (n, 4)) * np.concatenate([size, size], axis=1)
+    b = b + jitter
+    y1 = np.minimum(b[:, 0], b[:, 2]); y2 = np.maximum(b[:, 0], b[:, 2])
+    x1 = np.minimum(b[:, 1], b[:, 3]); x2 = np.maximum(b[:, 1], b[:, 3])
+    b = np.stack([y1, x1, y2, x2], axis=1)
+    b[:, 0::2] = np.clip(b[:, 0::2], 0, img_h)
+    b[:, 1::2] = np.clip(b[:, 1::2], 0, img_w)
+    return b.astype(np.float32)
+
+
+def tie_free_scores(rs, n):
+    """A random permutation of linspace(0, 1, n): no two scores are equal."""
+    return rs.permutation(np.linspace(0, 1, n)).astype(np.float32)
+
+
+def rois_xy(rs, n, n_img, img_h, img_w, lo=16., hi=512.):
+    """(n, 5) float32 rows (batch_index, x1, y1, x2, y2) in image coordinates."""
+    b = random_boxes(rs, n, img_h, img_w, lo, hi)
+    idx = rs.randint(0, n_img, n).astype(np.float32)
+    return np.stack([idx, b[:, 1], b[:, 0], b[:, 3], b[:, 2]], axis=1).astype(np.float32)
+
+
+def rpn_outputs(rs, n_anchor, loc_std=0.3):
+    """loc (n, 4) ~ N(0, loc_std), tie-free scores (n,)."""
+    loc = (rs.standard_normal((n_anchor, 4)) * loc_std).astype(np.float32)
+    score = (tie_free_scores(rs, n_anchor) * 12 - 6).astype(np.float32)
+    return loc, score

@@ -1,0 +1,140 @@
+"""tcgen05 implicit-GEMM convolution vs an fp32 reference of the same op.
+
+Operands are rounded to TF32 first (what the producing layer's epilogue / the
+weight preparation does in the model), so the products are exact in fp32 and the
+only difference left is the accumulation order: tolerance 1e-4 of max|ref|.  A
+second check feeds raw fp32 operands and asserts the north-star bound (<= 1e-3 of
+max|ref|) for the tensor core's own truncation.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from chainer_mask_rcnn_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def round_tf32(t):
+    out = torch.empty_like(t)
+    _lib.call('cmr_round_tf32', _lib.ptr(t), _lib.ptr(out), t.numel(), _lib.stream_ptr())
+    return out
+
+
+def conv_tc(x_nhwc, w_ohwi, stride, pad, scale=None, bias=None, addend=None, mask=None,
+            relu=False, round_out=False, tile_n=0, d_stride=1, d_off=(0, 0), d_hw=None):
+    B, H, W, C = x_nhwc.shape
+    N, kh, kw, _ = w_ohwi.shape
+    oh = (H + 2 * pad - kh) // stride + 1
+    ow = (W + 2 * pad - kw) // stride + 1
+    dh, dw = d_hw if d_hw else (oh, ow)
+    d = torch.zeros((B, dh, dw, N), device='cuda')
+    desc = _lib.ConvDesc(B, H, W, C, C, oh, ow, kh, kw, stride, pad, N, dh, dw, N, d_stride,
+                         d_off[0], d_off[1], int(relu), int(round_out), tile_n)
+    _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _lib.ptr(x_nhwc), _lib.ptr(w_ohwi),
+              _lib.ptr(d), _lib.ptr(scale), _lib.ptr(bias), _lib.ptr(addend), _lib.ptr(mask),
+              _lib.stream_ptr())
+    return d
+
+
+def ref_conv(x_nhwc, w_ohwi, stride, pad):
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).double(), w_ohwi.permute(0, 3, 1, 2).double(),
+                     stride=stride, padding=pad)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    return y.permute(0, 2, 3, 1).float().contiguous()
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+CASES = [
+    # B, H,  W,  C,   N,  k, s, p, tile
+    (1, 8, 16, 32, 64, 1, 1, 0, 64),        # one tile, one k-block
+    (1, 8, 16, 64, 64, 1, 1, 0, 64),        # two k-blocks
+    (2, 13, 17, 128, 128, 1, 1, 0, 128),    # ragged M, ring wraps (4 k-blocks, 3 stages)
+    (2, 13, 17, 256, 256, 1, 1, 0, 256),    # BN = 256
+    (1, 20, 23, 64, 96, 3, 1, 1, 128),      # 3x3 pad 1, N not a tile multiple
+    (2, 21, 19, 64, 128, 1, 2, 0, 128),     # 1x1 stride 2 (res3/res4 'a' blocks)
+    (1, 7, 7, 512, 512, 3, 1, 1, 0),        # res5 3x3, K = 4608, auto tile
+    (3, 14, 14, 1024, 80, 1, 1, 0, 0),      # mask head N = 80
+    (1, 51, 84, 1024, 75, 1, 1, 0, 0),      # RPN loc+score fused, N = 75 (scalar stores)
+]
+
+
+@pytest.mark.parametrize('B,H,W,C,N,k,s,p,tile', CASES)
+def test_conv_matches_fp32_reference(B, H, W, C, N, k, s, p, tile):
+    g = torch.Generator(device='cuda').manual_seed(B * 1000 + H * 10 + C)
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    w = round_tf32(torch.randn((N, k, k, C), device='cuda', generator=g) / (k * C ** 0.5))
+    want = ref_conv(x, w, s, p)
+    got = conv_tc(x, w, s, p, tile_n=tile)
+    assert got.shape == want.shape
+    assert rel(got, want) <= 1e-4
+
+
+def test_fused_epilogue():
+    g = torch.Generator(device='cuda').manual_seed(5)
+    B, H, W, C, N = 2, 9, 11, 64, 128
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    w = round_tf32(torch.randn((N, 3, 3, C), device='cuda', generator=g) / 24)
+    scale = torch.rand((N,), device='cuda', generator=g) + 0.5
+    bias = torch.randn((N,), device='cuda', generator=g)
+    addend = torch.randn((B, H, W, N), device='cuda', generator=g)
+    mask = torch.randn((B, H, W, N), device='cuda', generator=g)
+    base = ref_conv(x, w, 1, 1)
+    # forward epilogue: affine (conv first, then W*x+b as the reference), residual, relu
+    want = torch.relu(base * scale + bias + addend)
+    got = conv_tc(x, w, 1, 1, scale=scale, bias=bias, addend=addend, relu=True)
+    assert rel(got, want) <= 1e-4
+    # backward epilogue: add the other branch's gradient, then the ReLU mask
+    want = (base + addend) * (mask > 0)
+    got = conv_tc(x, w, 1, 1, addend=addend, mask=mask)
+    assert rel(got, want) <= 1e-4
+    # tf32-rounded output is idempotent under rounding
+    got = conv_tc(x, w, 1, 1, round_out=True)
+    assert torch.equal(got, round_tf32(got))
+    assert rel(got, base) <= 1e-3
+
+
+def test_strided_scatter_output():
+    """Deconvolution2D(2, stride 2) = four 1x1 GEMMs written with a pixel-shuffle store
+    (d_stride 2, offsets (dy, dx)); also the data gradient of a stride-2 1x1 conv."""
+    g = torch.Generator(device='cuda').manual_seed(6)
+    B, H, W, C, N = 2, 7, 7, 64, 64
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    wt = round_tf32(torch.randn((C, N, 2, 2), device='cuda', generator=g) / 8)   # (in, out, kh, kw)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), stride=2)
+    want = want.permute(0, 2, 3, 1).float()
+    out = torch.zeros((B, 2 * H, 2 * W, N), device='cuda')
+    for dy in range(2):
+        for dx in range(2):
+            w_tap = wt[:, :, dy, dx].t().contiguous().view(N, 1, 1, C)
+            desc = _lib.ConvDesc(B, H, W, C, C, H, W, 1, 1, 1, 0, N, 2 * H, 2 * W, N, 2, dy, dx,
+                                 0, 0, 0)
+            _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w_tap),
+                      _lib.ptr(out), None, None, None, None, _lib.stream_ptr())
+    assert rel(out, want) <= 1e-4
+
+
+def test_raw_fp32_operands_meet_north_star_bound():
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn((2, 25, 42, 256), device='cuda', generator=g)
+    w = torch.randn((256, 3, 3, 256), device='cuda', generator=g) / 48
+    want = ref_conv(x, w, 1, 1)
+    got = conv_tc(round_tf32(x), round_tf32(w), 1, 1)
+    assert rel(got, want) <= 1e-3
+
+
+def test_unsupported_channels_is_an_error_not_a_fallback():
+    x = torch.zeros((1, 4, 4, 3), device='cuda')
+    w = torch.zeros((8, 1, 1, 3), device='cuda')
+    with pytest.raises(_lib.CmrError):
+        conv_tc(x, w, 1, 0)

@@ -1,0 +1,151 @@
+"""ROIAlign CUDA kernels vs the oracle (reference-pinned) -- runs on the B200.
+
+Tolerance: north_star asks for <= 1e-3 relative fp32; the kernels follow the
+reference's fp32 operation order, so the tests hold them to 1e-5 of max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from chainer_mask_rcnn_b200 import _lib, functions
+from oracle import roi_align as ora
+
+pytestmark = pytest.mark.gpu
+REL = 1e-5
+
+
+def _rel(got, want):
+    return np.abs(got - want).max() / max(np.abs(want).max(), 1e-30)
+
+
+@pytest.mark.parametrize('ratio', [0, 1, 2])
+def test_reference_unit_fixture(golden_dir, ratio):
+    g = np.load(os.path.join(golden_dir, 'roi_align_unit.npz'))
+    oh, ow, sc = int(g['outh']), int(g['outw']), float(g['spatial_scale'])
+    y = functions.roi_align_2d(g['x'], g['rois'], oh, ow, sc, sampling_ratio=ratio)
+    assert isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == g['gy'].shape
+    assert _rel(y, g['y_r%d' % ratio]) <= REL
+    f = functions.ROIAlign2D(oh, ow, sc, ratio)
+    f.forward_gpu((g['x'], g['rois']))
+    gx, none = f.backward_gpu((g['x'], g['rois']), (g['gy'],))
+    assert none is None
+    assert _rel(gx, g['gx_r%d' % ratio]) <= REL
+
+
+def test_reference_check_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'roi_align_check.npz'))
+    y = functions.roi_align_2d(g['x'], g['rois'], 2, 2, 1.0)
+    assert _rel(y, g['y']) <= REL
+
+
+@pytest.mark.parametrize('oh', [7, 14])
+@pytest.mark.parametrize('ratio', [0, 2])
+def test_reference_random_fixture(golden_dir, oh, ratio):
+    g = np.load(os.path.join(golden_dir, 'roi_align_random.npz'))
+    y = functions.roi_align_2d(g['x'], g['rois'], oh, oh, 1. / 16, sampling_ratio=ratio)
+    assert _rel(y, g['y_%d_r%d' % (oh, ratio)]) <= REL
+    x = torch.from_numpy(g['x']).cuda().requires_grad_(True)
+    out = functions.roi_align_2d(x, torch.from_numpy(g['rois']).cuda(), oh, oh, 1. / 16,
+                                 sampling_ratio=ratio)
+    out.backward(torch.from_numpy(g['gy_%d' % oh]).cuda())
+    assert _rel(x.grad.cpu().numpy(), g['gx_%d_r%d' % (oh, ratio)]) <= REL
+
+
+def test_axes_yx_and_empty():
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((2, 5, 9, 11)).astype(np.float32)
+    rois = synth.rois_xy(rs, 6, 2, 9 * 16, 11 * 16)
+    a = functions.roi_align_2d(x, rois, 7, 7, 1. / 16, axes='xy')
+    b = functions.roi_align_2d(x, rois[:, [0, 2, 1, 4, 3]], 7, 7, 1. / 16, axes='yx')
+    np.testing.assert_array_equal(a, b)
+    e = functions.roi_align_2d(x, rois[:0], 7, 7, 1. / 16)
+    assert e.shape == (0, 5, 7, 7)
+
+
+def test_type_errors_like_reference():
+    x = np.zeros((1, 2, 4, 4), np.float64)
+    r = np.zeros((1, 5), np.float32)
+    with pytest.raises(TypeError):
+        functions.roi_align_2d(x, r, 2, 2, 1.0)
+    with pytest.raises(TypeError):
+        functions.roi_align_2d(x.astype(np.float32), np.zeros((1, 4), np.float32), 2, 2, 1.0)
+
+
+@pytest.mark.parametrize('oh,ratio,C', [(14, 0, 19), (7, 0, 8), (7, 2, 33), (5, 3, 4)])
+def test_oracle_random_shapes(oh, ratio, C):
+    """Ragged channel counts (not a multiple of the per-CTA chunk), several images,
+    degenerate (zero-area) and whole-image RoIs."""
+    rs = np.random.RandomState(oh * 10 + ratio)
+    N, H, W = 3, 20, 27
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = synth.rois_xy(rs, 24, N, H * 16, W * 16)
+    rois[0] = [0, 0, 0, W * 16, H * 16]
+    rois[1] = [2, 40, 50, 40, 50]
+    want = ora.roi_align_forward(x, rois, oh, oh, 1. / 16, ratio)
+    got = functions.roi_align_2d(x, rois, oh, oh, 1. / 16, sampling_ratio=ratio)
+    assert _rel(got, want) <= REL
+    gy = rs.standard_normal(want.shape).astype(np.float32)
+    want_gx = ora.roi_align_backward(x.shape, rois, gy, oh, oh, 1. / 16, ratio)
+    f = functions.ROIAlign2D(oh, oh, 1. / 16, ratio)
+    f.forward_gpu((x, rois))
+    got_gx, _ = f.backward_gpu((x, rois), (gy,))
+    assert _rel(got_gx, want_gx) <= REL
+
+
+def _nhwc(x, rois, outh, outw, stride, ratio, gy=None):
+    N, C, H, W = x.shape
+    xt = torch.from_numpy(x).cuda().permute(0, 2, 3, 1).contiguous()
+    rt = torch.from_numpy(rois).cuda()
+    R = rois.shape[0]
+    ohs, ows = -(-outh // stride), -(-outw // stride)
+    y = torch.empty((R, ohs, ows, C), device='cuda')
+    _lib.call('cmr_roi_align_nhwc_fwd', _lib.ptr(xt), N, H, W, C, _lib.ptr(rt), R, outh, outw,
+              stride, 1. / 16, ratio, _lib.ptr(y), _lib.stream_ptr())
+    gx = None
+    if gy is not None:
+        g = torch.from_numpy(gy).cuda().permute(0, 2, 3, 1).contiguous()
+        gx = torch.empty((N, H, W, C), device='cuda')
+        _lib.call('cmr_roi_align_nhwc_bwd', _lib.ptr(g), _lib.ptr(rt), R, N, H, W, C, outh, outw,
+                  stride, 1. / 16, ratio, _lib.ptr(gx), _lib.stream_ptr())
+        gx = gx.permute(0, 3, 1, 2).cpu().numpy()
+    return y.permute(0, 3, 1, 2).cpu().numpy(), gx
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+@pytest.mark.parametrize('ratio', [0, 2])
+def test_nhwc_variant_and_bin_stride(stride, ratio):
+    rs = np.random.RandomState(7 + stride)
+    N, C, H, W = 2, 64, 13, 17
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = synth.rois_xy(rs, 9, N, H * 16, W * 16)
+    full = ora.roi_align_forward(x, rois, 14, 14, 1. / 16, ratio)
+    want = full[:, :, ::stride, ::stride]
+    gy = rs.standard_normal(want.shape).astype(np.float32)
+    gy_full = np.zeros_like(full)
+    gy_full[:, :, ::stride, ::stride] = gy
+    want_gx = ora.roi_align_backward(x.shape, rois, gy_full, 14, 14, 1. / 16, ratio)
+    got, got_gx = _nhwc(x, rois, 14, 14, stride, ratio, gy)
+    assert _rel(got, want) <= REL
+    assert _rel(got_gx, want_gx) <= REL
+
+
+def test_full_size_against_torchvision_cpu():
+    """BASELINE config 5 shape (1024 x 50 x 68 map, 14 x 14 bins), 300 RoIs, against
+    torchvision's CPU roi_align(aligned=False), which agrees with the reference code
+    to 1.2e-7 and finishes in seconds where the reference loop needs
+    minutes.  Also checks gradient mass conservation at this size."""
+    import torchvision
+    rs = np.random.RandomState(5)
+    x = rs.standard_normal((1, 1024, 50, 68)).astype(np.float32)
+    rois = synth.rois_xy(rs, 300, 1, 800, 1088)
+    want = torchvision.ops.roi_align(torch.from_numpy(x), torch.from_numpy(rois), (14, 14),
+                                     1. / 16, 0, False).numpy()
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    y = functions.roi_align_2d(xt, torch.from_numpy(rois).cuda(), 14, 14, 1. / 16)
+    assert _rel(y.detach().cpu().numpy(), want) <= REL
+    y.backward(torch.ones_like(y))
+    total = float(xt.grad.double().sum())
+    assert abs(total - y.numel()) / y.numel() < 1e-5
