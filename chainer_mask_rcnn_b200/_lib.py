@@ -38,6 +38,7 @@ _SIGNATURES = {
                               c_void_p, c_size_t, c_void_p]),
     'cmr_conv_gemm_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
+    'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
@@ -48,6 +49,14 @@ class ConvDesc(ctypes.Structure):
         'batch', 'in_h', 'in_w', 'in_c', 'in_ld', 'out_h', 'out_w', 'kh', 'kw', 'stride',
         'pad', 'n', 'd_h', 'd_w', 'd_ld', 'd_stride', 'd_oy', 'd_ox', 'relu', 'round_tf32',
         'tile_n')]
+
+
+class WgradDesc(ctypes.Structure):
+    """struct cmr_wgrad_desc (include/cmr_b200.h)."""
+    _fields_ = [(n, c_int) for n in (
+        'batch', 'loop_h', 'loop_w', 'gy_h', 'gy_w', 'gy_ld', 'gy_stride', 'gy_off_y',
+        'gy_off_x', 'gy_c0', 'x_h', 'x_w', 'x_ld', 'x_stride', 'x_off_y', 'x_off_x', 'x_c0',
+        'rows', 'cols', 'gw_ld', 'gw_col0', 'splits')]
 
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

@@ -1,0 +1,288 @@
+// Weight gradient of Convolution2D / Deconvolution2D / Linear on tcgen05 (sm_100a).
+//
+//   gW[i, j] += row_scale[i] * sum_pix  P[map_p(pix), p_c0 + i] * Q[map_q(pix), q_c0 + j]
+//
+// a "pixel-reduction GEMM": the reduction runs over output pixels (b, oy, ox), P is
+// the upstream gradient gy (rows i = output channels), Q the layer input x at one
+// filter tap (columns j = input channels).  Both operands are therefore MN-major
+// for the tensor core (the contiguous axis is the channel axis, not the reduction
+// axis): tiles are staged as [pixel][32 channels = 128 B] rows in 128B-swizzled
+// shared memory and read with MN-major UMMA descriptors (TF32 supports them).
+// Each operand has its own pixel map (stride, offset), which covers stride-2 convs
+// (x sampled at 2*oy - pad + fr), zero padding (out-of-image -> zeros) and the
+// 2x2 stride-2 deconvolution (gy sampled at 2*y + dy).
+//
+// This replaces the gW computation of chainer's Convolution2DGradW /
+// Deconvolution2D / Linear backward for the links built at
+// models/region_proposal_network.py:75-80 and models/mask_rcnn_resnet.py:131-143.
+//
+// CTA = 288 threads: warps 0-3 gather P, warps 4-7 gather Q (cp.async 16 B, one
+// k-block = 32 pixels), warp 8 issues tcgen05.mma (128 x BN x 8).  grid =
+// (row tiles, column tiles, K splits); partial sums are added with vector
+// red.global.add (gW must be zeroed by the caller once per step).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cmr {
+namespace {
+
+using namespace tc;
+
+struct PixelMap {
+  const float* base;
+  int h, w, ld;      // tensor (batch, h, w, ld)
+  int stride, off_y, off_x;
+  int c0;            // first channel of this operand's tile range
+};
+
+struct WgradParams {
+  PixelMap p, q;
+  int loop_h, loop_w;  // pixel loop space (batch, loop_h, loop_w)
+  int M;               // number of pixels
+  int rows, cols;      // gW tile space: rows = output channels, cols = channels of one tap
+  float* gw;
+  int gw_ld;           // floats between consecutive rows of gW
+  int gw_col0;         // column offset of this tap inside a gW row
+  const float* row_scale;
+  int kb_per_split, num_kb;
+};
+
+constexpr int kBM = 128;
+constexpr int kPix = 32;  // pixels per k-block
+constexpr int kThreads = 288;
+
+template <int BN, int STAGES>
+struct WSmem {
+  static constexpr int kPBytes = kPix * kBM * 4;  // 16 KB
+  static constexpr int kQBytes = kPix * BN * 4;
+  static constexpr int kPOff = 0;
+  static constexpr int kQOff = STAGES * kPBytes;
+  static constexpr int kBarOff = kQOff + STAGES * kQBytes;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+// Gathers one k-block (32 pixels) x (NBLK * 32 channels) of an operand.
+// Lane layout per cp.async: 4 pixel rows x 128 B, i.e. 512 contiguous smem bytes.
+template <int NBLK>
+__device__ __forceinline__ void gather_tile(const PixelMap& pm, int pix0, int M, int loop_h,
+                                            int loop_w, int chan_limit, uint32_t stage_addr,
+                                            int t /* 0..127 */) {
+  const int jj = t & 7;
+  const int rsub = (t >> 3) & 3;
+  const int w = t >> 5;
+  const int lhw = loop_h * loop_w;
+  // A thread owns two pixel rows (decoded once each) x all NBLK channel blocks.
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = (2 * w + rr) * 4 + rsub;
+    const int pix = pix0 + row;
+    bool ok = pix < M;
+    const float* src_row = pm.base;
+    if (ok) {
+      const int img = pix / lhw;
+      const int rem = pix - img * lhw;
+      const int oy = rem / loop_w;
+      const int ox = rem - oy * loop_w;
+      const int y = oy * pm.stride + pm.off_y, x = ox * pm.stride + pm.off_x;
+      ok = (unsigned)y < (unsigned)pm.h && (unsigned)x < (unsigned)pm.w;
+      if (ok) src_row = pm.base + ((size_t)(img * pm.h + y) * pm.w + x) * pm.ld;
+    }
+    const uint32_t dst_row = stage_addr + row * 128 + ((jj ^ (row & 7)) << 4);
+#pragma unroll
+    for (int cblk = 0; cblk < NBLK; ++cblk) {
+      const int ch = pm.c0 + cblk * 32 + jj * 4;
+      const bool okc = ok && ch < chan_limit;
+      cp_async_16(dst_row + cblk * (kPix * 128), okc ? src_row + ch : pm.base, okc ? 16u : 0u);
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+conv_wgrad_tc_kernel(const WgradParams p) {
+  using L = WSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * kBM;
+  const int j0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction of the grid
+
+  if (warp == 8 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 256);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 7) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ---------------------------------------------------------- producers
+    const bool is_p = warp < 4;
+    const int t = threadIdx.x & 127;
+    PixelMap pm = is_p ? p.p : p.q;
+    pm.c0 += is_p ? i0 : j0;
+    const int chan_limit = (is_p ? p.p.c0 + p.rows : p.q.c0 + p.cols);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t phase = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], phase ^ 1);
+      const int pix0 = (kb_begin + kb) * kPix;
+      if (is_p)
+        gather_tile<kBM / 32>(pm, pix0, p.M, p.loop_h, p.loop_w, chan_limit,
+                              smem_base + L::kPOff + s * L::kPBytes, t);
+      else
+        gather_tile<BN / 32>(pm, pix0, p.M, p.loop_h, p.loop_w, chan_limit,
+                             smem_base + L::kQOff + s * L::kQBytes, t);
+      cp_async_mbar_arrive_noinc(&full_bar[s]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+
+    if (warp < 4) {
+      // -------------------------------------------------------- epilogue
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int row = i0 + warp * 32 + lane;
+      const bool row_ok = row < p.rows;
+      const float sc = (row_ok && p.row_scale) ? __ldg(p.row_scale + row) : 1.0f;
+      float* out_row = p.gw + (size_t)row * p.gw_ld + p.gw_col0;
+      const bool vec_ok = ((p.gw_ld & 3) == 0) && ((p.gw_col0 & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.gw) & 15) == 0);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        const int jc = j0 + chunk * 32;
+        if (jc >= p.cols) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(chunk * 32), v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int j = jc + g * 4;
+          if (j >= p.cols) break;
+          if (vec_ok && j + 3 < p.cols) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_row + j),
+                         "f"(__uint_as_float(v[g * 4 + 0]) * sc),
+                         "f"(__uint_as_float(v[g * 4 + 1]) * sc),
+                         "f"(__uint_as_float(v[g * 4 + 2]) * sc),
+                         "f"(__uint_as_float(v[g * 4 + 3]) * sc)
+                         : "memory");
+          } else {
+            for (int e = 0; e < 4 && j + e < p.cols; ++e)
+              atomicAdd(out_row + j + e, __uint_as_float(v[g * 4 + e]) * sc);
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 1, 1);  // both operands MN-major
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t phase = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
+        const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
+#pragma unroll
+        for (int k = 0; k < kPix / 8; ++k) {
+          // 8 pixels = one 1024 B swizzle atom per 32-channel block; blocks are
+          // kPix * 128 bytes apart (leading byte offset).
+          const uint64_t da = make_smem_desc_sw128(pa + k * 1024, kPix * 128, 1024);
+          const uint64_t db = make_smem_desc_sw128(qa + k * 1024, kPix * 128, 1024);
+          umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(tmem_full_bar);
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 7) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+template <int BN, int STAGES>
+int launch_wgrad(const WgradParams& p, int splits, cudaStream_t st) {
+  using L = WSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, STAGES>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      L::kDynamic));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits);
+  conv_wgrad_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(p);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+}  // namespace
+}  // namespace cmr
+
+using namespace cmr;
+
+extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const float* x,
+                                 float* gw, const float* row_scale, void* stream) {
+  CMR_REQUIRE(c && gy && x && gw);
+  CMR_REQUIRE(c->batch > 0 && c->loop_h > 0 && c->loop_w > 0 && c->rows > 0 && c->cols > 0);
+  CMR_REQUIRE(c->gy_h > 0 && c->gy_w > 0 && c->x_h > 0 && c->x_w > 0);
+  CMR_REQUIRE(c->gy_stride >= 1 && c->x_stride >= 1);
+  if (c->cols % 4 != 0 || c->x_ld % 4 != 0 || c->gy_ld % 4 != 0 || c->x_c0 % 4 != 0 ||
+      c->gy_c0 % 4 != 0)
+    return CMR_ERR_UNSUPPORTED;
+  CMR_REQUIRE(((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0);
+  const long long M = (long long)c->batch * c->loop_h * c->loop_w;
+  CMR_REQUIRE(M < (1ll << 31));
+  CMR_REQUIRE((long long)c->batch * c->gy_h * c->gy_w < (1ll << 31));
+  CMR_REQUIRE((long long)c->batch * c->x_h * c->x_w < (1ll << 31));
+  WgradParams p;
+  p.p.base = gy; p.p.h = c->gy_h; p.p.w = c->gy_w; p.p.ld = c->gy_ld;
+  p.p.stride = c->gy_stride; p.p.off_y = c->gy_off_y; p.p.off_x = c->gy_off_x; p.p.c0 = c->gy_c0;
+  p.q.base = x; p.q.h = c->x_h; p.q.w = c->x_w; p.q.ld = c->x_ld;
+  p.q.stride = c->x_stride; p.q.off_y = c->x_off_y; p.q.off_x = c->x_off_x; p.q.c0 = c->x_c0;
+  p.loop_h = c->loop_h; p.loop_w = c->loop_w; p.M = (int)M;
+  p.rows = c->rows; p.cols = c->cols;
+  p.gw = gw; p.gw_ld = c->gw_ld; p.gw_col0 = c->gw_col0;
+  p.row_scale = row_scale;
+  p.num_kb = ceil_div(p.M, kPix);
+  // Split the pixel reduction so that the grid fills the machine (~2 CTAs per SM).
+  const int bn = c->cols > 64 ? 128 : 64;
+  const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn);
+  int splits = c->splits;
+  if (splits <= 0) {
+    splits = ceil_div(2 * sm_count(), tiles);
+    const int max_splits = ceil_div(p.num_kb, 8);  // at least 8 k-blocks per CTA
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = ceil_div(p.num_kb, splits);
+  splits = ceil_div(p.num_kb, p.kb_per_split);
+  cudaStream_t st = as_stream(stream);
+  if (bn == 128) return launch_wgrad<128, 3>(p, splits, st);
+  return launch_wgrad<64, 4>(p, splits, st);
+}

@@ -76,6 +76,64 @@ __device__ __forceinline__ AxisTap axis_tap(float start, float bin, int p, int i
   return t;
 }
 
+// Per-(bin, sample) taps of one axis, packed {low offset, high offset, l, h}; a
+// negative low offset marks a skipped sample.  The geometry of a RoI is
+// CTA-uniform, so it is computed once per CTA into shared memory whenever
+// pooled * grid <= kMaxTaps on both axes (always, for RoIs clipped to the image);
+// otherwise threads compute their taps on the fly (same arithmetic).
+constexpr int kMaxTaps = 512;
+
+struct TapTables {
+  float4 y[kMaxTaps];
+  float4 x[kMaxTaps];
+};
+
+__device__ __forceinline__ float4 packed_tap(float start, float bin, int p, int i, int grid,
+                                             int limit, int mul) {
+  const AxisTap t = axis_tap(start, bin, p, i, grid, limit);
+  return make_float4(__int_as_float(t.valid ? t.low * mul : -1), __int_as_float(t.high * mul),
+                     t.l, t.h);
+}
+
+struct TapSource {
+  const TapTables* tt;
+  RoiGeom g;
+  int H, W, y_mul, x_mul;
+  bool tabled;
+  __device__ __forceinline__ float4 y(int ph, int iy) const {
+    return tabled ? tt->y[ph * g.grid_h + iy]
+                  : packed_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, y_mul);
+  }
+  __device__ __forceinline__ float4 x(int pw, int ix) const {
+    return tabled ? tt->x[pw * g.grid_w + ix]
+                  : packed_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, x_mul);
+  }
+};
+
+__device__ __forceinline__ TapSource make_taps(TapTables& tt, const RoiGeom& g, int outh,
+                                               int outw, int H, int W, int y_mul, int x_mul) {
+  TapSource ts;
+  ts.tt = &tt;
+  ts.g = g;
+  ts.H = H;
+  ts.W = W;
+  ts.y_mul = y_mul;
+  ts.x_mul = x_mul;
+  ts.tabled = (long long)outh * g.grid_h <= kMaxTaps && (long long)outw * g.grid_w <= kMaxTaps;
+  if (ts.tabled) {
+    for (int e = threadIdx.x; e < outh * g.grid_h; e += blockDim.x) {
+      const int ph = e / g.grid_h;
+      tt.y[e] = packed_tap(g.start_h, g.bin_h, ph, e - ph * g.grid_h, g.grid_h, H, y_mul);
+    }
+    for (int e = threadIdx.x; e < outw * g.grid_w; e += blockDim.x) {
+      const int pw = e / g.grid_w;
+      tt.x[e] = packed_tap(g.start_w, g.bin_w, pw, e - pw * g.grid_w, g.grid_w, W, x_mul);
+    }
+  }
+  __syncthreads();
+  return ts;
+}
+
 // ------------------------------------------------------------------ NCHW --
 constexpr int kChanPerCta = 8;
 
@@ -84,14 +142,21 @@ __global__ void __launch_bounds__(256)
 roi_align_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ rois,
                           float* __restrict__ y, int C, int H, int W, int outh, int outw,
                           float scale, int sampling_ratio, int chunks_per_roi) {
+  __shared__ TapTables tt;
   const int r = blockIdx.x / chunks_per_roi;
   const int c0 = (blockIdx.x - r * chunks_per_roi) * CB;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
+  const TapSource taps = make_taps(tt, g, outh, outw, H, W, W, 1);
   const int P = outh * outw;
   const size_t HW = (size_t)H * W;
   const float* __restrict__ plane0 = x + ((size_t)g.batch * C + c0) * HW;
   float* __restrict__ out0 = y + ((size_t)r * C + c0) * P;
   const int nch = min(CB, C - c0);
+  // count is a power of two in the common cases (1, 2, 4, 16): multiplying by the
+  // exact reciprocal is then bit-identical to the reference's division.
+  const int cnt = g.grid_h * g.grid_w;
+  const bool exact_inv = (cnt & (cnt - 1)) == 0;
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
 
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const int ph = p / outw;
@@ -100,13 +165,15 @@ roi_align_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
     for (int k = 0; k < CB; ++k) acc[k] = 0.f;
     for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+      const float4 ty = taps.y(ph, iy);
+      const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
+      if (yl < 0) continue;
       for (int ix = 0; ix < g.grid_w; ++ix) {
-        const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
-        if (!(ty.valid && tx.valid)) continue;
-        const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
-        const int o1 = ty.low * W + tx.low, o2 = ty.low * W + tx.high;
-        const int o3 = ty.high * W + tx.low, o4 = ty.high * W + tx.high;
+        const float4 tx = taps.x(pw, ix);
+        const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+        if (xl < 0) continue;
+        const float w1 = ty.w * tx.w, w2 = ty.w * tx.z, w3 = ty.z * tx.w, w4 = ty.z * tx.z;
+        const int o1 = yl + xl, o2 = yl + xh, o3 = yh + xl, o4 = yh + xh;
         if (nch == CB) {
           float v1[CB], v2[CB], v3[CB], v4[CB];
 #pragma unroll
@@ -131,7 +198,8 @@ roi_align_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__
     }
 #pragma unroll
     for (int k = 0; k < CB; ++k)
-      if (k < nch) out0[(size_t)k * P + p] = __fdiv_rn(acc[k], g.inv_count_den);
+      if (k < nch)
+        out0[(size_t)k * P + p] = exact_inv ? acc[k] * inv : __fdiv_rn(acc[k], g.inv_count_den);
   }
 }
 
@@ -140,14 +208,17 @@ __global__ void __launch_bounds__(256)
 roi_align_nchw_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                           float* __restrict__ gx, int C, int H, int W, int outh, int outw,
                           float scale, int sampling_ratio, int chunks_per_roi) {
+  __shared__ TapTables tt;
   const int r = blockIdx.x / chunks_per_roi;
   const int c0 = (blockIdx.x - r * chunks_per_roi) * CB;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
+  const TapSource taps = make_taps(tt, g, outh, outw, H, W, W, 1);
   const int P = outh * outw;
   const size_t HW = (size_t)H * W;
   float* __restrict__ plane0 = gx + ((size_t)g.batch * C + c0) * HW;
   const float* __restrict__ in0 = gy + ((size_t)r * C + c0) * P;
   const int nch = min(CB, C - c0);
+  const float d = g.inv_count_den;
 
   for (int p = threadIdx.x; p < P; p += blockDim.x) {
     const int ph = p / outw;
@@ -156,22 +227,24 @@ roi_align_nchw_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < CB; ++k) gval[k] = (k < nch) ? __ldg(in0 + (size_t)k * P + p) : 0.f;
     for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+      const float4 ty = taps.y(ph, iy);
+      const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
+      if (yl < 0) continue;
       for (int ix = 0; ix < g.grid_w; ++ix) {
-        const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
-        if (!(ty.valid && tx.valid)) continue;
-        const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
-        const int o1 = ty.low * W + tx.low, o2 = ty.low * W + tx.high;
-        const int o3 = ty.high * W + tx.low, o4 = ty.high * W + tx.high;
+        const float4 tx = taps.x(pw, ix);
+        const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+        if (xl < 0) continue;
+        const float w1 = ty.w * tx.w, w2 = ty.w * tx.z, w3 = ty.z * tx.w, w4 = ty.z * tx.z;
+        const int o1 = yl + xl, o2 = yl + xh, o3 = yh + xl, o4 = yh + xh;
 #pragma unroll
         for (int k = 0; k < CB; ++k) {
           if (k < nch) {
             float* pl = plane0 + (size_t)k * HW;
             // g_k = top_diff * w_k / count  (roi_align_2d.py:501-504)
-            atomicAdd(pl + o1, __fdiv_rn(gval[k] * w1, g.inv_count_den));
-            atomicAdd(pl + o2, __fdiv_rn(gval[k] * w2, g.inv_count_den));
-            atomicAdd(pl + o3, __fdiv_rn(gval[k] * w3, g.inv_count_den));
-            atomicAdd(pl + o4, __fdiv_rn(gval[k] * w4, g.inv_count_den));
+            atomicAdd(pl + o1, __fdiv_rn(gval[k] * w1, d));
+            atomicAdd(pl + o2, __fdiv_rn(gval[k] * w2, d));
+            atomicAdd(pl + o3, __fdiv_rn(gval[k] * w3, d));
+            atomicAdd(pl + o4, __fdiv_rn(gval[k] * w4, d));
           }
         }
       }
@@ -180,45 +253,6 @@ roi_align_nchw_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ NHWC --
-// grid = (R * oh_s * ow_s), block = C/4 threads (<= 1024) looping if C/4 larger.
-__global__ void __launch_bounds__(256)
-roi_align_nhwc_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ rois,
-                          float4* __restrict__ y, int H, int W, int C4, int outh, int outw,
-                          int bin_stride, int oh_s, int ow_s, float scale,
-                          int sampling_ratio) {
-  const int P = oh_s * ow_s;
-  const int r = blockIdx.x / P;
-  const int p = blockIdx.x - r * P;
-  const int ph = (p / ow_s) * bin_stride;
-  const int pw = (p % ow_s) * bin_stride;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
-  const float4* __restrict__ img = x + (size_t)g.batch * H * W * C4;
-  float4* __restrict__ out = y + (size_t)blockIdx.x * C4;
-
-  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
-      for (int ix = 0; ix < g.grid_w; ++ix) {
-        const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
-        if (!(ty.valid && tx.valid)) continue;
-        const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
-        const float4 v1 = __ldg(img + (size_t)(ty.low * W + tx.low) * C4 + c);
-        const float4 v2 = __ldg(img + (size_t)(ty.low * W + tx.high) * C4 + c);
-        const float4 v3 = __ldg(img + (size_t)(ty.high * W + tx.low) * C4 + c);
-        const float4 v4 = __ldg(img + (size_t)(ty.high * W + tx.high) * C4 + c);
-        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-        acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-        acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-      }
-    }
-    const float d = g.inv_count_den;
-    out[c] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d),
-                         __fdiv_rn(acc.w, d));
-  }
-}
-
 __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
   // sm_90+: 128-bit vector reduction to global memory.
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x),
@@ -226,38 +260,60 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
                : "memory");
 }
 
+// One CTA per (RoI, produced output row); lanes over channels as float4.
+// forward: src = x (N,H,W,C), dst = y;   backward: src = gy, dst = gx.
+template <bool kBackward>
 __global__ void __launch_bounds__(256)
-roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict__ rois,
-                          float4* __restrict__ gx, int H, int W, int C4, int outh, int outw,
-                          int bin_stride, int oh_s, int ow_s, float scale,
-                          int sampling_ratio) {
-  const int P = oh_s * ow_s;
-  const int r = blockIdx.x / P;
-  const int p = blockIdx.x - r * P;
-  const int ph = (p / ow_s) * bin_stride;
-  const int pw = (p % ow_s) * bin_stride;
+roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
+                      float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
+                      int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio) {
+  __shared__ TapTables tt;
+  const int r = blockIdx.x / oh_s;
+  const int row = blockIdx.x - r * oh_s;
+  const int ph = row * bin_stride;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
-  float4* __restrict__ img = gx + (size_t)g.batch * H * W * C4;
-  const float4* __restrict__ in = gy + (size_t)blockIdx.x * C4;
+  const TapSource taps = make_taps(tt, g, outh, outw, H, W, W * C4, C4);
+  const size_t img_off = (size_t)g.batch * H * W * C4;
   const float d = g.inv_count_den;
+  const size_t bin0 = ((size_t)r * oh_s + row) * ow_s;
 
   for (int c = threadIdx.x; c < C4; c += blockDim.x) {
-    const float4 gv = __ldg(in + c);
-    for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
-      for (int ix = 0; ix < g.grid_w; ++ix) {
-        const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
-        if (!(ty.valid && tx.valid)) continue;
-        const float w[4] = {ty.h * tx.h, ty.h * tx.l, ty.l * tx.h, ty.l * tx.l};
-        const int o[4] = {ty.low * W + tx.low, ty.low * W + tx.high, ty.high * W + tx.low,
-                          ty.high * W + tx.high};
+    for (int q = 0; q < ow_s; ++q) {
+      const int pw = q * bin_stride;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 gv = acc;
+      if (kBackward) gv = __ldg(src + (bin0 + q) * C4 + c);
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const float4 ty = taps.y(ph, iy);
+        const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
+        if (yl < 0) continue;
+        for (int ix = 0; ix < g.grid_w; ++ix) {
+          const float4 tx = taps.x(pw, ix);
+          const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+          if (xl < 0) continue;
+          const float w[4] = {ty.w * tx.w, ty.w * tx.z, ty.z * tx.w, ty.z * tx.z};
+          const int o[4] = {yl + xl, yl + xh, yh + xl, yh + xh};
+          if (!kBackward) {
+            const float4* img = src + img_off + c;
+            const float4 v1 = __ldg(img + o[0]), v2 = __ldg(img + o[1]);
+            const float4 v3 = __ldg(img + o[2]), v4 = __ldg(img + o[3]);
+            acc.x += w[0] * v1.x + w[1] * v2.x + w[2] * v3.x + w[3] * v4.x;
+            acc.y += w[0] * v1.y + w[1] * v2.y + w[2] * v3.y + w[3] * v4.y;
+            acc.z += w[0] * v1.z + w[1] * v2.z + w[2] * v3.z + w[3] * v4.z;
+            acc.w += w[0] * v1.w + w[1] * v2.w + w[2] * v3.w + w[3] * v4.w;
+          } else {
+            float4* img = dst + img_off + c;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float4 t = make_float4(__fdiv_rn(gv.x * w[k], d), __fdiv_rn(gv.y * w[k], d),
-                                 __fdiv_rn(gv.z * w[k], d), __fdiv_rn(gv.w * w[k], d));
-          red_add_f4(img + (size_t)o[k] * C4 + c, t);
+            for (int k = 0; k < 4; ++k)
+              red_add_f4(img + o[k],
+                         make_float4(__fdiv_rn(gv.x * w[k], d), __fdiv_rn(gv.y * w[k], d),
+                                     __fdiv_rn(gv.z * w[k], d), __fdiv_rn(gv.w * w[k], d)));
+          }
         }
       }
+      if (!kBackward)
+        dst[(bin0 + q) * C4 + c] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d),
+                                               __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
     }
   }
 }
@@ -268,6 +324,8 @@ int pick_threads(int positions) {
   if (t > 256) t = 256;
   return t;
 }
+
+int nhwc_threads(int C4) { return C4 >= 256 ? 256 : (C4 >= 128 ? 128 : (C4 >= 64 ? 64 : 32)); }
 
 }  // namespace
 }  // namespace cmr
@@ -316,11 +374,10 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(x && rois && y);
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
-  CMR_REQUIRE((long long)R * oh_s * ow_s < (1ll << 31));
-  const int C4 = C / 4;
-  const int threads = C4 >= 256 ? 256 : (C4 >= 128 ? 128 : (C4 >= 64 ? 64 : 32));
-  roi_align_nhwc_fwd_kernel<<<R * oh_s * ow_s, threads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C4, outh,
+  CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
+  CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  roi_align_nhwc_kernel<false><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C / 4, outh,
       outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -336,11 +393,10 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(gy && rois);
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
-  CMR_REQUIRE((long long)R * oh_s * ow_s < (1ll << 31));
-  const int C4 = C / 4;
-  const int threads = C4 >= 256 ? 256 : (C4 >= 128 ? 128 : (C4 >= 64 ? 64 : 32));
-  roi_align_nhwc_bwd_kernel<<<R * oh_s * ow_s, threads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C4, outh,
+  CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
+  CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  roi_align_nhwc_kernel<true><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
       outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
   CMR_LAUNCH_CHECK();
   return CMR_OK;

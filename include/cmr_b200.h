@@ -134,6 +134,31 @@ int cmr_conv_gemm_tc(const cmr_conv_desc* desc, const float* a, const float* w,
                      float* d, const float* scale, const float* bias,
                      const float* addend, const float* mask, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Weight gradient on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate):
+ *   gw[i, gw_col0 + j] += row_scale[i] * sum over pixels (b, oy, ox) of
+ *        gy[b, oy*gy_stride + gy_off_y, ox*gy_stride + gy_off_x, gy_c0 + i]
+ *      *  x[b, oy*x_stride  + x_off_y,  ox*x_stride  + x_off_x,  x_c0 + j]
+ * for i < rows, j < cols, (oy, ox) in loop_h x loop_w; out-of-tensor pixels read
+ * zeros.  One call covers one filter tap: for a (n, kh, kw, c) filter bank call it
+ * with x_off = (fr - pad, fs - pad), gw_col0 = (fr*kw + fs)*c, gw_ld = kh*kw*c.
+ * Replaces the gW of chainer's Convolution2D / Deconvolution2D / Linear backward
+ * for the links at chainer_mask_rcnn/models/region_proposal_network.py:75-80 and
+ * models/mask_rcnn_resnet.py:131-143.  gw is accumulated into (zero it first).
+ * splits: 0 = automatic split of the pixel reduction across CTAs.
+ * ------------------------------------------------------------------------ */
+typedef struct cmr_wgrad_desc {
+  int batch, loop_h, loop_w;
+  int gy_h, gy_w, gy_ld, gy_stride, gy_off_y, gy_off_x, gy_c0;
+  int x_h, x_w, x_ld, x_stride, x_off_y, x_off_x, x_c0;
+  int rows, cols;
+  int gw_ld, gw_col0;
+  int splits;
+} cmr_wgrad_desc;
+
+int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* x,
+                      float* gw, const float* row_scale, void* stream);
+
 /* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
 int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
 

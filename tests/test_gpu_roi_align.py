@@ -74,7 +74,7 @@ def test_type_errors_like_reference():
         functions.roi_align_2d(x.astype(np.float32), np.zeros((1, 4), np.float32), 2, 2, 1.0)
 
 
-@pytest.mark.parametrize('oh,ratio,C', [(14, 0, 19), (7, 0, 8), (7, 2, 33), (5, 3, 4)])
+@pytest.mark.parametrize('oh,ratio,C', [(14, 0, 19), (7, 0, 8), (7, 2, 33), (5, 3, 4), (14, 40, 4)])
 def test_oracle_random_shapes(oh, ratio, C):
     """Ragged channel counts (not a multiple of the per-CTA chunk), several images,
     degenerate (zero-area) and whole-image RoIs."""
