@@ -6,8 +6,9 @@
 // the upstream gradient gy (rows i = output channels), Q the layer input x at one
 // filter tap (columns j = input channels).  Both operands are therefore MN-major
 // for the tensor core (the contiguous axis is the channel axis, not the reduction
-// axis): tiles are staged as [pixel][32 channels = 128 B] rows in 128B-swizzled
-// shared memory and read with MN-major UMMA descriptors (TF32 supports them).
+// axis): tiles are staged as [pixel][32 channels = 128 B] rows in shared memory with
+// the SWIZZLE_128B_BASE32B pattern (the one layout tcgen05 reads MN-major 32-bit
+// operands from) and read with MN-major UMMA descriptors.
 // Each operand has its own pixel map (stride, offset), which covers stride-2 convs
 // (x sampled at 2*oy - pad + fr), zero padding (out-of-image -> zeros) and the
 // 2x2 stride-2 deconvolution (gy sampled at 2*y + dy).
@@ -88,7 +89,9 @@ __device__ __forceinline__ void gather_tile(const PixelMap& pm, int pix0, int M,
       ok = (unsigned)y < (unsigned)pm.h && (unsigned)x < (unsigned)pm.w;
       if (ok) src_row = pm.base + ((size_t)(img * pm.h + y) * pm.w + x) * pm.ld;
     }
-    const uint32_t dst_row = stage_addr + row * 128 + ((jj ^ (row & 7)) << 4);
+    // SWIZZLE_128B_BASE32B: 32-byte chunk (jj >> 1) lands at chunk ^ (row & 3).
+    const uint32_t dst_row =
+        stage_addr + row * 128 + ((((jj >> 1) ^ (row & 3)) << 5) | ((jj & 1) << 4));
 #pragma unroll
     for (int cblk = 0; cblk < NBLK; ++cblk) {
       const int ch = pm.c0 + cblk * 32 + jj * 4;
@@ -205,10 +208,10 @@ conv_wgrad_tc_kernel(const WgradParams p) {
         const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
 #pragma unroll
         for (int k = 0; k < kPix / 8; ++k) {
-          // 8 pixels = one 1024 B swizzle atom per 32-channel block; blocks are
-          // kPix * 128 bytes apart (leading byte offset).
-          const uint64_t da = make_smem_desc_sw128(pa + k * 1024, kPix * 128, 1024);
-          const uint64_t db = make_smem_desc_sw128(qa + k * 1024, kPix * 128, 1024);
+          // 8 pixels = two 4-row (512 B) swizzle atoms per 32-channel block (stride
+          // byte offset); blocks are kPix * 128 bytes apart (leading byte offset).
+          const uint64_t da = make_smem_desc(pa + k * 1024, kPix * 128, 512, 1);
+          const uint64_t db = make_smem_desc(qa + k * 1024, kPix * 128, 512, 1);
           umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);

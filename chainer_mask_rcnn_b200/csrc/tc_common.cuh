@@ -132,15 +132,22 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //  bits [0,14)  start address >> 4      bits [16,30) leading byte offset >> 4
 //  bits [32,46) stride byte offset >> 4 bits [46,48) version (1 on sm_100)
 //  bits [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                         uint32_t sbo_bytes) {
+//               (1 = SWIZZLE_128B_BASE32B: the only layout the tensor core accepts for
+//               MN-major 32-bit operands -- 32-byte chunks of a 128 B row XOR-ed with
+//               (row & 3); atoms are 4 rows x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                         uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 
 // Instruction descriptor for kind::tf32, fp32 accumulate.
