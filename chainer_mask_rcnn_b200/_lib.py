@@ -13,6 +13,7 @@ c_int = ctypes.c_int
 c_float = ctypes.c_float
 c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
+c_longlong = ctypes.c_longlong
 
 # name -> (restype, argtypes); mirrors include/cmr_b200.h one to one.
 _SIGNATURES = {
@@ -24,7 +25,7 @@ _SIGNATURES = {
     'cmr_roi_align_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'cmr_roi_align_nhwc_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p,
-                                       c_int, c_int, c_int, c_int, c_float, c_int,
+                                       c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                        c_void_p, c_void_p]),
     'cmr_roi_align_nhwc_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_float, c_int,
@@ -40,6 +41,24 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p]),
     'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'cmr_pack_image_nhwc4': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+    'cmr_max_pool_nhwc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_int, c_int, c_void_p, c_void_p]),
+    'cmr_avg_pool_nhwc_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    'cmr_avg_pool_nhwc_bwd_accum': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                            c_int, c_void_p]),
+    'cmr_col_sum': (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'cmr_prep_dgrad_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
+                                      c_void_p, c_int, c_void_p, c_void_p]),
+    'cmr_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
+                                 c_float, c_float, c_void_p]),
+    'cmr_rpn_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_longlong,
+                             c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    'cmr_roi_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                             c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    'cmr_mask_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_void_p]),
 }
 
 

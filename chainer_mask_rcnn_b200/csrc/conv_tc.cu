@@ -325,7 +325,7 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   CMR_REQUIRE(c->batch > 0 && c->in_h > 0 && c->in_w > 0 && c->out_h > 0 && c->out_w > 0);
   CMR_REQUIRE(c->kh > 0 && c->kw > 0 && c->stride > 0 && c->pad >= 0 && c->n > 0);
   if (c->in_c <= 0 || c->in_c % kBK != 0) return CMR_ERR_UNSUPPORTED;
-  CMR_REQUIRE(c->in_ld >= c->in_c && c->in_ld % 4 == 0);
+  CMR_REQUIRE(c->in_ld > 0 && c->in_ld % 4 == 0);
   CMR_REQUIRE((reinterpret_cast<uintptr_t>(a) & 15) == 0);
   CMR_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0);
   const long long M = (long long)c->batch * c->out_h * c->out_w;

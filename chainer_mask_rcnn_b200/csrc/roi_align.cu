@@ -253,6 +253,12 @@ roi_align_nchw_bwd_kernel(const float* __restrict__ gy, const float* __restrict_
 }
 
 // ------------------------------------------------------------------ NHWC --
+__device__ __forceinline__ float round_tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
   // sm_90+: 128-bit vector reduction to global memory.
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x),
@@ -266,7 +272,8 @@ template <bool kBackward>
 __global__ void __launch_bounds__(256)
 roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                       float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
-                      int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio) {
+                      int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
+                      int round_out) {
   __shared__ TapTables tt;
   const int r = blockIdx.x / oh_s;
   const int row = blockIdx.x - r * oh_s;
@@ -311,9 +318,15 @@ roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ 
           }
         }
       }
-      if (!kBackward)
-        dst[(bin0 + q) * C4 + c] = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d),
-                                               __fdiv_rn(acc.z, d), __fdiv_rn(acc.w, d));
+      if (!kBackward) {
+        float4 o = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d),
+                               __fdiv_rn(acc.w, d));
+        if (round_out) {
+          o.x = round_tf32_rn(o.x); o.y = round_tf32_rn(o.y);
+          o.z = round_tf32_rn(o.z); o.w = round_tf32_rn(o.w);
+        }
+        dst[(bin0 + q) * C4 + c] = o;
+      }
     }
   }
 }
@@ -368,7 +381,7 @@ extern "C" int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int 
 extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C,
                                       const float* rois, int R, int outh, int outw,
                                       int bin_stride, float spatial_scale, int sampling_ratio,
-                                      float* y, void* stream) {
+                                      int round_tf32, float* y, void* stream) {
   CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
   CMR_REQUIRE(sampling_ratio >= 0 && bin_stride >= 1 && C % 4 == 0);
   if (R == 0) return CMR_OK;
@@ -378,7 +391,7 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
   roi_align_nhwc_kernel<false><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
+      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, round_tf32);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -397,7 +410,7 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
   roi_align_nhwc_kernel<true><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
+      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, 0);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -56,11 +56,13 @@ int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int N, int C,
  * x (N,H,W,C), y (R,outh/bin_stride,outw/bin_stride,C).  Only the bins
  * (ph, pw) with ph % bin_stride == 0 and pw % bin_stride == 0 are produced:
  * res5.a's stride-2 1x1 convolutions read no others when roi_size == 14.
- * C must be a multiple of 4. */
+ * C must be a multiple of 4.  round_tf32 != 0 rounds y to tf32 (it is the A operand
+ * of res5.a's tensor-core GEMMs). */
 int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C,
                            const float* rois, int R, int outh, int outw,
                            int bin_stride, float spatial_scale,
-                           int sampling_ratio, float* y, void* stream);
+                           int sampling_ratio, int round_tf32, float* y,
+                           void* stream);
 int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N,
                            int H, int W, int C, int outh, int outw,
                            int bin_stride, float spatial_scale,
@@ -108,7 +110,9 @@ int cmr_proposals(const float* loc, const float* score, const float* anchor,
  * (functions/affine_channel_2d.py:17-20), bias, residual add and ReLU fused.
  *
  * a : NHWC activations (batch, in_h, in_w, in_ld) of which in_c channels are
- *     used (in_c % 32 == 0); rows of the GEMM are output pixels (b, oy, ox),
+ *     used (in_c % 32 == 0; in_ld < in_c is allowed and makes one "channel" run
+ *     span several pixels of a row -- the stem reads 8 RGB0 pixels = 32 floats per
+ *     filter row this way); rows of the GEMM are output pixels (b, oy, ox),
  *     oy < out_h, ox < out_w, reading input pixel (oy*stride - pad + fr,
  *     ox*stride - pad + fs); out-of-image taps read zeros.
  * w : filter bank (n, kh, kw, in_c) fp32, i.e. K-major.
@@ -161,6 +165,64 @@ int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* 
 
 /* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
 int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * HBM-bound pieces of the graph around the convolutions (csrc/misc.cu).
+ * ------------------------------------------------------------------------ */
+/* (B,3,H,W) fp32 image planes -> (B,Hp,Wp,4) zero-padded RGB0 pixels, tf32-rounded;
+ * the image sits at (pad_top, pad_left).  Input side of extractor.conv1
+ * (chainer_mask_rcnn/models/resnet_extractor.py:63-66). */
+int cmr_pack_image_nhwc4(const float* img, int B, int H, int W, int Hp, int Wp,
+                         int pad_top, int pad_left, float* out, void* stream);
+/* chainer.functions.max_pooling_2d(ksize, stride, pad) on NHWC (cover_all is
+ * expressed through out_h/out_w); models/resnet_extractor.py:67-69. */
+int cmr_max_pool_nhwc(const float* x, int B, int H, int W, int C, int ksize,
+                      int stride, int pad, int out_h, int out_w, float* y,
+                      void* stream);
+/* average_pooling_2d over the whole HW window (models/mask_rcnn_resnet.py:187):
+ * x (R,HW,C) -> y (R,C); backward adds g/HW to `out` (R,HW,C), then zeroes where
+ * mask <= 0 (mask may be NULL). */
+int cmr_avg_pool_nhwc_fwd(const float* x, int R, int HW, int C, float* y,
+                          int round_tf32, void* stream);
+int cmr_avg_pool_nhwc_bwd_accum(const float* g, int R, int HW, int C, float* out,
+                                const float* mask, int round_tf32, void* stream);
+/* out[j] = sum_m g[m*ld + c0 + j], j < n  (bias gradients). */
+int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, float* out,
+                void* stream);
+/* Filter bank of the data-gradient GEMM:
+ * out[i][flip ? T-1-t : t][o] = tf32(w[o*stride_o + t*stride_t + i] * scale[o]). */
+int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long long stride_o,
+                          long long stride_t, const float* scale, int flip,
+                          float* out, void* stream);
+/* MomentumSGD + WeightDecay (examples/train_common.py:176-180) on a flat buffer:
+ * g' = grad_scale*g + wd*p;  v = momentum*v - lr*g';  p += v.  n % 4 == 0. */
+int cmr_sgd_momentum(float* param, const float* grad, float* velocity, size_t n,
+                     float lr, float momentum, float weight_decay,
+                     float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Losses of MaskRCNNTrainChain.__call__ and their gradients
+ * (chainer_mask_rcnn/models/mask_rcnn_train_chain.py:160-213), csrc/loss.cu.
+ * losses: device float[8]; [0] rpn_loc [1] rpn_cls [2] roi_loc [3] roi_cls
+ * [4] roi_mask, [5..7] scratch.  Gradient buffers are fully written.
+ * ------------------------------------------------------------------------ */
+/* loc (n_pixel, ld_loc) holds 4*A values per pixel, score (n_pixel, ld_score) A;
+ * gt_loc (n_pixel*A, 4), gt_label (n_pixel*A) in {-1,0,1};
+ * g (n_pixel, ld_g): [0,4A) d/dloc, [4A,5A) d/dscore, [5A,ld_g) zeros. */
+int cmr_rpn_loss(const float* loc, int ld_loc, const float* score, int ld_score,
+                 const float* gt_loc, const int32_t* gt_label, long long n_pixel,
+                 int n_anchor, float sigma, float* g, int ld_g, float* losses,
+                 void* stream);
+/* cls_loc (R, ld_cls_loc) 4*n_class values, score (R, ld_score) n_class logits;
+ * g (R, ld_g): [0,4*n_class) d/dcls_loc, [4*n_class,5*n_class) d/dscore, rest 0. */
+int cmr_roi_loss(const float* cls_loc, int ld_cls_loc, const float* score,
+                 int ld_score, const float* gt_loc, const int32_t* gt_label, int R,
+                 int n_class, float sigma, float* g, int ld_g, float* losses,
+                 void* stream);
+/* masks (R,HW,n_fg) logits, gt_mask (R,HW) in {-1,0,1}; g same shape as masks. */
+int cmr_mask_loss(const float* masks, const int32_t* gt_label,
+                  const int32_t* gt_mask, int R, int HW, int n_fg, float* g,
+                  float* losses, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ def bench_roi(out):
 
             def fwd_nhwc():
                 _lib.call('cmr_roi_align_nhwc_fwd', _lib.ptr(x_nhwc), 1, 50, 68, 1024,
-                          _lib.ptr(rois), R, oh, oh, 1, 1. / 16, ratio, _lib.ptr(yn),
+                          _lib.ptr(rois), R, oh, oh, 1, 1. / 16, ratio, 0, _lib.ptr(yn),
                           _lib.stream_ptr())
 
             def bwd_nhwc():
@@ -168,6 +168,34 @@ def bench_conv(out):
         print(json.dumps(rec)); out.append(rec)
 
 
+def bench_peaks(out):
+    """cuBLAS TF32 / bf16 GEMM throughput on this box (roofline denominators)."""
+    n = 8192
+    a = torch.randn((n, n), device='cuda')
+    b = torch.randn((n, n), device='cuda')
+    torch.backends.cuda.matmul.allow_tf32 = True
+    med, best = time_ms(lambda: torch.matmul(a, b), iters=10, warmup=3, flush=False)
+    rec = dict(kernel='cublas_tf32_8192', ms=med, ms_min=best, tflops=2.0 * n ** 3 / best / 1e9,
+               tflops_median=2.0 * n ** 3 / med / 1e9)
+    print(json.dumps(rec)); out.append(rec)
+    # sustained: back to back for ~3 s
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    iters = max(10, int(3000 / best))
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, b)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    rec = dict(kernel='cublas_tf32_8192_sustained', ms=ms, tflops=2.0 * n ** 3 / ms / 1e9)
+    print(json.dumps(rec)); out.append(rec)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ah, bh = a.bfloat16(), b.bfloat16()
+    med, best = time_ms(lambda: torch.matmul(ah, bh), iters=10, warmup=3, flush=False)
+    rec = dict(kernel='cublas_bf16_8192', ms=med, ms_min=best, tflops=2.0 * n ** 3 / best / 1e9)
+    print(json.dumps(rec)); out.append(rec)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', nargs='?', default='all')
@@ -180,6 +208,8 @@ if __name__ == '__main__':
         bench_nms(out)
     if args.what in ('conv', 'all'):
         bench_conv(out)
+    if args.what in ('peaks', 'all'):
+        bench_peaks(out)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         with open(args.out, 'w') as f:
