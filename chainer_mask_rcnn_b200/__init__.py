@@ -9,5 +9,7 @@ copied to the GPU and back.  There is no CPU implementation in this package.
 from . import _lib  # noqa: F401
 from . import functions  # noqa: F401
 from . import utils  # noqa: F401
+from . import models  # noqa: F401
+from . import optimizers  # noqa: F401
 
-__version__ = '0.1.0'
+__version__ = '0.2.0'

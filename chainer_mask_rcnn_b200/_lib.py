@@ -20,6 +20,9 @@ _SIGNATURES = {
     'cmr_status_string': (ctypes.c_char_p, [c_int]),
     'cmr_version': (c_int, []),
     'cmr_last_cuda_error': (ctypes.c_char_p, []),
+    'cmr_launch_count': (c_longlong, []),
+    'cmr_prof_enable': (c_int, [c_int]),
+    'cmr_prof_collect': (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
     'cmr_roi_align_fwd': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                   c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
     'cmr_roi_align_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
@@ -50,15 +53,15 @@ _SIGNATURES = {
                                             c_int, c_void_p]),
     'cmr_col_sum': (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
     'cmr_prep_dgrad_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
-                                      c_void_p, c_int, c_void_p, c_void_p]),
+                                      c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     'cmr_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                                  c_float, c_float, c_void_p]),
     'cmr_rpn_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_longlong,
                              c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     'cmr_roi_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                              c_float, c_void_p, c_int, c_void_p, c_void_p]),
-    'cmr_mask_loss': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                              c_void_p, c_void_p]),
+    'cmr_mask_loss': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 

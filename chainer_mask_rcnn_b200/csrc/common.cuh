@@ -20,7 +20,21 @@ void record_cuda_error(cudaError_t e, const char* file, int line);
     }                                                        \
   } while (0)
 
-#define CMR_LAUNCH_CHECK() CMR_CUDA_TRY(cudaGetLastError())
+// Every kernel launch of the library passes through here: counts it (cmr_launch_count)
+// and surfaces launch errors.
+void count_launch();
+#define CMR_LAUNCH_CHECK()               \
+  do {                                   \
+    ::cmr::count_launch();               \
+    CMR_CUDA_TRY(cudaGetLastError());    \
+  } while (0)
+
+// Optional per-launch timing of the tensor-core kernels (cmr_prof_enable): a pair of
+// CUDA events on the launching stream around the launch, plus the launch's algorithmic
+// work (FLOPs), summed by cmr_prof_collect.  Skipped while a stream is being captured.
+enum ProfKind { kProfConvGemm = 0, kProfWgrad = 1, kProfKinds = 2 };
+void prof_begin(int kind, double work, cudaStream_t st);
+void prof_end(cudaStream_t st);
 
 #define CMR_REQUIRE(cond)                 \
   do {                                    \

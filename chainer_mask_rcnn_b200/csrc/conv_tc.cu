@@ -308,7 +308,9 @@ int launch(const CUtensorMap& tmap, const ConvGemmParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.M, kBM), ceil_div(p.N, BN));
+  prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
   conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, p);
+  prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -238,7 +238,9 @@ int launch_wgrad(const WgradParams& p, int splits, cudaStream_t st) {
     configured = true;
   }
   dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits);
+  prof_begin(kProfWgrad, 2.0 * p.M * (double)p.rows * p.cols, st);
   conv_wgrad_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(p);
+  prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -158,17 +158,17 @@ roi_loss_kernel(const float* __restrict__ cls_loc, int ld_cl, const float* __res
   block_atomic_add(l_cls, losses + 3);
 }
 
-// One thread per element of the (R, HW, n_fg) mask logits.
+// One thread per element of the (R, HW, ld_g) gradient buffer.
 __global__ void __launch_bounds__(256)
-mask_loss_kernel(const float* __restrict__ masks, const int* __restrict__ gt_label,
+mask_loss_kernel(const float* __restrict__ masks, int ld_m, const int* __restrict__ gt_label,
                  const int* __restrict__ gt_mask, size_t total, int HW, int n_fg,
-                 float* __restrict__ g, float* __restrict__ losses,
+                 float* __restrict__ g, int ld_g, float* __restrict__ losses,
                  const int* __restrict__ count) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (e < total) {
-    const int c = (int)(e % n_fg);
-    const size_t pix = e / n_fg;
+    const int c = (int)(e % ld_g);
+    const size_t pix = e / ld_g;
     const int r = (int)(pix / HW);
     int sel = __ldg(gt_label + r) - 1;  // roi_masks[arange, label - 1]: -1 wraps to the last class
     if (sel < 0) sel += n_fg;
@@ -177,7 +177,7 @@ mask_loss_kernel(const float* __restrict__ masks, const int* __restrict__ gt_lab
       const int t = __ldg(gt_mask + pix);
       if (t >= 0) {
         const float inv_n = 1.0f / (float)max(*count, 1);
-        l = sigmoid_ce(__ldg(masks + e), t, &gv) * inv_n;
+        l = sigmoid_ce(__ldg(masks + pix * ld_m + c), t, &gv) * inv_n;
         gv *= inv_n;
       }
     }
@@ -236,9 +236,11 @@ extern "C" int cmr_roi_loss(const float* cls_loc, int ld_cls_loc, const float* s
   return CMR_OK;
 }
 
-extern "C" int cmr_mask_loss(const float* masks, const int32_t* gt_label, const int32_t* gt_mask,
-                             int R, int HW, int n_fg, float* g, float* losses, void* stream) {
+extern "C" int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt_label,
+                             const int32_t* gt_mask, int R, int HW, int n_fg, float* g, int ld_g,
+                             float* losses, void* stream) {
   CMR_REQUIRE(masks && gt_label && gt_mask && g && losses && R > 0 && HW > 0 && n_fg > 0);
+  CMR_REQUIRE(ld_masks >= n_fg && ld_g >= n_fg);
   cudaStream_t st = as_stream(stream);
   int* count = reinterpret_cast<int*>(losses + 7);
   CMR_CUDA_TRY(cudaMemsetAsync(losses + 4, 0, sizeof(float), st));
@@ -247,9 +249,9 @@ extern "C" int cmr_mask_loss(const float* masks, const int32_t* gt_label, const 
   count_ge0_kernel<<<(unsigned)min((long long)sm_count() * 8, ceil_div_ll(npix, 256)), 256, 0,
                      st>>>(gt_mask, npix, count);
   CMR_LAUNCH_CHECK();
-  const size_t total = npix * n_fg;
+  const size_t total = npix * ld_g;
   mask_loss_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
-      masks, gt_label, gt_mask, total, HW, n_fg, g, losses, count);
+      masks, ld_masks, gt_label, gt_mask, total, HW, n_fg, g, ld_g, losses, count);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -140,14 +140,14 @@ col_sum_kernel(const float* __restrict__ g, long long M, int ld, int c0, int n,
 }
 
 // ------------------------------------------------------ filter re-layout ---
-// out[i][flip ? T-1-t : t][o] = round_tf32(w[o*so + t*st + i] * scale[o])
+// out[(i*T + (flip ? T-1-t : t))*ld_out + col0 + o] = round_tf32(w[o*so + t*st + i] * scale[o])
 // (the filter bank of the data-gradient GEMM: transposed, spatially flipped for a
 // correlation, with the frozen AffineChannel2D slope folded in, since
 // gx = conv^T(W_affine * gy); functions/affine_channel_2d.py:48-52).
 __global__ void __launch_bounds__(256)
 prep_dgrad_weight_kernel(const float* __restrict__ w, int O, int T, int I, long long so,
                          long long st, const float* __restrict__ scale, int flip,
-                         float* __restrict__ out) {
+                         float* __restrict__ out, int ld_out, int col0) {
   __shared__ float tile[32][33];
   const int t = blockIdx.z;
   const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
@@ -165,7 +165,8 @@ prep_dgrad_weight_kernel(const float* __restrict__ w, int O, int T, int I, long 
   const int to = flip ? T - 1 - t : t;
   for (int r = ty; r < 32; r += 8) {
     const int i = i0 + r, o = o0 + tx;
-    if (i < I && o < O) out[((size_t)i * T + to) * O + o] = tc::round_tf32(tile[tx][r]);
+    if (i < I && o < O)
+      out[((size_t)i * T + to) * ld_out + col0 + o] = tc::round_tf32(tile[tx][r]);
   }
 }
 
@@ -269,12 +270,13 @@ extern "C" int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, f
 
 extern "C" int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long long stride_o,
                                      long long stride_t, const float* scale, int flip,
-                                     float* out, void* stream) {
+                                     float* out, int ld_out, int col0, void* stream) {
   CMR_REQUIRE(w && out && O > 0 && T > 0 && I > 0 && T < 65536);
+  CMR_REQUIRE(col0 >= 0 && ld_out >= col0 + O);
   dim3 grid(ceil_div(I, 32), ceil_div(O, 32), T);
   CMR_REQUIRE(grid.y < 65536);
   prep_dgrad_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, O, T, I, stride_o, stride_t,
-                                                                scale, flip, out);
+                                                                scale, flip, out, ld_out, col0);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -1,0 +1,180 @@
+"""Device plumbing shared by the model classes: thin wrappers over the C ABI
+(include/cmr_b200.h) working on channels-last torch CUDA tensors, and the flat
+parameter / gradient / momentum buffers.
+
+Everything the network computes runs in libcmr_b200's kernels; torch is used for
+device memory, streams and views only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+f32 = torch.float32
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def conv_out(size, k, s, p):
+    return (size + 2 * p - k) // s + 1
+
+
+def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=None,
+              addend=None, mask=None, relu=False, round_out=True, in_c=None, in_ld=None,
+              out_hw=None, d_stride=1, d_off=(0, 0), tile_n=0):
+    """out[b, oy*d_stride+d_off[0], ox*d_stride+d_off[1], :n] =
+    epilogue(sum_{fr,fs,c} x[b, oy*stride-pad+fr, ox*stride-pad+fs, c] * w[n, fr, fs, c]).
+    x (B,H,W,C) contiguous NHWC; w (n, kh, kw, in_c) contiguous; see cmr_conv_gemm_tc."""
+    B, H, W, C = x.shape
+    in_c = C if in_c is None else in_c
+    in_ld = C if in_ld is None else in_ld
+    oh, ow = out_hw if out_hw else (conv_out(H, kh, stride, pad), conv_out(W, kw, stride, pad))
+    if out is None:
+        out = torch.empty((B, oh, ow, n), dtype=f32, device=x.device)
+    _, dh, dw, dld = out.shape
+    desc = _lib.ConvDesc(B, H, W, in_c, in_ld, oh, ow, kh, kw, stride, pad, n, dh, dw, dld,
+                         d_stride, d_off[0], d_off[1], int(relu), int(round_out), tile_n)
+    _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _p(x), _p(w), _p(out), _p(scale),
+              _p(bias), _p(addend), _p(mask), stream())
+    return out
+
+
+def wgrad_tap(gy, x, gw, rows, cols, loop_hw, gw_ld, gw_col0=0, gy_stride=1, gy_off=(0, 0),
+              gy_c0=0, x_stride=1, x_off=(0, 0), x_c0=0, row_scale=None):
+    """gw[i, gw_col0 + j] += row_scale[i] * sum_pix gy[pix_gy, gy_c0+i] * x[pix_x, x_c0+j]
+    (cmr_conv_wgrad_tc).  gy (B,gh,gw,ld), x (B,xh,xw,ld) contiguous NHWC."""
+    B, gh, gww, gld = gy.shape
+    _, xh, xw, xld = x.shape
+    d = _lib.WgradDesc(B, loop_hw[0], loop_hw[1], gh, gww, gld, gy_stride, gy_off[0], gy_off[1],
+                       gy_c0, xh, xw, xld, x_stride, x_off[0], x_off[1], x_c0, rows, cols,
+                       gw_ld, gw_col0, 0)
+    _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _p(gy), _p(x), _p(gw), _p(row_scale),
+              stream())
+
+
+def round_tf32(src, dst=None):
+    dst = src if dst is None else dst
+    _lib.call('cmr_round_tf32', _p(src), _p(dst), src.numel(), stream())
+    return dst
+
+
+def column_sums(g, c0, n, out):
+    """out[:n] = sum over all leading axes of g[..., c0:c0+n] (g contiguous)."""
+    ld = g.shape[-1]
+    rows = g.numel() // ld
+    _lib.call('cmr_col_sum', _p(g), rows, ld, c0, n, _p(out), stream())
+    return out
+
+
+def prep_dgrad_weight(w, O, T, I, stride_o, stride_t, scale, flip, out, ld_out=None, col0=0):
+    _lib.call('cmr_prep_dgrad_weight', _p(w), O, T, I, stride_o, stride_t, _p(scale), int(flip),
+              _p(out), O if ld_out is None else ld_out, col0, stream())
+    return out
+
+
+def max_pool(x, k, stride, pad, cover_all=True):
+    B, H, W, C = x.shape
+    if cover_all:
+        oh = (H + 2 * pad - k + stride - 1) // stride + 1
+        ow = (W + 2 * pad - k + stride - 1) // stride + 1
+    else:
+        oh, ow = conv_out(H, k, stride, pad), conv_out(W, k, stride, pad)
+    y = torch.empty((B, oh, ow, C), dtype=f32, device=x.device)
+    _lib.call('cmr_max_pool_nhwc', _p(x), B, H, W, C, k, stride, pad, oh, ow, _p(y), stream())
+    return y
+
+
+def avg_pool(x, round_out=True):
+    """(R, h, w, C) -> (R, C) mean over h*w."""
+    R, h, w, C = x.shape
+    y = torch.empty((R, C), dtype=f32, device=x.device)
+    _lib.call('cmr_avg_pool_nhwc_fwd', _p(x), R, h * w, C, _p(y), int(round_out), stream())
+    return y
+
+
+def avg_pool_bwd_accum(g, out, mask, round_out=True):
+    R, h, w, C = out.shape
+    _lib.call('cmr_avg_pool_nhwc_bwd_accum', _p(g), R, h * w, C, _p(out), _p(mask),
+              int(round_out), stream())
+    return out
+
+
+def roi_align_nhwc(x, rois_xy, outh, outw, bin_stride, spatial_scale, sampling_ratio=0,
+                   round_out=True):
+    N, H, W, C = x.shape
+    R = rois_xy.shape[0]
+    ohs, ows = -(-outh // bin_stride), -(-outw // bin_stride)
+    y = torch.empty((R, ohs, ows, C), dtype=f32, device=x.device)
+    _lib.call('cmr_roi_align_nhwc_fwd', _p(x), N, H, W, C, _p(rois_xy), R, outh, outw,
+              bin_stride, float(spatial_scale), sampling_ratio, int(round_out), _p(y), stream())
+    return y
+
+
+def roi_align_nhwc_bwd(gy, rois_xy, x_shape, outh, outw, bin_stride, spatial_scale,
+                       sampling_ratio=0):
+    N, H, W, C = x_shape
+    gx = torch.empty((N, H, W, C), dtype=f32, device=gy.device)
+    _lib.call('cmr_roi_align_nhwc_bwd', _p(gy), _p(rois_xy), rois_xy.shape[0], N, H, W, C, outh,
+              outw, bin_stride, float(spatial_scale), sampling_ratio, _p(gx), stream())
+    return gx
+
+
+def as_nchw_view(x_nhwc):
+    """(B,H,W,C) contiguous -> (B,C,H,W) view on the same memory (channels-last)."""
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def to_nhwc(x):
+    """Accepts an NCHW-shaped tensor; returns a contiguous (B,H,W,C) tensor, without a
+    copy when the memory is already channels-last (what this package produces)."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+# ------------------------------------------------------------------ params --
+ALIGN = 64  # floats: every parameter starts on a 256-byte boundary (TMA base alignment)
+
+
+class FlatStore(object):
+    """A set of named fp32 parameters carved out of one flat device buffer, so that
+    the gradient all-reduce and the SGD update are single launches over it (the
+    reference packs gradients the same way inside ChainerMN's communicator,
+    examples/train_common.py:99,177-178)."""
+
+    def __init__(self):
+        self.specs = []        # (name, shape, offset)
+        self.index = {}
+        self.size = 0
+        self.data = None
+
+    def add(self, name, shape):
+        if self.data is not None:
+            raise RuntimeError('store already allocated')
+        n = int(np.prod(shape))
+        off = self.size
+        self.specs.append((name, tuple(shape), off))
+        self.index[name] = len(self.specs) - 1
+        self.size = off + (n + ALIGN - 1) // ALIGN * ALIGN
+        return name
+
+    def allocate(self, device):
+        self.data = torch.zeros((max(self.size, 4),), dtype=f32, device=device)
+        return self
+
+    def view(self, name, buf=None):
+        _, shape, off = self.specs[self.index[name]]
+        buf = self.data if buf is None else buf
+        return buf[off:off + int(np.prod(shape))].view(shape)
+
+    def names(self):
+        return [s[0] for s in self.specs]
+
+    def __contains__(self, name):
+        return name in self.index

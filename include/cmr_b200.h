@@ -35,6 +35,16 @@ const char* cmr_status_string(int status);
 int cmr_version(void);
 /* Last CUDA error string recorded by this library on the calling thread. */
 const char* cmr_last_cuda_error(void);
+/* Number of CUDA kernels this library has launched in this process so far. */
+long long cmr_launch_count(void);
+/* Measurement aid for bench.py: when enabled, every tensor-core launch is bracketed
+ * by a pair of CUDA events on its stream.  cmr_prof_collect(kind) waits for the
+ * recorded launches of `kind` (0 = cmr_conv_gemm_tc, 1 = cmr_conv_wgrad_tc), returns
+ * their summed device time (ms), summed algorithmic FLOPs (2*M*N*K per launch, no
+ * padding) and count, and forgets them. */
+int cmr_prof_enable(int on);
+int cmr_prof_collect(int kind, double* total_ms, double* total_work,
+                     long long* launches);
 
 /* ------------------------------------------------------------------------ *
  * ROIAlign, reference layout (x NCHW fp32, rois (R,5) = b,x1,y1,x2,y2).
@@ -189,11 +199,13 @@ int cmr_avg_pool_nhwc_bwd_accum(const float* g, int R, int HW, int C, float* out
 /* out[j] = sum_m g[m*ld + c0 + j], j < n  (bias gradients). */
 int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, float* out,
                 void* stream);
-/* Filter bank of the data-gradient GEMM:
- * out[i][flip ? T-1-t : t][o] = tf32(w[o*stride_o + t*stride_t + i] * scale[o]). */
+/* Filter bank of the data-gradient GEMM (row length ld_out >= col0 + O, so that
+ * several layers can share one fused bank):
+ * out[(i*T + (flip ? T-1-t : t))*ld_out + col0 + o] =
+ *     tf32(w[o*stride_o + t*stride_t + i] * scale[o]);  scale may be NULL. */
 int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long long stride_o,
                           long long stride_t, const float* scale, int flip,
-                          float* out, void* stream);
+                          float* out, int ld_out, int col0, void* stream);
 /* MomentumSGD + WeightDecay (examples/train_common.py:176-180) on a flat buffer:
  * g' = grad_scale*g + wd*p;  v = momentum*v - lr*g';  p += v.  n % 4 == 0. */
 int cmr_sgd_momentum(float* param, const float* grad, float* velocity, size_t n,
@@ -219,10 +231,11 @@ int cmr_roi_loss(const float* cls_loc, int ld_cls_loc, const float* score,
                  int ld_score, const float* gt_loc, const int32_t* gt_label, int R,
                  int n_class, float sigma, float* g, int ld_g, float* losses,
                  void* stream);
-/* masks (R,HW,n_fg) logits, gt_mask (R,HW) in {-1,0,1}; g same shape as masks. */
-int cmr_mask_loss(const float* masks, const int32_t* gt_label,
+/* masks (R,HW,ld_masks) logits in channels [0,n_fg), gt_mask (R,HW) in {-1,0,1};
+ * g (R,HW,ld_g): channel label-1 of each RoI gets the gradient, the rest zeros. */
+int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt_label,
                   const int32_t* gt_mask, int R, int HW, int n_fg, float* g,
-                  float* losses, void* stream);
+                  int ld_g, float* losses, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,8 @@ def _stub_chainer():
     chainer = types.ModuleType('chainer')
     cuda = types.ModuleType('chainer.cuda')
     cuda.get_array_module = lambda *a: numpy
+    cuda.to_cpu = lambda a: a
+    cuda.to_gpu = lambda a: a
     function = types.ModuleType('chainer.function')
 
     class Function(object):
@@ -54,10 +56,26 @@ def _stub_chainer():
     }
 
 
-def _load(relpath, modname):
+def _stub_chainercv():
+    """chainercv is absent: the two helpers the reference's
+    ProposalTargetCreator imports are served by the oracle's restatements."""
+    from . import bbox as ob
+    names = ['chainercv', 'chainercv.links', 'chainercv.links.model',
+             'chainercv.links.model.faster_rcnn', 'chainercv.links.model.faster_rcnn.utils',
+             'chainercv.links.model.faster_rcnn.utils.bbox2loc', 'chainercv.utils',
+             'chainercv.utils.bbox', 'chainercv.utils.bbox.bbox_iou']
+    mods = {n: types.ModuleType(n) for n in names}
+    mods['chainercv.links.model.faster_rcnn.utils.bbox2loc'].bbox2loc = ob.bbox2loc
+    mods['chainercv.utils.bbox.bbox_iou'].bbox_iou = ob.bbox_iou
+    return mods
+
+
+def _load(relpath, modname, extra_stubs=None):
     if not reference_available():
         return None
     stubs = _stub_chainer()
+    if extra_stubs:
+        stubs.update(extra_stubs)
     saved = {k: sys.modules.get(k) for k in stubs}
     sys.modules.update(stubs)
     try:
@@ -83,6 +101,14 @@ def load_affine_channel_module():
     """-> module of chainer_mask_rcnn/functions/affine_channel_2d.py, or None."""
     return _load('chainer_mask_rcnn/functions/affine_channel_2d.py',
                  '_ref_affine_channel_2d')
+
+
+def load_proposal_target_creator_module():
+    """-> module of chainer_mask_rcnn/models/utils/proposal_target_creator.py (the
+    reference's own host-side sampler, run verbatim; bbox2loc / bbox_iou come from
+    oracle/bbox.py), or None."""
+    return _load('chainer_mask_rcnn/models/utils/proposal_target_creator.py',
+                 '_ref_proposal_target_creator', _stub_chainercv())
 
 
 def ref_roi_align_forward(x, rois_xy, outh, outw, spatial_scale, sampling_ratio):

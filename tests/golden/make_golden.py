@@ -111,12 +111,27 @@ def affine_fixture():
     return dict(x=x, W=W, b=b, gy=gy, y=y, gx=gx, gW=gW, gb=gb)
 
 
+def proposal_target_fixture():
+    """The reference's own ProposalTargetCreator (models/utils/proposal_target_creator.py:
+    63-184) run verbatim on a seeded scene (tests/synth.py detection_scene)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import synth
+    mod = ref_loader.load_proposal_target_creator_module()
+    scene_seed, np_seed, n_sample = 5, 1234, 64
+    roi, bbox, label, mask, _ = synth.detection_scene(scene_seed)
+    np.random.seed(np_seed)
+    sr, gl, glab, gm = mod.ProposalTargetCreator(n_sample=n_sample)(roi, bbox, label, mask)
+    return dict(scene_seed=scene_seed, np_seed=np_seed, n_sample=n_sample, sample_roi=sr,
+                gt_roi_loc=gl.astype(np.float32), gt_roi_label=glab, gt_roi_mask=gm)
+
+
 def main():
     assert ref_loader.reference_available(), 'needs /root/reference'
     np.savez_compressed(os.path.join(HERE, 'roi_align_unit.npz'), **unit_fixture())
     np.savez_compressed(os.path.join(HERE, 'roi_align_check.npz'), **check_fixture())
     np.savez_compressed(os.path.join(HERE, 'roi_align_random.npz'), **random_fixture())
     np.savez_compressed(os.path.join(HERE, 'affine_channel.npz'), **affine_fixture())
+    np.savez_compressed(os.path.join(HERE, 'proposal_targets.npz'), **proposal_target_fixture())
     print('golden vectors written to', HERE)
 
 

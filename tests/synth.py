@@ -48,3 +48,26 @@ def rpn_outputs(rs, n_anchor, loc_std=0.3):
     loc = (rs.standard_normal((n_anchor, 4)) * loc_std).astype(np.float32)
     score = (tie_free_scores(rs, n_anchor) * 12 - 6).astype(np.float32)
     return loc, score
+
+
+def detection_scene(seed, n_gt=6, H=320, W=416, n_roi=300):
+    """A small detection scene: ground-truth boxes with elliptical instance masks and
+    candidate RoIs (half jittered copies of the ground truth, half random).
+    -> roi (n_roi,4), bbox, label, mask (n_gt,H,W) int32, (H, W)."""
+    rs = np.random.RandomState(seed)
+    bbox = random_boxes(rs, n_gt, H, W, 40., 200.)
+    bbox = bbox[(bbox[:, 2] - bbox[:, 0] > 10) & (bbox[:, 3] - bbox[:, 1] > 10)]
+    label = rs.randint(0, 20, len(bbox)).astype(np.int32)
+    mask = np.zeros((len(bbox), H, W), np.int32)
+    yy, xx = np.mgrid[:H, :W]
+    for i, (y1, x1, y2, x2) in enumerate(bbox):
+        cy, cx, ry, rx = (y1 + y2) / 2, (x1 + x2) / 2, (y2 - y1) / 2, (x2 - x1) / 2
+        mask[i] = (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1).astype(np.int32)
+    jitter = bbox[rs.randint(0, len(bbox), n_roi // 2)] + rs.normal(0, 8, (n_roi // 2, 4))
+    roi = np.concatenate([jitter, random_boxes(rs, n_roi - n_roi // 2, H, W)])
+    roi = np.stack([np.minimum(roi[:, 0], roi[:, 2]), np.minimum(roi[:, 1], roi[:, 3]),
+                    np.maximum(roi[:, 0], roi[:, 2]) + 1, np.maximum(roi[:, 1], roi[:, 3]) + 1],
+                   axis=1)
+    roi[:, 0::2] = np.clip(roi[:, 0::2], 0, H)
+    roi[:, 1::2] = np.clip(roi[:, 1::2], 0, W)
+    return roi.astype(np.float32), bbox, label, mask, (H, W)

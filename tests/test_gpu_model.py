@@ -1,0 +1,309 @@
+"""Model-level parity: the CUDA graph (MaskRCNNResNet / MaskRCNNTrainChain) against
+the NumPy oracle of the reference graph (oracle/model.py) on identical parameters and
+inputs, at a width (base_channels=32) and image size the oracle finishes in seconds.
+
+Tolerances.  The north star asks <= 1e-3 (max|delta| / max|ref|) per operator on
+identical inputs; that is what the per-kernel tests assert.  Here whole stages are
+chained (TF32 tensor-core products, fp32 accumulation, up to ~50 layers deep), so
+end-to-end bounds are looser and are written next to each assertion.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from chainer_mask_rcnn_b200 import models
+from chainer_mask_rcnn_b200.models import engine as E
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+BASE = 32
+N_FG = 5
+SCALES = (4, 8, 16, 32)
+
+
+def rel(got, want):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def nchw(t_nhwc):
+    return t_nhwc.permute(0, 3, 1, 2).cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def setup():
+    rs = np.random.RandomState(0)
+    cfg = om.Config(n_layers=50, n_fg_class=N_FG, anchor_scales=SCALES, roi_size=14, base=BASE)
+    params = om.make_params(cfg, rs)
+    # non-trivial conv1 bias / head biases so that every epilogue term is exercised
+    for k in params:
+        if k.endswith('/b') and '/bn' not in k:
+            params[k] = (rs.standard_normal(params[k].shape) * 0.05).astype(np.float32)
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE)
+    model.load_state_dict(params)
+    x = (rs.uniform(0, 255, (2, 3, 128, 160)) - 115.).astype(np.float32)
+    return cfg, params, model, x, rs
+
+
+def test_parameter_names_and_layouts_round_trip(setup):
+    cfg, params, model, _, _ = setup
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(params)
+    for k in params:
+        assert sd[k].shape == params[k].shape, k
+        np.testing.assert_array_equal(sd[k], params[k])
+    frozen = {k for k in params if om.is_frozen(k)}
+    assert frozen == set(model.ctx.frozen.names())
+
+
+def test_extractor_stages_match_oracle(setup):
+    cfg, params, model, x, _ = setup
+    tape = {}
+    want, _ = om.extractor(cfg, params, x, tape)
+    ctx = model.ctx
+    ctx.prepare(backward=False)
+    xt = torch.from_numpy(x).cuda()
+    ex = model.extractor
+    h = ex.conv1.forward(xt)
+    assert rel(nchw(h), tape['extractor/conv1']) <= 1e-3            # one layer
+    h = E.max_pool(h, 3, 2, 1)
+    assert nchw(h).shape == tape['extractor/pool1'].shape            # cover_all output size
+    assert rel(nchw(h), tape['extractor/pool1']) <= 1e-3
+    h = ex.res2.forward(h)
+    assert rel(nchw(h), tape['extractor/res2']) <= 2e-3             # 10 layers deep
+    # each stage again on the oracle's own input: identical inputs, one stage deep
+    for stage, blk in (('res3', ex.res3), ('res4', ex.res4)):
+        prev = {'res3': 'res2', 'res4': 'res3'}[stage]
+        src = torch.from_numpy(tape['extractor/' + prev]).cuda().permute(0, 2, 3, 1).contiguous()
+        got = blk.forward(E.round_tf32(src))
+        assert rel(nchw(got), tape['extractor/' + stage]) <= 2e-3
+    got = model.extractor(x)
+    assert tuple(got.shape) == want.shape
+    assert rel(got, want) <= 5e-3                                    # 40 layers end to end
+
+
+def test_call_matches_oracle_given_same_proposals(setup):
+    """MaskRCNN.__call__: proposals are integer-exact given the same RPN outputs
+    (tests/test_gpu_nms.py); here the RPN outputs differ at the 1e-3 level, so the head
+    is compared on the model's own proposals."""
+    cfg, params, model, x, _ = setup
+    from chainer_mask_rcnn_b200.utils import config
+    with config.using_config('train', False):
+        cls_locs, scores, rois, roi_indices, masks = model(x, np.array([1., 1.], np.float32))
+    assert cls_locs.shape[1] == 4 * (N_FG + 1) and scores.shape[1] == N_FG + 1
+    assert masks.shape[1:] == (N_FG, 14, 14)
+    R = rois.shape[0]
+    assert roi_indices.shape == (R,) and roi_indices.dtype == torch.int32
+    feat, _ = om.extractor(cfg, params, x)
+    sel = np.linspace(0, R - 1, 24).astype(np.int64)
+    w_cl, w_sc, w_m, _ = om.head_forward(cfg, params, feat, rois.cpu().numpy()[sel],
+                                         roi_indices.cpu().numpy()[sel])
+    assert rel(cls_locs[sel], w_cl) <= 1e-2
+    assert rel(scores[sel], w_sc) <= 1e-2
+    assert rel(masks[sel], w_m) <= 1e-2
+
+
+def _targets(cfg, rs, x, n_anchor_total, n_roi=24):
+    H, W = x.shape[2:]
+    rois = synth.random_boxes(rs, n_roi, H, W, 12., 120.)
+    idx = (np.arange(n_roi) % 2).astype(np.int32)
+    gt_roi_locs = (rs.standard_normal((n_roi, 4)) * 0.5).astype(np.float32)
+    gt_roi_labels = rs.randint(0, cfg.n_class, n_roi).astype(np.int32)
+    gt_roi_labels[:4] = 0
+    gt_roi_masks = rs.randint(0, 2, (n_roi, 14, 14)).astype(np.int32)
+    gt_roi_masks[gt_roi_labels == 0] = -1
+    gt_rpn_labels = rs.choice([-1, 0, 1], size=n_anchor_total, p=[0.8, 0.12, 0.08]).astype(np.int32)
+    gt_rpn_locs = (rs.standard_normal((n_anchor_total, 4)) * 0.3).astype(np.float32)
+    return rois, idx, gt_roi_locs, gt_roi_labels, gt_roi_masks, gt_rpn_locs, gt_rpn_labels
+
+
+def test_train_step_losses_and_gradients_match_oracle(setup):
+    cfg, params, model, x, rs = setup
+    feat, _ = om.extractor(cfg, params, x)
+    n_anchor = feat.shape[2] * feat.shape[3] * cfg.n_anchor
+    (rois, idx, gt_roi_locs, gt_roi_labels, gt_roi_masks, gt_rpn_locs,
+     gt_rpn_labels) = _targets(cfg, rs, x, 2 * n_anchor)
+    want_losses, want_grads = om.train_step_grads(cfg, params, x, rois, idx, gt_roi_locs,
+                                                  gt_roi_labels, gt_roi_masks, gt_rpn_locs,
+                                                  gt_rpn_labels)
+    chain = models.MaskRCNNTrainChain(model)
+    ctx = model.ctx
+    ctx.prepare(backward=True)
+    ctx.recording = True
+    xt = torch.from_numpy(x).cuda()
+    f = model.extractor.forward_nhwc(xt)
+    rpn_locs, rpn_scores, _, _, _, _ = model.rpn.forward_nhwc(f, x.shape[2:], np.ones(2))
+    up = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    chain.cleargrads()
+    loss = chain.forward_with_targets(f, rpn_locs, rpn_scores, up(rois), up(idx), up(gt_roi_locs),
+                                      up(gt_roi_labels), up(gt_roi_masks), up(gt_rpn_locs),
+                                      up(gt_rpn_labels))
+    ctx.recording = False
+    for k in ('rpn_loc_loss', 'rpn_cls_loss', 'roi_loc_loss', 'roi_cls_loss', 'roi_mask_loss'):
+        got = float(chain.observation[k].item())
+        assert abs(got - float(want_losses[k])) <= 2e-3 * max(abs(float(want_losses[k])), 1e-3), k
+    assert abs(loss.item() - float(want_losses['loss'])) <= 2e-3 * float(want_losses['loss'])
+    loss.backward()
+    torch.cuda.synchronize()
+    sd_names = set(ctx.train.names())
+    assert set(want_grads) == sd_names
+    worst, l2 = {}, {}
+    for name in sorted(want_grads):
+        kind = ctx.kinds[name][0]
+        g = ctx.grad(name)
+        if kind == 'conv':
+            g = g.permute(0, 3, 1, 2)
+        elif kind == 'deconv':
+            g = g.permute(2, 1, 0).reshape(ctx.kinds[name][1])
+        else:
+            g = g.reshape(ctx.kinds[name][1])
+        worst[name] = rel(g, want_grads[name])
+        gn = g.detach().cpu().numpy().astype(np.float64)
+        l2[name] = float(np.linalg.norm(gn - want_grads[name]) /
+                         max(np.linalg.norm(want_grads[name]), 1e-30))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                           'gpurun_out')
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, 'grad_errors.json'), 'w') as fjs:
+            json.dump({'max_rel': worst, 'l2_rel': l2}, fjs, indent=1, sort_keys=True)
+    # The backward pass chains ~35 TF32 GEMMs behind ~50 forward ones, and a forward
+    # activation that differs by 1e-3 flips a few ReLU gates, which moves single
+    # gradient entries by O(1) of their size: bound the relative L2 error at 3e-2 and
+    # the worst entry at 5e-2 of max|grad| per tensor (measured: growing smoothly from
+    # 6e-4 next to the losses to 2e-2 at res3).  The next test removes the gate flips
+    # and holds the backward kernels to 3e-3.
+    bad = {k: (worst[k], l2[k]) for k in worst if not (worst[k] <= 5e-2 and l2[k] <= 3e-2)}
+    assert not bad, bad
+    # the layers next to the losses are one or two GEMMs deep: hold them tighter
+    for name in ('head/mask/W', 'head/cls_loc/W', 'head/score/W', 'rpn/loc/W', 'rpn/score/W',
+                 'head/mask/b', 'head/cls_loc/b', 'rpn/loc/b'):
+        assert worst[name] <= 5e-3, (name, worst[name])
+
+
+def _np_nchw(t):
+    return np.ascontiguousarray(t.detach().permute(0, 3, 1, 2).cpu().numpy())
+
+
+def test_backward_on_identical_activations(setup):
+    """Backward kernels alone: the oracle's backward is evaluated on the activations the
+    CUDA forward produced (same ReLU gates, same GEMM inputs), so only the TF32 products
+    and the accumulation order of the backward GEMMs differ."""
+    from oracle import nn as onn
+    cfg, params, model, x, rs = setup
+    chain = models.MaskRCNNTrainChain(model)
+    ctx = model.ctx
+    ctx.prepare(backward=True)
+    ctx.recording = True
+    f = model.extractor.forward_nhwc(torch.from_numpy(x).cuda())
+    rpn_locs, rpn_scores, _, _, _, _ = model.rpn.forward_nhwc(f, x.shape[2:], np.ones(2))
+    n_anchor = f.shape[1] * f.shape[2] * cfg.n_anchor
+    (rois, idx, gt_roi_locs, gt_roi_labels, gt_roi_masks, gt_rpn_locs,
+     gt_rpn_labels) = _targets(cfg, np.random.RandomState(11), x, 2 * n_anchor)
+    up = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    chain.cleargrads()
+    loss = chain.forward_with_targets(f, rpn_locs, rpn_scores, up(rois), up(idx), up(gt_roi_locs),
+                                      up(gt_roi_labels), up(gt_roi_masks), up(gt_rpn_locs),
+                                      up(gt_rpn_labels))
+    ctx.recording = False
+    # ---- harvest the CUDA forward's activations into the oracle's cache format
+    def block_caches(bb):
+        return [tuple(_np_nchw(t) for t in b.saved) for b in bb.blocks]
+    caches = {'res3': block_caches(model.extractor.res3), 'res4': block_caches(model.extractor.res4)}
+    hs = model.head.saved
+    res5_caches = block_caches(model.head.res5)
+    pool7 = res5_caches[0][0]
+    pool14 = np.zeros(pool7.shape[:2] + (14, 14), np.float32)
+    pool14[:, :, ::2, ::2] = pool7
+    res5_caches[0] = (pool14,) + res5_caches[0][1:]
+    idx_rois = np.concatenate((idx.astype(np.float32)[:, None], rois), axis=1)
+    hc = dict(idx_rois=idx_rois, res5=_np_nchw(hs['res5']),
+              pool5=hs['pool5'].cpu().numpy()[:, :, None, None], d6=_np_nchw(hs['d6']),
+              blocks=res5_caches, feat_shape=_np_nchw(f).shape)
+    feat_np, h_np = (_np_nchw(t) for t in model.rpn.saved)
+    o = chain.outputs
+    _, g = om.train_losses(cfg, o['rpn_locs'].cpu().numpy(), o['rpn_scores'].cpu().numpy(),
+                           gt_rpn_locs, gt_rpn_labels, o['roi_cls_locs'].cpu().numpy(),
+                           o['roi_scores'].cpu().numpy(), _np_nchw(o['roi_masks']), gt_roi_locs,
+                           gt_roi_labels, gt_roi_masks)
+    want = {}
+    g_feat = om.head_backward(cfg, params, hc, g['roi_cls_locs'], g['roi_scores'], g['roi_masks'],
+                              want)
+    g_feat = g_feat + om.rpn_backward(cfg, params, feat_np, h_np, g['rpn_locs'], g['rpn_scores'],
+                                      want)
+    om.extractor_backward(cfg, params, caches, g_feat, want)
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {}
+    for name in sorted(want):
+        kind = ctx.kinds[name][0]
+        gt = ctx.grad(name)
+        if kind == 'conv':
+            gt = gt.permute(0, 3, 1, 2)
+        elif kind == 'deconv':
+            gt = gt.permute(2, 1, 0).reshape(ctx.kinds[name][1])
+        else:
+            gt = gt.reshape(ctx.kinds[name][1])
+        errs[name] = rel(gt, want[name])
+    bad = {k: v for k, v in errs.items() if not v <= 3e-3}
+    assert set(want) == set(ctx.train.names())
+    assert not bad, bad
+
+
+def test_sgd_update_matches_numpy(setup):
+    cfg, params, model, x, rs = setup
+    from chainer_mask_rcnn_b200 import optimizers
+    ctx = model.ctx
+    opt = optimizers.MomentumSGD(lr=0.01, momentum=0.9)
+    opt.setup(models.MaskRCNNTrainChain(model))
+    opt.add_hook(optimizers.WeightDecay(1e-4))
+    g = torch.Generator(device='cuda').manual_seed(1)
+    ctx.grads.copy_(torch.randn(ctx.grads.shape, device='cuda', generator=g))
+    p0 = ctx.train.data.clone()
+    frozen0 = ctx.frozen.data.clone()
+    v = torch.zeros_like(p0)
+    for _ in range(2):
+        gg = ctx.grads + 1e-4 * p0
+        v = 0.9 * v - 0.01 * gg
+        p0 = p0 + v
+        opt.update()
+    assert float((ctx.train.data - p0).abs().max()) <= 1e-6
+    assert torch.equal(ctx.frozen.data, frozen0)
+    model.load_state_dict(params)     # restore for other tests
+
+
+def test_full_train_chain_runs_and_decreases_loss():
+    """End-to-end __call__ with the host target creators (tiny image, random targets):
+    the loss is finite and a few SGD steps on a fixed batch reduce it."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(3)
+    np.random.seed(3)
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE)
+    chain = models.MaskRCNNTrainChain(model)
+    opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+    opt.add_hook(optimizers.WeightDecay(1e-4))
+    H, W = 160, 192
+    imgs = (rs.uniform(0, 255, (2, 3, H, W)) - 115.).astype(np.float32)
+    bboxes, labels, masks = [], [], []
+    for _ in range(2):
+        b = synth.random_boxes(rs, 3, H, W, 40., 120.)
+        b = b[(b[:, 2] - b[:, 0] > 8) & (b[:, 3] - b[:, 1] > 8)]
+        m = np.zeros((len(b), H, W), np.int32)
+        for i, (y1, x1, y2, x2) in enumerate(b.astype(int)):
+            m[i, y1:y2, x1:x2] = 1
+        bboxes.append(b); labels.append(rs.randint(0, N_FG, len(b)).astype(np.int32))
+        masks.append(m)
+    scales = np.ones(2, np.float32)
+    hist = []
+    for _ in range(6):
+        np.random.seed(7)
+        loss = opt.update(chain, imgs, bboxes, labels, masks, scales)
+        hist.append(loss.item())
+    assert all(np.isfinite(hist)), hist
+    assert hist[-1] < hist[0], hist
