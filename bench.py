@@ -268,14 +268,12 @@ def main():
     # end to end: images start in pinned host memory every step, the loss is read back
     e2e = None
     if not args.no_e2e:
-        h2d = [imgs_pinned.numel() * 4]
-        d2h = [4]
+        h2d, d2h = [0], [0]
 
         def step_e2e():
             loss = opt.update(chain, imgs_pinned, bboxes, labels, masks, scales)
-            t = chain.targets
-            h2d.append(sum(v.numel() * v.element_size() for v in t.values()))
-            d2h.append(BS * 2000 * 16 + BS * 4)        # proposals + counts for host sampling
+            h2d[0] = chain.h2d_bytes                    # images + ground truth + mask targets
+            d2h[0] = chain.d2h_bytes + 4                # sampled foreground RoIs + the loss
             losses.append(loss.array)
             return loss.item()
 
@@ -284,7 +282,7 @@ def main():
         ms_e2e, wall_e2e = timed(step_e2e, n_e2e)
         per = max(ms_e2e, wall_e2e) / n_e2e
         e2e = {'value': BS * world / (per * 1e-3), 'unit': 'images/s',
-               'h2d_bytes_per_step': int(h2d[0] + h2d[-1]), 'd2h_bytes_per_step': int(d2h[0] + d2h[-1]),
+               'h2d_bytes_per_step': int(h2d[0]), 'd2h_bytes_per_step': int(d2h[0]),
                'ms_per_step': per}
 
     if rank == 0:

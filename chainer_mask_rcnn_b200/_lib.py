@@ -14,6 +14,7 @@ c_float = ctypes.c_float
 c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
 c_longlong = ctypes.c_longlong
+c_ulonglong = ctypes.c_ulonglong
 
 # name -> (restype, argtypes); mirrors include/cmr_b200.h one to one.
 _SIGNATURES = {
@@ -60,6 +61,15 @@ _SIGNATURES = {
                              c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     'cmr_roi_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                              c_float, c_void_p, c_int, c_void_p, c_void_p]),
+    'cmr_anchor_targets_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'cmr_anchor_targets': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float,
+                                   c_float, c_int, c_float, c_float, c_float, c_ulonglong,
+                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'cmr_proposal_targets_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'cmr_proposal_targets': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_float, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_ulonglong, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'cmr_mask_loss': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, c_int, c_void_p, c_void_p]),
 }

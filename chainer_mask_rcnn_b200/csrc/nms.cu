@@ -308,6 +308,22 @@ int launch_nms(const float4* boxes, const int* n_arr, int n_max, int B, float th
 }
 
 }  // namespace
+
+// Shared with targets.cu: sorts `rows` independent key arrays of n_pad (power of two).
+int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {
+  const int chunk = n_pad < kSortChunk ? n_pad : kSortChunk;
+  const size_t smem = sizeof(unsigned long long) * chunk;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CMR_CUDA_TRY(cudaFuncSetAttribute(bitonic_sort_desc_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(unsigned long long) * kSortChunk)));
+    attr_set = true;
+  }
+  bitonic_sort_desc_kernel<<<rows, kSortThreads, smem, st>>>(keys, n_pad);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
 }  // namespace cmr
 
 using namespace cmr;
@@ -400,17 +416,8 @@ extern "C" int cmr_proposals(const float* loc, const float* score, const float* 
     CMR_LAUNCH_CHECK();
   }
   {
-    const int chunk = w.n_pad < kSortChunk ? w.n_pad : kSortChunk;
-    const size_t smem = sizeof(unsigned long long) * chunk;
-    static bool attr_set = false;
-    if (!attr_set) {
-      CMR_CUDA_TRY(cudaFuncSetAttribute(bitonic_sort_desc_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(unsigned long long) * kSortChunk)));
-      attr_set = true;
-    }
-    bitonic_sort_desc_kernel<<<B, kSortThreads, smem, st>>>(keys, w.n_pad);
-    CMR_LAUNCH_CHECK();
+    int rc = launch_sort_desc_u64(keys, w.n_pad, B, st);
+    if (rc != CMR_OK) return rc;
   }
   {
     dim3 grid(ceil_div(n_pre, 256), B);

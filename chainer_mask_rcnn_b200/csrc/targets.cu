@@ -1,0 +1,367 @@
+// Training-target creation on the device (sm_100a), so that the train step has no
+// host-side NumPy pass between the RPN and the RoI head:
+//
+//   cmr_anchor_targets    chainercv AnchorTargetCreator as called per image at
+//                         chainer_mask_rcnn/models/mask_rcnn_train_chain.py:151-158
+//   cmr_proposal_targets  ProposalTargetCreator.__call__ minus the mask rasterisation
+//                         (models/utils/proposal_target_creator.py:115-161)
+//
+// Both are integer/index work around an IoU matrix that is never materialised: each
+// thread owns one anchor / candidate RoI and walks the (few dozen) ground-truth boxes
+// held in shared memory.  IoU follows chainercv.utils.bbox_iou in fp32 without FMA
+// contraction (areas without +1).  Random subsampling ("np.random.choice(idx, k,
+// replace=False)") is a sort of (class, hash(seed, index), index) keys: the first k keys
+// of a class are a uniform random k-subset.  The reference draws from NumPy's global
+// Mersenne Twister on the host; which subset is drawn is not part of the parity
+// contract, its size and eligibility rules are.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cmr {
+
+// nms.cu: descending bitonic sort of n_pad (power of two) 64-bit keys, one CTA per row.
+int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st);
+
+namespace {
+
+constexpr int kMaxGt = 256;
+
+__device__ __forceinline__ float iou_f(const float4 a, const float4 b) {  // (y1,x1,y2,x2)
+  const float tl_y = fmaxf(a.x, b.x), tl_x = fmaxf(a.y, b.y);
+  const float br_y = fminf(a.z, b.z), br_x = fminf(a.w, b.w);
+  float inter = __fmul_rn(__fsub_rn(br_y, tl_y), __fsub_rn(br_x, tl_x));
+  if (!(tl_y < br_y && tl_x < br_x)) inter = __fmul_rn(inter, 0.0f);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+__device__ __forceinline__ unsigned int hash31(unsigned long long seed, unsigned long long i) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);  // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 33) | 1u;  // 31 bits, never zero
+}
+
+// chainercv bbox2loc(src, dst) in fp32.
+__device__ __forceinline__ float4 box2loc(const float4 s, const float4 d) {
+  float h = __fsub_rn(s.z, s.x), w = __fsub_rn(s.w, s.y);
+  const float cy = __fadd_rn(s.x, __fmul_rn(0.5f, h)), cx = __fadd_rn(s.y, __fmul_rn(0.5f, w));
+  const float bh = __fsub_rn(d.z, d.x), bw = __fsub_rn(d.w, d.y);
+  const float bcy = __fadd_rn(d.x, __fmul_rn(0.5f, bh)), bcx = __fadd_rn(d.y, __fmul_rn(0.5f, bw));
+  const float eps = 1.1920929e-07f;
+  h = fmaxf(h, eps);
+  w = fmaxf(w, eps);
+  return make_float4(__fdiv_rn(__fsub_rn(bcy, cy), h), __fdiv_rn(__fsub_rn(bcx, cx), w),
+                     logf(__fdiv_rn(bh, h)), logf(__fdiv_rn(bw, w)));
+}
+
+__device__ __forceinline__ void load_gt(const float4* __restrict__ bbox, int n, float4* sm) {
+  for (int g = threadIdx.x; g < n; g += blockDim.x) sm[g] = bbox[g];
+  __syncthreads();
+}
+
+// ------------------------------------------------------------ anchor targets --
+// Pass 1: per-gt maximum IoU over the inside anchors (as uint bits: IoU >= 0).
+__global__ void __launch_bounds__(256)
+anchor_gtmax_kernel(const float4* __restrict__ anchor, int S, const float4* __restrict__ bbox,
+                    const int* __restrict__ n_bbox, int G, float img_h, float img_w,
+                    unsigned int* __restrict__ gt_max) {
+  __shared__ float4 gt[kMaxGt];
+  __shared__ unsigned int smax[kMaxGt];
+  const int b = blockIdx.y;
+  const int n = min(n_bbox[b], G);
+  load_gt(bbox + (size_t)b * G, n, gt);
+  for (int g = threadIdx.x; g < n; g += blockDim.x) smax[g] = 0u;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) {
+    const float4 a = __ldg(anchor + i);
+    if (a.x >= 0.f && a.y >= 0.f && a.z <= img_h && a.w <= img_w)
+      for (int g = 0; g < n; ++g) {
+        const float v = iou_f(a, gt[g]);
+        if (v > 0.f) atomicMax(&smax[g], __float_as_uint(v));
+      }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < n; g += blockDim.x)
+    if (smax[g]) atomicMax(gt_max + (size_t)b * G + g, smax[g]);
+}
+
+// Pass 2: labels, box targets, sort keys, class counts.
+__global__ void __launch_bounds__(256)
+anchor_label_kernel(const float4* __restrict__ anchor, int S, int n_pad,
+                    const float4* __restrict__ bbox, const int* __restrict__ n_bbox, int G,
+                    float img_h, float img_w, float pos_iou, float neg_iou,
+                    const unsigned int* __restrict__ gt_max, unsigned long long seed,
+                    float4* __restrict__ gt_loc, int* __restrict__ gt_label,
+                    unsigned long long* __restrict__ keys, int* __restrict__ counts) {
+  __shared__ float4 gt[kMaxGt];
+  __shared__ float gmax[kMaxGt];
+  const int b = blockIdx.y;
+  const int n = min(n_bbox[b], G);
+  load_gt(bbox + (size_t)b * G, n, gt);
+  for (int g = threadIdx.x; g < n; g += blockDim.x)
+    gmax[g] = __uint_as_float(gt_max[(size_t)b * G + g]);
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int label = -1;
+  unsigned long long key = 0ull;
+  if (i < S) {
+    const float4 a = __ldg(anchor + i);
+    float4 loc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n > 0 && a.x >= 0.f && a.y >= 0.f && a.z <= img_h && a.w <= img_w) {
+      float best = -1.f;
+      int arg = 0;
+      bool is_gt_best = false;
+      for (int g = 0; g < n; ++g) {
+        const float v = iou_f(a, gt[g]);
+        if (v > best) {
+          best = v;
+          arg = g;
+        }
+        is_gt_best |= (v == gmax[g]);
+      }
+      if (best < neg_iou) label = 0;
+      if (is_gt_best) label = 1;
+      if (best >= pos_iou) label = 1;
+      loc = box2loc(a, gt[arg]);
+      const unsigned long long r = hash31(seed, (unsigned long long)b * S + i);
+      if (label == 1) key = (1ull << 63) | (r << 32) | (unsigned int)i;
+      if (label == 0) key = (r << 32) | (unsigned int)i;
+    }
+    gt_loc[(size_t)b * S + i] = loc;
+    gt_label[(size_t)b * S + i] = label;
+  }
+  if (i < n_pad) keys[(size_t)b * n_pad + i] = key;
+  const int np = __syncthreads_count(label == 1);
+  const int nn = __syncthreads_count(label == 0);
+  if (threadIdx.x == 0) {
+    if (np) atomicAdd(counts + 2 * b, np);
+    if (nn) atomicAdd(counts + 2 * b + 1, nn);
+  }
+}
+
+// Pass 3 (after the sort): positives beyond the budget and negatives beyond what is
+// left of n_sample are set to "ignore".
+__global__ void __launch_bounds__(256)
+anchor_subsample_kernel(const unsigned long long* __restrict__ keys, int n_pad, int S,
+                        const int* __restrict__ counts, int n_sample, int max_pos,
+                        int* __restrict__ gt_label) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_pad) return;
+  const unsigned long long key = keys[(size_t)b * n_pad + k];
+  if (key == 0ull) return;
+  const int n_pos = counts[2 * b];
+  const int kept_pos = min(n_pos, max_pos);
+  const int idx = (int)(key & 0xffffffffull);
+  const bool drop = (key >> 63) ? (k >= max_pos) : (k - n_pos >= n_sample - kept_pos);
+  if (drop) gt_label[(size_t)b * S + idx] = -1;
+}
+
+// ---------------------------------------------------------- proposal targets --
+// Candidates of image b: its proposals followed by its ground-truth boxes.
+__device__ __forceinline__ float4 candidate(const float4* __restrict__ rois, int n_roi,
+                                            const float4* gt, int c) {
+  return c < n_roi ? __ldg(rois + c) : gt[c - n_roi];
+}
+
+__global__ void __launch_bounds__(256)
+proposal_assign_kernel(const float4* __restrict__ rois, const int* __restrict__ n_roi_arr,
+                       int roi_stride, const float4* __restrict__ bbox,
+                       const int* __restrict__ n_bbox, int G, int n_pad, float pos_iou,
+                       float neg_hi, float neg_lo, unsigned long long seed,
+                       int* __restrict__ assign, unsigned long long* __restrict__ keys,
+                       int* __restrict__ counts) {
+  __shared__ float4 gt[kMaxGt];
+  const int b = blockIdx.y;
+  const int n = min(n_bbox[b], G);
+  const int n_roi = min(n_roi_arr[b], roi_stride);
+  load_gt(bbox + (size_t)b * G, n, gt);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int cls = -1;
+  unsigned long long key = 0ull;
+  if (c < n_roi + n && n > 0) {
+    const float4 box = candidate(rois + (size_t)b * roi_stride, n_roi, gt, c);
+    float best = -INFINITY;
+    int arg = 0;
+    for (int g = 0; g < n; ++g) {
+      const float v = iou_f(box, gt[g]);
+      if (v > best || (v != v && best == best)) {  // NaN ranks highest, like numpy argmax
+        best = v;
+        arg = g;
+      }
+    }
+    assign[(size_t)b * n_pad + c] = arg;
+    if (best >= pos_iou) cls = 1;
+    else if (best < neg_hi && best >= neg_lo) cls = 0;
+    const unsigned long long r = hash31(seed, (unsigned long long)b * n_pad + c);
+    if (cls == 1) key = (1ull << 63) | (r << 32) | (unsigned int)c;
+    if (cls == 0) key = (r << 32) | (unsigned int)c;
+  }
+  if (c < n_pad) keys[(size_t)b * n_pad + c] = key;
+  const int np = __syncthreads_count(cls == 1);
+  const int nn = __syncthreads_count(cls == 0);
+  if (threadIdx.x == 0) {
+    if (np) atomicAdd(counts + 2 * b, np);
+    if (nn) atomicAdd(counts + 2 * b + 1, nn);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+proposal_emit_targets_kernel(const unsigned long long* __restrict__ keys, int n_pad,
+                             const int* __restrict__ assign, const int* __restrict__ counts,
+                             const float4* __restrict__ rois, const int* __restrict__ n_roi_arr,
+                             int roi_stride, const float4* __restrict__ bbox,
+                             const int* __restrict__ label, const int* __restrict__ n_bbox, int G,
+                             int n_sample, int max_pos, float4 mean, float4 stdv,
+                             float4* __restrict__ sample_roi, float4* __restrict__ gt_loc,
+                             int* __restrict__ gt_label, int* __restrict__ gt_assign,
+                             int* __restrict__ n_pos_out) {
+  __shared__ float4 gt[kMaxGt];
+  const int b = blockIdx.y;
+  const int n = min(n_bbox[b], G);
+  const int n_roi = min(n_roi_arr[b], roi_stride);
+  load_gt(bbox + (size_t)b * G, n, gt);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_sample) return;
+  const int n_pos = counts[2 * b], n_neg = counts[2 * b + 1];
+  const int kept_pos = min(n_pos, max_pos);
+  const int kept_neg = min(n_sample - kept_pos, n_neg);
+  if (j == 0) n_pos_out[b] = kept_pos;
+  float4 box = make_float4(0.f, 0.f, 0.f, 0.f), loc = box;
+  int lab = -1, asg = -1;
+  if (j < kept_pos + kept_neg) {
+    const int k = j < kept_pos ? j : n_pos + (j - kept_pos);
+    const int c = (int)(keys[(size_t)b * n_pad + k] & 0xffffffffull);
+    const int g = assign[(size_t)b * n_pad + c];
+    box = candidate(rois + (size_t)b * roi_stride, n_roi, gt, c);
+    const float4 l = box2loc(box, gt[g]);
+    loc = make_float4(__fdiv_rn(__fsub_rn(l.x, mean.x), stdv.x), __fdiv_rn(__fsub_rn(l.y, mean.y), stdv.y),
+                      __fdiv_rn(__fsub_rn(l.z, mean.z), stdv.z), __fdiv_rn(__fsub_rn(l.w, mean.w), stdv.w));
+    if (j < kept_pos) {
+      lab = __ldg(label + (size_t)b * G + g) + 1;
+      asg = g;
+    } else {
+      lab = 0;
+    }
+  }
+  const size_t o = (size_t)b * n_sample + j;
+  sample_roi[o] = box;
+  gt_loc[o] = loc;
+  gt_label[o] = lab;
+  gt_assign[o] = asg;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+}  // namespace cmr
+
+using namespace cmr;
+
+extern "C" size_t cmr_anchor_targets_workspace_bytes(int B, int n_anchor, int max_bbox) {
+  if (B <= 0 || n_anchor <= 0 || max_bbox <= 0) return 256;
+  return align_up(sizeof(unsigned long long) * (size_t)B * next_pow2(n_anchor), 256) +
+         align_up(sizeof(unsigned int) * (size_t)B * max_bbox, 256) + align_up(8 * (size_t)B, 256);
+}
+
+extern "C" int cmr_anchor_targets(const float* anchor, int n_anchor, const float* bbox,
+                                  const int32_t* n_bbox, int B, int max_bbox, float img_h,
+                                  float img_w, int n_sample, float pos_iou_thresh,
+                                  float neg_iou_thresh, float pos_ratio, unsigned long long seed,
+                                  float* gt_loc, int32_t* gt_label, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  CMR_REQUIRE(anchor && bbox && n_bbox && gt_loc && gt_label && workspace);
+  CMR_REQUIRE(B > 0 && n_anchor > 0 && max_bbox > 0 && max_bbox <= kMaxGt && n_sample > 0);
+  CMR_REQUIRE(((reinterpret_cast<uintptr_t>(anchor) | reinterpret_cast<uintptr_t>(bbox) |
+                reinterpret_cast<uintptr_t>(gt_loc)) & 15) == 0);
+  if (workspace_bytes < cmr_anchor_targets_workspace_bytes(B, n_anchor, max_bbox))
+    return CMR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int n_pad = next_pow2(n_anchor);
+  char* ws = reinterpret_cast<char*>(workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+  ws += align_up(sizeof(unsigned long long) * (size_t)B * n_pad, 256);
+  unsigned int* gt_max = reinterpret_cast<unsigned int*>(ws);
+  ws += align_up(sizeof(unsigned int) * (size_t)B * max_bbox, 256);
+  int* counts = reinterpret_cast<int*>(ws);
+  CMR_CUDA_TRY(cudaMemsetAsync(gt_max, 0, sizeof(unsigned int) * (size_t)B * max_bbox, st));
+  CMR_CUDA_TRY(cudaMemsetAsync(counts, 0, 8 * (size_t)B, st));
+  const float4* a4 = reinterpret_cast<const float4*>(anchor);
+  const float4* b4 = reinterpret_cast<const float4*>(bbox);
+  dim3 grid(ceil_div(n_pad, 256), B);
+  anchor_gtmax_kernel<<<dim3(ceil_div(n_anchor, 256), B), 256, 0, st>>>(
+      a4, n_anchor, b4, n_bbox, max_bbox, img_h, img_w, gt_max);
+  CMR_LAUNCH_CHECK();
+  anchor_label_kernel<<<grid, 256, 0, st>>>(a4, n_anchor, n_pad, b4, n_bbox, max_bbox, img_h,
+                                           img_w, pos_iou_thresh, neg_iou_thresh, gt_max, seed,
+                                           reinterpret_cast<float4*>(gt_loc), gt_label, keys,
+                                           counts);
+  CMR_LAUNCH_CHECK();
+  int rc = launch_sort_desc_u64(keys, n_pad, B, st);
+  if (rc != CMR_OK) return rc;
+  anchor_subsample_kernel<<<grid, 256, 0, st>>>(keys, n_pad, n_anchor, counts, n_sample,
+                                               (int)(pos_ratio * n_sample), gt_label);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+extern "C" size_t cmr_proposal_targets_workspace_bytes(int B, int max_roi, int max_bbox) {
+  if (B <= 0 || max_roi <= 0 || max_bbox <= 0) return 256;
+  const size_t n_pad = next_pow2(max_roi + max_bbox);
+  return align_up(sizeof(unsigned long long) * B * n_pad, 256) +
+         align_up(sizeof(int) * B * n_pad, 256) + align_up(8 * (size_t)B, 256);
+}
+
+extern "C" int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int max_roi,
+                                    const float* bbox, const int32_t* label,
+                                    const int32_t* n_bbox, int B, int max_bbox, int n_sample,
+                                    float pos_ratio, float pos_iou_thresh, float neg_iou_thresh_hi,
+                                    float neg_iou_thresh_lo, const float* loc_mean,
+                                    const float* loc_std, unsigned long long seed,
+                                    float* sample_roi, float* gt_roi_loc, int32_t* gt_roi_label,
+                                    int32_t* gt_assign, int32_t* n_pos, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  CMR_REQUIRE(rois && n_roi && bbox && label && n_bbox && loc_mean && loc_std && workspace);
+  CMR_REQUIRE(sample_roi && gt_roi_loc && gt_roi_label && gt_assign && n_pos);
+  CMR_REQUIRE(B > 0 && max_roi > 0 && max_bbox > 0 && max_bbox <= kMaxGt && n_sample > 0);
+  CMR_REQUIRE(((reinterpret_cast<uintptr_t>(rois) | reinterpret_cast<uintptr_t>(bbox) |
+                reinterpret_cast<uintptr_t>(sample_roi) | reinterpret_cast<uintptr_t>(gt_roi_loc)) &
+               15) == 0);
+  if (workspace_bytes < cmr_proposal_targets_workspace_bytes(B, max_roi, max_bbox))
+    return CMR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int n_pad = next_pow2(max_roi + max_bbox);
+  char* ws = reinterpret_cast<char*>(workspace);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+  ws += align_up(sizeof(unsigned long long) * (size_t)B * n_pad, 256);
+  int* assign = reinterpret_cast<int*>(ws);
+  ws += align_up(sizeof(int) * (size_t)B * n_pad, 256);
+  int* counts = reinterpret_cast<int*>(ws);
+  CMR_CUDA_TRY(cudaMemsetAsync(counts, 0, 8 * (size_t)B, st));
+  const float4* r4 = reinterpret_cast<const float4*>(rois);
+  const float4* b4 = reinterpret_cast<const float4*>(bbox);
+  proposal_assign_kernel<<<dim3(ceil_div(n_pad, 256), B), 256, 0, st>>>(
+      r4, n_roi, max_roi, b4, n_bbox, max_bbox, n_pad, pos_iou_thresh, neg_iou_thresh_hi,
+      neg_iou_thresh_lo, seed, assign, keys, counts);
+  CMR_LAUNCH_CHECK();
+  int rc = launch_sort_desc_u64(keys, n_pad, B, st);
+  if (rc != CMR_OK) return rc;
+  const float4 mean = make_float4(loc_mean[0], loc_mean[1], loc_mean[2], loc_mean[3]);
+  const float4 stdv = make_float4(loc_std[0], loc_std[1], loc_std[2], loc_std[3]);
+  proposal_emit_targets_kernel<<<dim3(ceil_div(n_sample, 256), B), 256, 0, st>>>(
+      keys, n_pad, assign, counts, r4, n_roi, max_roi, b4, label, n_bbox, max_bbox, n_sample,
+      (int)nearbyintf(n_sample * pos_ratio), mean, stdv, reinterpret_cast<float4*>(sample_roi),
+      reinterpret_cast<float4*>(gt_roi_loc), gt_roi_label, gt_assign, n_pos);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}

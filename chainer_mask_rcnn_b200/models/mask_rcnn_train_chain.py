@@ -4,8 +4,13 @@ Mirrors ``MaskRCNNTrainChain`` (chainer_mask_rcnn/models/mask_rcnn_train_chain.p
 25-189).  ``__call__(imgs, bboxes, labels, masks, scales)`` returns the scalar loss
 (rpn_loc + rpn_cls + roi_loc + roi_cls + roi_mask, unweighted, :180-181) as a
 :class:`Loss`; ``loss.backward()`` runs the static backward schedule and fills the
-flat gradient buffer.  The two target creators stay on the host, as in the
-reference (:126-158); AnchorTargetCreator runs while the GPU computes the backbone.
+flat gradient buffer.
+
+Targets.  By default anchors and proposals are labelled / sampled on the device
+(models/utils/device_targets.py, csrc/targets.cu) and only the mask-target
+rasterisation runs on the host (cv2, as in the reference), overlapped with the head's
+forward pass.  Passing the host ``AnchorTargetCreator`` / ``ProposalTargetCreator``
+objects instead reproduces the reference's NumPy-seeded sampling exactly (:126-158).
 """
 import numpy as np
 import torch
@@ -14,8 +19,9 @@ from . import engine as E
 from .. import _lib
 from ..utils import config
 from .mask_rcnn import as_device_f32
-from .utils import AnchorTargetCreator
-from .utils import ProposalTargetCreator
+from .utils import DeviceAnchorTargetCreator
+from .utils import DeviceProposalTargetCreator
+from .utils import GroundTruth
 
 LOSS_NAMES = ('rpn_loc_loss', 'rpn_cls_loss', 'roi_loc_loss', 'roi_cls_loss', 'roi_mask_loss')
 
@@ -50,24 +56,34 @@ def _host(a):
 class MaskRCNNTrainChain(object):
 
     def __init__(self, mask_rcnn, rpn_sigma=3., roi_sigma=1., anchor_target_creator=None,
-                 proposal_target_creator=None):
+                 proposal_target_creator=None, seed=0):
         self.mask_rcnn = mask_rcnn
         self.ctx = mask_rcnn.ctx
         self.rpn_sigma = rpn_sigma
         self.roi_sigma = roi_sigma
-        self.anchor_target_creator = anchor_target_creator or AnchorTargetCreator()
-        self.proposal_target_creator = proposal_target_creator or ProposalTargetCreator()
+        self.anchor_target_creator = anchor_target_creator or DeviceAnchorTargetCreator()
+        self.proposal_target_creator = proposal_target_creator or DeviceProposalTargetCreator()
         self.loc_normalize_mean = mask_rcnn.loc_normalize_mean
         self.loc_normalize_std = mask_rcnn.loc_normalize_std
         self.observation = {}
         self.targets = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._seed = int(seed)
+        self._calls = 0
+        self._pinned = {}
+        self._roi_index = {}
 
     def cleargrads(self):
         self.ctx.grads.zero_()
 
+    # ------------------------------------------------------------------ call --
     def __call__(self, imgs, bboxes, labels, masks, scales):
         m, ctx = self.mask_rcnn, self.ctx
         ctx.prepare(backward=True)
+        self.h2d_bytes = self.d2h_bytes = 0
+        if not (isinstance(imgs, torch.Tensor) and imgs.is_cuda):
+            self.h2d_bytes += int(np.prod(imgs.shape)) * 4
         x = as_device_f32(imgs)
         dev = x.device
         scales = _host(scales)
@@ -75,55 +91,109 @@ class MaskRCNNTrainChain(object):
         img_size = (H, W)
         bboxes = [_host(b).astype(np.float32) for b in bboxes]
         labels = [_host(l) for l in labels]
-
+        self._calls += 1
         ctx.recording = True
         try:
             with config.using_config('train', True):
                 feat = m.extractor.forward_nhwc(x)
-                rpn_locs, rpn_scores, rois, _, cnt, (anchor_np, _) = m.rpn.forward_nhwc(
+                rpn_locs, rpn_scores, rois, _, cnt, (anchor_np, anchor) = m.rpn.forward_nhwc(
                     feat, img_size, scales)
-            # RPN targets need only the ground truth: computed while the GPU is busy
-            gt_rpn = [self.anchor_target_creator(b, anchor_np, img_size) for b in bboxes]
-            gt_rpn_locs = np.concatenate([g[0] for g in gt_rpn]).astype(np.float32)
-            gt_rpn_labels = np.concatenate([g[1] for g in gt_rpn]).astype(np.int32)
+            dev_anchor = isinstance(self.anchor_target_creator, DeviceAnchorTargetCreator)
+            dev_prop = isinstance(self.proposal_target_creator, DeviceProposalTargetCreator)
+            gt = None
+            if dev_anchor or dev_prop:
+                gt = GroundTruth(bboxes, labels, dev)
+                self.h2d_bytes += gt.nbytes
+            seed = (self._seed << 20) + 2 * self._calls
+            # ---- RPN targets
+            if dev_anchor:
+                gt_rpn_locs, gt_rpn_labels = self.anchor_target_creator(gt, anchor, img_size, seed)
+                gt_rpn_locs = gt_rpn_locs.view(-1, 4)
+                gt_rpn_labels = gt_rpn_labels.view(-1)
+            else:
+                pairs = [self.anchor_target_creator(b, anchor_np, img_size) for b in bboxes]
+                gt_rpn_locs = self._upload(np.concatenate([p[0] for p in pairs]), np.float32, dev)
+                gt_rpn_labels = self._upload(np.concatenate([p[1] for p in pairs]), np.int32, dev)
+            # ---- RoI sampling + head targets
+            if dev_prop:
+                ptc = self.proposal_target_creator
+                sroi, gloc, glab, gasg, npos = ptc.sample(rois, cnt, gt, seed + 1,
+                                                          self.loc_normalize_mean,
+                                                          self.loc_normalize_std)
+                n = sroi.shape[1]
+                max_pos = int(np.round(ptc.n_sample * ptc.pos_ratio))
+                h_roi = self._pinned_like('roi', (batch_size, max_pos, 4), torch.float32)
+                h_asg = self._pinned_like('asg', (batch_size, max_pos), torch.int32)
+                h_np = self._pinned_like('np', (batch_size,), torch.int32)
+                h_roi.copy_(sroi[:, :max_pos], non_blocking=True)
+                h_asg.copy_(gasg[:, :max_pos], non_blocking=True)
+                h_np.copy_(npos, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record()
+                self.d2h_bytes += h_roi.numel() * 4 + h_asg.numel() * 4 + h_np.numel() * 4
+                key = (batch_size, n, str(dev))
+                if key not in self._roi_index:
+                    self._roi_index[key] = torch.arange(batch_size, dtype=torch.int32, device=dev) \
+                        .repeat_interleave(n)
+                sample_rois = sroi.view(-1, 4)
+                sample_idx = self._roi_index[key]
+                gt_roi_locs, gt_roi_labels = gloc.view(-1, 4), glab.view(-1)
 
-            rois_h = rois.cpu().numpy()           # host sync: proposals are sampled on the host
-            counts = cnt.cpu().numpy()
-            s_rois, s_idx, gt_locs, gt_labels, gt_masks = [], [], [], [], []
-            for i in range(batch_size):
-                sr, gl, glab, gm = self.proposal_target_creator(
+                def gt_roi_masks():
+                    # runs after the head's forward pass has been enqueued
+                    ready.synchronize()
+                    mt = ptc.mask_targets(h_roi.numpy(), h_asg.numpy(), h_np.numpy(), masks)
+                    full = np.full((batch_size, n, ptc.mask_size, ptc.mask_size), -1, np.int32)
+                    full[:, :max_pos] = mt
+                    return self._upload(full.reshape(-1, ptc.mask_size, ptc.mask_size), np.int32,
+                                        dev)
+            else:
+                rois_h = rois.cpu().numpy()       # host sync: proposals are sampled on the host
+                counts = cnt.cpu().numpy()
+                self.d2h_bytes += rois_h.nbytes + counts.nbytes
+                parts = [self.proposal_target_creator(
                     rois_h[i, :counts[i]], bboxes[i], labels[i], masks[i],
-                    self.loc_normalize_mean, self.loc_normalize_std)
-                s_rois.append(sr)
-                s_idx.append(np.full((len(sr),), i, dtype=np.int32))
-                gt_locs.append(gl)
-                gt_labels.append(glab)
-                gt_masks.append(gm)
-            up = lambda parts, dt: torch.from_numpy(  # noqa: E731
-                np.ascontiguousarray(np.concatenate(parts, axis=0), dtype=dt)).to(dev, non_blocking=True)
-            sample_rois = up(s_rois, np.float32)
-            sample_idx = up(s_idx, np.int32)
-            gt_roi_locs = up(gt_locs, np.float32)
-            gt_roi_labels = up(gt_labels, np.int32)
-            gt_roi_masks = up(gt_masks, np.int32)
-            gt_rpn_locs_d = torch.from_numpy(gt_rpn_locs).to(dev, non_blocking=True)
-            gt_rpn_labels_d = torch.from_numpy(gt_rpn_labels).to(dev, non_blocking=True)
+                    self.loc_normalize_mean, self.loc_normalize_std) for i in range(batch_size)]
+                sample_rois = self._upload(np.concatenate([p[0] for p in parts]), np.float32, dev)
+                sample_idx = self._upload(np.concatenate(
+                    [np.full((len(p[0]),), i, np.int32) for i, p in enumerate(parts)]), np.int32, dev)
+                gt_roi_locs = self._upload(np.concatenate([p[1] for p in parts]), np.float32, dev)
+                gt_roi_labels = self._upload(np.concatenate([p[2] for p in parts]), np.int32, dev)
+                gt_roi_masks = self._upload(np.concatenate([p[3] for p in parts]), np.int32, dev)
             self.targets = dict(sample_rois=sample_rois, sample_roi_indices=sample_idx,
                                 gt_roi_locs=gt_roi_locs, gt_roi_labels=gt_roi_labels,
-                                gt_roi_masks=gt_roi_masks, gt_rpn_locs=gt_rpn_locs_d,
-                                gt_rpn_labels=gt_rpn_labels_d)
+                                gt_roi_masks=gt_roi_masks, gt_rpn_locs=gt_rpn_locs,
+                                gt_rpn_labels=gt_rpn_labels)
             return self.forward_with_targets(feat, rpn_locs, rpn_scores, **self.targets)
         finally:
             ctx.recording = False
 
+    def _upload(self, a, dtype, dev):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        self.h2d_bytes += a.nbytes
+        return torch.from_numpy(a).to(dev, non_blocking=True)
+
+    def _pinned_like(self, key, shape, dtype):
+        buf = self._pinned.get(key)
+        if buf is None or tuple(buf.shape) != tuple(shape):
+            buf = torch.empty(shape, dtype=dtype).pin_memory()
+            self._pinned[key] = buf
+        return buf
+
     def forward_with_targets(self, feat, rpn_locs, rpn_scores, sample_rois, sample_roi_indices,
                              gt_roi_locs, gt_roi_labels, gt_roi_masks, gt_rpn_locs,
                              gt_rpn_labels):
-        """Head forward + losses for given samples/targets (everything on the device)."""
+        """Head forward + losses for given samples/targets (everything on the device).
+        ``gt_roi_masks`` may be a callable producing the tensor; it is called after the
+        head's forward pass has been enqueued, so host work inside it overlaps."""
         m, ctx = self.mask_rcnn, self.ctx
         dev = feat.device
         head, rpn = m.head, m.rpn
         cls_locs, scores, masks = head.forward_nhwc(feat, sample_rois, sample_roi_indices)
+        if callable(gt_roi_masks):
+            gt_roi_masks = gt_roi_masks()
+            if self.targets is not None:
+                self.targets['gt_roi_masks'] = gt_roi_masks
         R = cls_locs.shape[0]
         n, hh, ww, _ = feat.shape
         A = rpn.n_anchor

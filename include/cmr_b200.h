@@ -237,6 +237,41 @@ int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt_label,
                   const int32_t* gt_mask, int R, int HW, int n_fg, float* g,
                   int ld_g, float* losses, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Training targets on the device (csrc/targets.cu).  bbox (B,max_bbox,4) holds the
+ * ground-truth boxes (y1,x1,y2,x2) of each image padded to max_bbox <= 256 rows,
+ * n_bbox (B) their counts (device int32).  `seed` drives the random subsampling.
+ * ------------------------------------------------------------------------ */
+/* chainercv AnchorTargetCreator, called per image at
+ * chainer_mask_rcnn/models/mask_rcnn_train_chain.py:151-158, for the whole batch:
+ * gt_loc (B,n_anchor,4), gt_label (B,n_anchor) in {-1 ignore, 0, 1}. */
+size_t cmr_anchor_targets_workspace_bytes(int B, int n_anchor, int max_bbox);
+int cmr_anchor_targets(const float* anchor, int n_anchor, const float* bbox,
+                       const int32_t* n_bbox, int B, int max_bbox, float img_h,
+                       float img_w, int n_sample, float pos_iou_thresh,
+                       float neg_iou_thresh, float pos_ratio,
+                       unsigned long long seed, float* gt_loc, int32_t* gt_label,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* ProposalTargetCreator.__call__ up to the mask targets
+ * (chainer_mask_rcnn/models/utils/proposal_target_creator.py:115-161):
+ * rois (B,max_roi,4) + n_roi (B) as produced by cmr_proposals; label (B,max_bbox)
+ * foreground class ids; loc_mean / loc_std: HOST float[4].
+ * Outputs, n_sample rows per image, foreground rows first: sample_roi, gt_roi_loc
+ * (normalised), gt_roi_label (class+1, 0 = background, -1 = padding row when an
+ * image has too few candidates), gt_assign (ground-truth index of each foreground
+ * row, else -1), n_pos (B) foreground rows per image. */
+size_t cmr_proposal_targets_workspace_bytes(int B, int max_roi, int max_bbox);
+int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int max_roi,
+                         const float* bbox, const int32_t* label,
+                         const int32_t* n_bbox, int B, int max_bbox, int n_sample,
+                         float pos_ratio, float pos_iou_thresh,
+                         float neg_iou_thresh_hi, float neg_iou_thresh_lo,
+                         const float* loc_mean, const float* loc_std,
+                         unsigned long long seed, float* sample_roi,
+                         float* gt_roi_loc, int32_t* gt_roi_label,
+                         int32_t* gt_assign, int32_t* n_pos, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -277,15 +277,22 @@ def test_sgd_update_matches_numpy(setup):
     model.load_state_dict(params)     # restore for other tests
 
 
-def test_full_train_chain_runs_and_decreases_loss():
-    """End-to-end __call__ with the host target creators (tiny image, random targets):
-    the loss is finite and a few SGD steps on a fixed batch reduce it."""
+@pytest.mark.parametrize('targets', ['device', 'host'])
+def test_full_train_chain_runs_and_decreases_loss(targets):
+    """End-to-end __call__ (tiny image, random targets) with the device target creators
+    (default) and with the reference-order host ones: the loss is finite and a few SGD
+    steps on a fixed batch reduce it."""
     from chainer_mask_rcnn_b200 import optimizers
     rs = np.random.RandomState(3)
     np.random.seed(3)
     model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
                                   base_channels=BASE)
-    chain = models.MaskRCNNTrainChain(model)
+    if targets == 'host':
+        chain = models.MaskRCNNTrainChain(
+            model, anchor_target_creator=models.utils.AnchorTargetCreator(),
+            proposal_target_creator=models.utils.ProposalTargetCreator())
+    else:
+        chain = models.MaskRCNNTrainChain(model)
     opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
     opt.add_hook(optimizers.WeightDecay(1e-4))
     H, W = 160, 192
