@@ -14,15 +14,20 @@
 // (functions/affine_channel_2d.py:17-20), bias, residual add, ReLU and the ReLU
 // mask of the backward pass are fused in the epilogue.
 //
-// CTA = 192 threads:
-//   warps 0-3  A producers: cp.async 16 B gathers straight into the 128B-swizzled
-//              K-major tile the tensor core reads; afterwards the epilogue warps
-//              (TMEM lane quarter = warp id)
-//   warp  4    B producer: one thread issues TMA (cp.async.bulk.tensor.2d) loads
-//   warp  5    one thread issues tcgen05.mma (128 x BN x 8 per instruction) and
-//              tcgen05.commit; accumulator lives in TMEM (BN columns)
-// full/empty mbarrier ring of STAGES k-blocks (32 fp32 = one 128 B swizzle row).
-// Two CTAs are resident per SM, so one CTA's epilogue overlaps the other's MMAs.
+// Persistent, warp-specialised CTA (448 threads, one per SM) walking output tiles
+// (128 x BN) in n-fastest order:
+//   warps 0-3   A producers: cp.async 16 B gathers straight into the 128B-swizzled
+//               K-major tile the tensor core reads (implicit im2col, zero fill)
+//   warp  4     B producer: one thread issues TMA (cp.async.bulk.tensor.2d) loads
+//   warp  5     one thread issues tcgen05.mma (128 x BN x 8 per instruction) and
+//               tcgen05.commit; the accumulator lives in TMEM, double buffered
+//               (2 x BN columns) so tile i+1's MMAs overlap tile i's epilogue
+//   warps 6-13  epilogue: tcgen05.ld (lane = row) -> per-warp shared-memory
+//               transpose -> rows written as full 128 B lines (coalesced); the
+//               residual addend and the ReLU-mask operand are prefetched the same
+//               way before the accumulator is read
+// full/empty mbarrier ring of STAGES k-blocks (32 fp32 = one 128 B swizzle row)
+// shared by all tiles; tmem_full/tmem_empty barriers per accumulator buffer.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -44,28 +49,35 @@ struct ConvGemmParams {
   const float* addend;
   const float* mask;
   int relu, round_out;
+  int m_tiles, n_tiles;
 };
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;                      // fp32 per k-block = 128 bytes
 constexpr int kABytes = kBM * kBK * 4;       // 16 KB
 constexpr int kProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 6;                 // first epilogue warp
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 448
+constexpr int kXposePitch = 33;              // floats per row of the transpose buffer
 
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kABytes;
-  static constexpr int kBarOff = kBOff + STAGES * kBBytes;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kXposeOff = kBOff + STAGES * kBBytes;
+  static constexpr int kXposeBytes = kEpiWarps * 32 * kXposePitch * 4;
+  static constexpr int kBarOff = kXposeOff + kXposeBytes;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for 1024 B alignment
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES>;
+  constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -73,14 +85,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
   const uint32_t smem_base = raw_addr + pad;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
   const int num_kb = p.K / kBK;
+  const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap_b);
@@ -88,179 +100,240 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
       mbar_init(&full_bar[s], kProducerThreads + 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], kEpiWarps);
+    }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int ohw = p.out_h * p.out_w;
 
   if (warp < 4) {
     // ------------------------------------------------ A producer (im2col gather)
     const int t = threadIdx.x;
     const int j = t & 7;
     const int r0 = t >> 3;
-    int pix_base[8], iy0[8], ix0[8];
-    const int ohw = p.out_h * p.out_w;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int m = m0 + r0 + 16 * i;
-      if (m < p.M) {
-        const int img = m / ohw;
-        const int rem = m - img * ohw;
-        const int oy = rem / p.out_w;
-        const int ox = rem - oy * p.out_w;
-        pix_base[i] = img * p.in_h * p.in_w;
-        iy0[i] = oy * p.stride - p.pad;
-        ix0[i] = ox * p.stride - p.pad;
-      } else {
-        pix_base[i] = 0;
-        iy0[i] = -(1 << 28);  // never inside the image -> zero fill
-        ix0[i] = -(1 << 28);
-      }
-    }
     const uint32_t dst_off =
         (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
     const int cpt = p.in_c / kBK;  // k-blocks per filter tap
-    int fr = 0, fs = 0, cb = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t phase = (kb / STAGES) & 1;
-      mbar_wait(&empty_bar[s], phase ^ 1);
-      const uint32_t a_stage = smem_base + L::kAOff + s * kABytes + dst_off;
-      const float* src_c = p.a + cb * kBK + j * 4;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.n_tiles) * kBM;
+      int pix_base[8], iy0[8], ix0[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int iy = iy0[i] + fr, ix = ix0[i] + fs;
-        const bool ok = (unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w;
-        const float* src =
-            ok ? src_c + (size_t)(pix_base[i] + iy * p.in_w + ix) * p.in_ld : p.a;
-        cp_async_16(a_stage + i * 2048, src, ok ? 16u : 0u);
+        const int m = m0 + r0 + 16 * i;
+        if (m < p.M) {
+          const int img = m / ohw;
+          const int rem = m - img * ohw;
+          const int oy = rem / p.out_w;
+          const int ox = rem - oy * p.out_w;
+          pix_base[i] = img * p.in_h * p.in_w;
+          iy0[i] = oy * p.stride - p.pad;
+          ix0[i] = ox * p.stride - p.pad;
+        } else {
+          pix_base[i] = 0;
+          iy0[i] = -(1 << 28);  // never inside the image -> zero fill
+          ix0[i] = -(1 << 28);
+        }
       }
-      cp_async_mbar_arrive_noinc(&full_bar[s]);
-      if (++cb == cpt) {
-        cb = 0;
-        if (++fs == p.kw) {
-          fs = 0;
-          ++fr;
+      int fr = 0, fs = 0, cb = 0;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        const uint32_t a_stage = smem_base + L::kAOff + s * kABytes + dst_off;
+        const float* src_c = p.a + cb * kBK + j * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int iy = iy0[i] + fr, ix = ix0[i] + fs;
+          const bool ok = (unsigned)iy < (unsigned)p.in_h && (unsigned)ix < (unsigned)p.in_w;
+          const float* src =
+              ok ? src_c + (size_t)(pix_base[i] + iy * p.in_w + ix) * p.in_ld : p.a;
+          cp_async_16(a_stage + i * 2048, src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(&full_bar[s]);
+        if (++cb == cpt) {
+          cb = 0;
+          if (++fs == p.kw) {
+            fs = 0;
+            ++fr;
+          }
         }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-
-    // ------------------------------------------------------------- epilogue
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
-    size_t doff = 0;
-    const bool row_ok = row < p.M;
-    if (row_ok) {
-      const int img = row / ohw;
-      const int rem = row - img * ohw;
-      const int oy = rem / p.out_w;
-      const int ox = rem - oy * p.out_w;
-      doff = ((size_t)(img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w + ox * p.d_stride +
-              p.d_ox) * p.d_ld;
-    }
-    const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
-                        (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0) &&
-                        (!p.mask || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
-#pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      const int nc = n0 + chunk * 32;
-      if (nc >= p.N) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(chunk * 32), v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int n = nc + g * 4;
-        if (n >= p.N) break;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[g * 4 + e]);
-        const bool full4 = vec_ok && (n + 3 < p.N);
-        if (full4) {
-          if (p.scale) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-            o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w;
-          }
-          if (p.bias) {
-            const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            o[0] += bi.x; o[1] += bi.y; o[2] += bi.z; o[3] += bi.w;
-          }
-          if (p.addend) {
-            const float4 ad = __ldg(reinterpret_cast<const float4*>(p.addend + doff + n));
-            o[0] += ad.x; o[1] += ad.y; o[2] += ad.z; o[3] += ad.w;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-          }
-          if (p.mask) {
-            const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask + doff + n));
-            o[0] = mk.x > 0.f ? o[0] : 0.f; o[1] = mk.y > 0.f ? o[1] : 0.f;
-            o[2] = mk.z > 0.f ? o[2] : 0.f; o[3] = mk.w > 0.f ? o[3] : 0.f;
-          }
-          if (p.round_out) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
-          }
-          *reinterpret_cast<float4*>(p.d + doff + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int e = 0; e < 4 && n + e < p.N; ++e) {
-            float x = o[e];
-            if (p.scale) x *= __ldg(p.scale + n + e);
-            if (p.bias) x += __ldg(p.bias + n + e);
-            if (p.addend) x += __ldg(p.addend + doff + n + e);
-            if (p.relu) x = fmaxf(x, 0.f);
-            if (p.mask) x = __ldg(p.mask + doff + n + e) > 0.f ? x : 0.f;
-            if (p.round_out) x = round_tf32(x);
-            p.d[doff + n + e] = x;
-          }
-        }
-      }
-    }
   } else if (warp == 4) {
     // ------------------------------------------------------ B producer (TMA)
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t phase = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], L::kBBytes);
-        tma_load_2d(smem_base + L::kBOff + s * L::kBBytes, &tmap_b, &full_bar[s], kb * kBK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % p.n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], L::kBBytes);
+          tma_load_2d(smem_base + L::kBOff + s * L::kBBytes, &tmap_b, &full_bar[s], kb * kBK,
+                      n0);
+        }
       }
     }
-  } else {
+  } else if (warp == 5) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t phase = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], phase);
+    uint32_t it = 0, tc_ = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
+      const uint32_t buf = tc_ & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((tc_ >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint64_t da = make_smem_desc_sw128(smem_base + L::kAOff + s * kABytes, 16, 1024);
-        const uint64_t db =
-            make_smem_desc_sw128(smem_base + L::kBOff + s * L::kBBytes, 16, 1024);
+      const uint32_t acc = tmem_base + buf * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % STAGES;
+        const uint32_t phase = (it / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t da = make_smem_desc_sw128(smem_base + L::kAOff + s * kABytes, 16, 1024);
+          const uint64_t db =
+              make_smem_desc_sw128(smem_base + L::kBOff + s * L::kBBytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k)  // 8 tf32 = 32 bytes per MMA -> +2 (16 B units)
-          umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < kBK / 8; ++k)  // 8 tf32 = 32 bytes per MMA -> +2 (16 B units)
+            umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
       }
+      if (lane == 0) umma_commit(&tmem_full_bar[buf]);
       __syncwarp();
     }
-    if (lane == 0) umma_commit(tmem_full_bar);
-    __syncwarp();
+  } else {
+    // ------------------------------------------------------------- epilogue
+    const int ew = warp - kEpiWarp0;          // 0..7
+    const int q = warp & 3;                   // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                 // which half of the BN columns
+    float* xp = reinterpret_cast<float*>(smem + L::kXposeOff) + ew * 32 * kXposePitch;
+    const int sub = lane >> 3;                // row within a 4-row store group
+    const int c4 = (lane & 7) * 4;            // first of this lane's 4 columns in a chunk
+    const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
+                        (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0) &&
+                        (!p.mask || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
+    constexpr int kChunks = (BN / 2 + 31) / 32;   // 32-column chunks per half
+    uint32_t tc_ = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
+      const int m0 = (tile / p.n_tiles) * kBM;
+      const int n0 = (tile % p.n_tiles) * BN;
+      const uint32_t buf = tc_ & 1;
+      // output offsets of this lane's 8 rows (row = 32q + 4i + sub)
+      long long doff[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = m0 + q * 32 + 4 * i + sub;
+        if (row < p.M) {
+          const int img = row / ohw;
+          const int rem = row - img * ohw;
+          const int oy = rem / p.out_w;
+          const int ox = rem - oy * p.out_w;
+          doff[i] = ((long long)(img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w +
+                     ox * p.d_stride + p.d_ox) * p.d_ld;
+        } else {
+          doff[i] = -1;
+        }
+      }
+      bool waited = false;
+#pragma unroll 1
+      for (int chunk = 0; chunk < kChunks; ++chunk) {
+        const int cbase = half * (BN / 2) + chunk * 32;   // column of the tile
+        const int n = n0 + cbase + c4;                    // this lane's first global column
+        if (n0 + cbase >= p.N) break;
+        const bool full4 = vec_ok && (n + 3 < p.N);
+        // prefetch the addend / mask operands (coalesced: 8 lanes cover one 128 B row)
+        float4 ad[8], mk[8];
+        if (full4) {
+          if (p.addend) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + doff[i] + n))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (p.mask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.mask + doff[i] + n))
+                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+          }
+        }
+        if (!waited) {
+          mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cbase, v);
+        tmem_ld_wait();
+        __syncwarp();   // previous chunk's reads of the transpose buffer are done
+#pragma unroll
+        for (int c = 0; c < 32; ++c) xp[lane * kXposePitch + c] = __uint_as_float(v[c]);
+        __syncwarp();
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full4) {
+          if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+          if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (doff[i] < 0) continue;
+          const float* src = xp + (4 * i + sub) * kXposePitch + c4;
+          float o[4] = {src[0], src[1], src[2], src[3]};
+          if (full4) {
+            if (p.scale) { o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w; }
+            if (p.bias) { o[0] += bi.x; o[1] += bi.y; o[2] += bi.z; o[3] += bi.w; }
+            if (p.addend) { o[0] += ad[i].x; o[1] += ad[i].y; o[2] += ad[i].z; o[3] += ad[i].w; }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+            }
+            if (p.mask) {
+              o[0] = mk[i].x > 0.f ? o[0] : 0.f; o[1] = mk[i].y > 0.f ? o[1] : 0.f;
+              o[2] = mk[i].z > 0.f ? o[2] : 0.f; o[3] = mk[i].w > 0.f ? o[3] : 0.f;
+            }
+            if (p.round_out) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+            }
+            *reinterpret_cast<float4*>(p.d + doff[i] + n) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int e = 0; e < 4 && n + e < p.N; ++e) {
+              float x = o[e];
+              if (p.scale) x *= __ldg(p.scale + n + e);
+              if (p.bias) x += __ldg(p.bias + n + e);
+              if (p.addend) x += __ldg(p.addend + doff[i] + n + e);
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (p.mask) x = __ldg(p.mask + doff[i] + n + e) > 0.f ? x : 0.f;
+              if (p.round_out) x = round_tf32(x);
+              p.d[doff[i] + n + e] = x;
+            }
+          }
+        }
+      }
+      if (!waited) {   // this warp had no columns to write: still consume the phase
+        mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
+        tc_fence_after();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------ host ----
@@ -307,9 +380,13 @@ int launch(const CUtensorMap& tmap, const ConvGemmParams& p, cudaStream_t st) {
                                       L::kDynamic));
     configured = true;
   }
-  dim3 grid(ceil_div(p.M, kBM), ceil_div(p.N, BN));
+  ConvGemmParams q = p;
+  q.m_tiles = ceil_div(p.M, kBM);
+  q.n_tiles = ceil_div(p.N, BN);
+  const long long tiles = (long long)q.m_tiles * q.n_tiles;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
-  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, p);
+  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, q);
   prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -349,17 +426,31 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   CMR_REQUIRE((c->out_h - 1) * c->d_stride + c->d_oy < c->d_h);
   CMR_REQUIRE((c->out_w - 1) * c->d_stride + c->d_ox < c->d_w);
 
-  // Tile width: the widest N tile that does not waste more than half a tile.
+  // Tile width: minimise (waves over the SMs) x (per-tile cost); narrower tiles move
+  // more operand bytes per FLOP through L2 (relative tile rates 1 : 0.75 : 0.5).
   int bn = c->tile_n;
-  if (bn == 0) bn = p.N > 128 ? 256 : (p.N > 64 ? 128 : 64);
+  if (bn == 0) {
+    const int widths[3] = {256, 128, 64};
+    const double rate[3] = {1.0, 0.75, 0.5};
+    double best = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      if (i < 2 && p.N <= widths[i] / 2) continue;   // more than half the tile would be padding
+      const long long tiles = (long long)ceil_div(p.M, kBM) * ceil_div(p.N, widths[i]);
+      const double cost = (double)ceil_div_ll(tiles, sm_count()) * widths[i] / rate[i];
+      if (bn == 0 || cost < best) {
+        bn = widths[i];
+        best = cost;
+      }
+    }
+  }
   CUtensorMap tmap;
   int rc = make_tmap_2d(&tmap, w, (uint64_t)p.N, (uint64_t)p.K, (uint32_t)bn);
   if (rc != CMR_OK) return rc;
   cudaStream_t st = as_stream(stream);
   switch (bn) {
-    case 64: return launch<64, 4>(tmap, p, st);
-    case 128: return launch<128, 3>(tmap, p, st);
-    case 256: return launch<256, 4>(tmap, p, st);
+    case 64: return launch<64, 6>(tmap, p, st);
+    case 128: return launch<128, 5>(tmap, p, st);
+    case 256: return launch<256, 3>(tmap, p, st);
     default: return CMR_ERR_INVALID_ARG;
   }
 }
