@@ -88,7 +88,7 @@ class WgradDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         'batch', 'loop_h', 'loop_w', 'gy_h', 'gy_w', 'gy_ld', 'gy_stride', 'gy_off_y',
         'gy_off_x', 'gy_c0', 'x_h', 'x_w', 'x_ld', 'x_stride', 'x_off_y', 'x_off_x', 'x_c0',
-        'rows', 'cols', 'gw_ld', 'gw_col0', 'splits')]
+        'rows', 'cols', 'gw_ld', 'gw_col0', 'splits', 'taps_h', 'taps_w')]
 
 
 EXPORTED_SYMBOLS = tuple(sorted(_SIGNATURES))

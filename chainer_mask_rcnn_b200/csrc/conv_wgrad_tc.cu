@@ -29,6 +29,15 @@ namespace {
 
 using namespace tc;
 
+// n / d and n % d for 0 <= n < 2^31 by a precomputed multiply-shift (d >= 1).
+struct FastDiv {
+  unsigned int d, mul, shr;
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = d == 1 ? n : (int)(__umulhi((unsigned int)n, mul) >> shr);
+    r = n - q * (int)d;
+  }
+};
+
 struct PixelMap {
   const float* base;
   int h, w, ld;      // tensor (batch, h, w, ld)
@@ -39,6 +48,7 @@ struct PixelMap {
 struct WgradParams {
   PixelMap p, q;
   int loop_h, loop_w;  // pixel loop space (batch, loop_h, loop_w)
+  FastDiv div_hw, div_w;
   int M;               // number of pixels
   int rows, cols;      // gW tile space: rows = output channels, cols = channels of one tap
   float* gw;
@@ -46,6 +56,7 @@ struct WgradParams {
   int gw_col0;         // column offset of this tap inside a gW row
   const float* row_scale;
   int kb_per_split, num_kb;
+  int splits, taps_w;  // grid.z = taps * splits; tap (fr, fs) shifts q by (fr, fs) pixels
 };
 
 constexpr int kBM = 128;
@@ -66,13 +77,13 @@ struct WSmem {
 // Gathers one k-block (32 pixels) x (NBLK * 32 channels) of an operand.
 // Lane layout per cp.async: 4 pixel rows x 128 B, i.e. 512 contiguous smem bytes.
 template <int NBLK>
-__device__ __forceinline__ void gather_tile(const PixelMap& pm, int pix0, int M, int loop_h,
-                                            int loop_w, int chan_limit, uint32_t stage_addr,
+__device__ __forceinline__ void gather_tile(const PixelMap& pm, int pix0, int M,
+                                            const FastDiv& div_hw, const FastDiv& div_w,
+                                            int chan_limit, uint32_t stage_addr,
                                             int t /* 0..127 */) {
   const int jj = t & 7;
   const int rsub = (t >> 3) & 3;
   const int w = t >> 5;
-  const int lhw = loop_h * loop_w;
   // A thread owns two pixel rows (decoded once each) x all NBLK channel blocks.
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
@@ -81,10 +92,9 @@ __device__ __forceinline__ void gather_tile(const PixelMap& pm, int pix0, int M,
     bool ok = pix < M;
     const float* src_row = pm.base;
     if (ok) {
-      const int img = pix / lhw;
-      const int rem = pix - img * lhw;
-      const int oy = rem / loop_w;
-      const int ox = rem - oy * loop_w;
+      int img, rem, oy, ox;
+      div_hw.divmod(pix, img, rem);
+      div_w.divmod(rem, oy, ox);
       const int y = oy * pm.stride + pm.off_y, x = ox * pm.stride + pm.off_x;
       ok = (unsigned)y < (unsigned)pm.h && (unsigned)x < (unsigned)pm.w;
       if (ok) src_row = pm.base + ((size_t)(img * pm.h + y) * pm.w + x) * pm.ld;
@@ -119,7 +129,9 @@ conv_wgrad_tc_kernel(const WgradParams p) {
   const int lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * kBM;
   const int j0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int tap = blockIdx.z / p.splits;
+  const int tap_fr = tap / p.taps_w, tap_fs = tap - tap_fr * p.taps_w;
+  const int kb_begin = (blockIdx.z - tap * p.splits) * p.kb_per_split;
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
   const int nkb = kb_end - kb_begin;  // >= 1 by construction of the grid
 
@@ -143,6 +155,10 @@ conv_wgrad_tc_kernel(const WgradParams p) {
     const int t = threadIdx.x & 127;
     PixelMap pm = is_p ? p.p : p.q;
     pm.c0 += is_p ? i0 : j0;
+    if (!is_p) {
+      pm.off_y += tap_fr;
+      pm.off_x += tap_fs;
+    }
     const int chan_limit = (is_p ? p.p.c0 + p.rows : p.q.c0 + p.cols);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES;
@@ -150,10 +166,10 @@ conv_wgrad_tc_kernel(const WgradParams p) {
       mbar_wait(&empty_bar[s], phase ^ 1);
       const int pix0 = (kb_begin + kb) * kPix;
       if (is_p)
-        gather_tile<kBM / 32>(pm, pix0, p.M, p.loop_h, p.loop_w, chan_limit,
+        gather_tile<kBM / 32>(pm, pix0, p.M, p.div_hw, p.div_w, chan_limit,
                               smem_base + L::kPOff + s * L::kPBytes, t);
       else
-        gather_tile<BN / 32>(pm, pix0, p.M, p.loop_h, p.loop_w, chan_limit,
+        gather_tile<BN / 32>(pm, pix0, p.M, p.div_hw, p.div_w, chan_limit,
                              smem_base + L::kQOff + s * L::kQBytes, t);
       cp_async_mbar_arrive_noinc(&full_bar[s]);
     }
@@ -166,7 +182,7 @@ conv_wgrad_tc_kernel(const WgradParams p) {
       const int row = i0 + warp * 32 + lane;
       const bool row_ok = row < p.rows;
       const float sc = (row_ok && p.row_scale) ? __ldg(p.row_scale + row) : 1.0f;
-      float* out_row = p.gw + (size_t)row * p.gw_ld + p.gw_col0;
+      float* out_row = p.gw + (size_t)row * p.gw_ld + p.gw_col0 + tap * p.cols;
       const bool vec_ok = ((p.gw_ld & 3) == 0) && ((p.gw_col0 & 3) == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.gw) & 15) == 0);
 #pragma unroll 1
@@ -227,8 +243,23 @@ conv_wgrad_tc_kernel(const WgradParams p) {
   if (warp == 7) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+// Round-up magic number for 31-bit dividends: q = (n * mul) >> (32 + shr).
+FastDiv make_fast_div(int d) {
+  FastDiv f;
+  f.d = (unsigned int)d;
+  f.mul = 0;
+  f.shr = 0;
+  if (d <= 1) return f;
+  unsigned int l = 0;
+  while ((1u << l) < (unsigned int)d) ++l;               // ceil(log2 d)
+  const unsigned long long m = ((1ull << (31 + l)) + d - 1) / d;   // fits in 32 bits
+  f.mul = (unsigned int)m;
+  f.shr = l - 1;
+  return f;
+}
+
 template <int BN, int STAGES>
-int launch_wgrad(const WgradParams& p, int splits, cudaStream_t st) {
+int launch_wgrad(const WgradParams& p, int splits, int taps, cudaStream_t st) {
   using L = WSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -237,8 +268,8 @@ int launch_wgrad(const WgradParams& p, int splits, cudaStream_t st) {
                                       L::kDynamic));
     configured = true;
   }
-  dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits);
-  prof_begin(kProfWgrad, 2.0 * p.M * (double)p.rows * p.cols, st);
+  dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits * taps);
+  prof_begin(kProfWgrad, 2.0 * p.M * (double)p.rows * p.cols * taps, st);
   conv_wgrad_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(p);
   prof_end(st);
   CMR_LAUNCH_CHECK();
@@ -270,24 +301,33 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   p.q.base = x; p.q.h = c->x_h; p.q.w = c->x_w; p.q.ld = c->x_ld;
   p.q.stride = c->x_stride; p.q.off_y = c->x_off_y; p.q.off_x = c->x_off_x; p.q.c0 = c->x_c0;
   p.loop_h = c->loop_h; p.loop_w = c->loop_w; p.M = (int)M;
+  p.div_hw = make_fast_div(c->loop_h * c->loop_w);
+  p.div_w = make_fast_div(c->loop_w);
   p.rows = c->rows; p.cols = c->cols;
   p.gw = gw; p.gw_ld = c->gw_ld; p.gw_col0 = c->gw_col0;
   p.row_scale = row_scale;
   p.num_kb = ceil_div(p.M, kPix);
   // Split the pixel reduction so that the grid fills the machine (~2 CTAs per SM).
   const int bn = c->cols > 64 ? 128 : 64;
-  const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn);
+  const int taps_h = c->taps_h > 1 ? c->taps_h : 1, taps_w = c->taps_w > 1 ? c->taps_w : 1;
+  const int taps = taps_h * taps_w;
+  CMR_REQUIRE(taps == 1 || ((c->gw_col0 + taps * c->cols) <= c->gw_ld && c->cols % 4 == 0));
+  const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn) * taps;
   int splits = c->splits;
   if (splits <= 0) {
-    splits = ceil_div(2 * sm_count(), tiles);
+    // one full wave of the 2 CTAs per SM that fit: never spill a few CTAs into a second
+    splits = (2 * sm_count()) / tiles;
     const int max_splits = ceil_div(p.num_kb, 8);  // at least 8 k-blocks per CTA
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
   }
+  CMR_REQUIRE((long long)splits * taps < 65536);
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = ceil_div(p.num_kb, splits);
   splits = ceil_div(p.num_kb, p.kb_per_split);
+  p.splits = splits;
+  p.taps_w = taps_w;
   cudaStream_t st = as_stream(stream);
-  if (bn == 128) return launch_wgrad<128, 3>(p, splits, st);
-  return launch_wgrad<64, 4>(p, splits, st);
+  if (bn == 128) return launch_wgrad<128, 3>(p, splits, taps, st);
+  return launch_wgrad<64, 4>(p, splits, taps, st);
 }

@@ -48,14 +48,14 @@ def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=N
 
 
 def wgrad_tap(gy, x, gw, rows, cols, loop_hw, gw_ld, gw_col0=0, gy_stride=1, gy_off=(0, 0),
-              gy_c0=0, x_stride=1, x_off=(0, 0), x_c0=0, row_scale=None):
+              gy_c0=0, x_stride=1, x_off=(0, 0), x_c0=0, row_scale=None, taps=(1, 1)):
     """gw[i, gw_col0 + j] += row_scale[i] * sum_pix gy[pix_gy, gy_c0+i] * x[pix_x, x_c0+j]
     (cmr_conv_wgrad_tc).  gy (B,gh,gw,ld), x (B,xh,xw,ld) contiguous NHWC."""
     B, gh, gww, gld = gy.shape
     _, xh, xw, xld = x.shape
     d = _lib.WgradDesc(B, loop_hw[0], loop_hw[1], gh, gww, gld, gy_stride, gy_off[0], gy_off[1],
                        gy_c0, xh, xw, xld, x_stride, x_off[0], x_off[1], x_c0, rows, cols,
-                       gw_ld, gw_col0, 0)
+                       gw_ld, gw_col0, 0, taps[0], taps[1])
     _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _p(gy), _p(x), _p(gw), _p(row_scale),
               stream())
 

@@ -183,11 +183,8 @@ class Conv(object):
         B, oh, ow, _ = g.shape
         k, cin = self.k, self.cin
         scale = c.param(self.aW) if self.aW else None
-        for fr in range(k):
-            for fs in range(k):
-                E.wgrad_tap(g, x, gw, self.cout, cin, (oh, ow), k * k * cin,
-                            gw_col0=(fr * k + fs) * cin, x_stride=self.stride,
-                            x_off=(fr - self.pad, fs - self.pad), row_scale=scale)
+        E.wgrad_tap(g, x, gw, self.cout, cin, (oh, ow), k * k * cin, x_stride=self.stride,
+                    x_off=(-self.pad, -self.pad), row_scale=scale, taps=(k, k))
         if self.b and self.trainable:
             E.column_sums(g, 0, self.cout, c.grad(self.b))
 

@@ -168,6 +168,9 @@ typedef struct cmr_wgrad_desc {
   int rows, cols;
   int gw_ld, gw_col0;
   int splits;
+  int taps_h, taps_w;   /* > 1: all filter taps in one launch; tap (fr, fs) reads x at
+                           x_off + (fr, fs) and accumulates into column block
+                           gw_col0 + (fr*taps_w + fs)*cols.  0 or 1 = a single tap. */
 } cmr_wgrad_desc;
 
 int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* x,

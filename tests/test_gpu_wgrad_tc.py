@@ -20,7 +20,7 @@ def wgrad_conv(x, gy, kh, kw, stride, pad, row_scale=None, splits=0):
     for fr in range(kh):
         for fs in range(kw):
             d = _lib.WgradDesc(B, oh, ow, oh, ow, N, 1, 0, 0, 0, H, W, C, stride, fr - pad,
-                               fs - pad, 0, N, C, kh * kw * C, (fr * kw + fs) * C, splits)
+                               fs - pad, 0, N, C, kh * kw * C, (fr * kw + fs) * C, splits, 1, 1)
             _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _lib.ptr(gy), _lib.ptr(x),
                       _lib.ptr(gw), _lib.ptr(row_scale), _lib.stream_ptr())
     return gw
@@ -60,6 +60,21 @@ def test_wgrad_matches_autograd(B, H, W, C, N, k, s, p, splits):
     assert rel(got, want) <= 1e-4
 
 
+@pytest.mark.parametrize('B,H,W,C,N,k,p', [(2, 20, 23, 128, 128, 3, 1), (16, 7, 7, 512, 512, 3, 1),
+                                           (2, 13, 17, 64, 96, 3, 1), (1, 9, 9, 64, 64, 7, 3)])
+def test_all_taps_in_one_launch(B, H, W, C, N, k, p):
+    g = torch.Generator(device='cuda').manual_seed(C + k)
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    gy = round_tf32(torch.randn((B, H, W, N), device='cuda', generator=g))
+    want = ref_wgrad(x, gy, k, k, 1, p)
+    gw = torch.zeros((N, k, k, C), device='cuda')
+    d = _lib.WgradDesc(B, H, W, H, W, N, 1, 0, 0, 0, H, W, C, 1, -p, -p, 0, N, C, k * k * C, 0, 0,
+                       k, k)
+    _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _lib.ptr(gy), _lib.ptr(x), _lib.ptr(gw), None,
+              _lib.stream_ptr())
+    assert rel(gw, want) <= 1e-4
+
+
 def test_row_scale_and_accumulation():
     g = torch.Generator(device='cuda').manual_seed(3)
     x = round_tf32(torch.randn((2, 9, 11, 128), device='cuda', generator=g))
@@ -69,7 +84,7 @@ def test_row_scale_and_accumulation():
     got = wgrad_conv(x, gy, 1, 1, 1, 0, row_scale=scale)
     assert rel(got, want) <= 1e-4
     # gw is accumulated into: a second call doubles it
-    d = _lib.WgradDesc(2, 9, 11, 9, 11, 128, 1, 0, 0, 0, 9, 11, 128, 1, 0, 0, 0, 128, 128, 128, 0, 0)
+    d = _lib.WgradDesc(2, 9, 11, 9, 11, 128, 1, 0, 0, 0, 9, 11, 128, 1, 0, 0, 0, 128, 128, 128, 0, 0, 1, 1)
     _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _lib.ptr(gy), _lib.ptr(x), _lib.ptr(got),
               _lib.ptr(scale), _lib.stream_ptr())
     assert rel(got, 2 * want) <= 1e-4
@@ -89,7 +104,7 @@ def test_deconv_tap_weight_gradient():
     for dy in range(2):
         for dx in range(2):
             d = _lib.WgradDesc(B, H, W, 2 * H, 2 * W, N, 2, dy, dx, 0, H, W, C, 1, 0, 0, 0,
-                               N, C, C, 0, 0)
+                               N, C, C, 0, 0, 1, 1)
             _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _lib.ptr(gy), _lib.ptr(x),
                       _lib.ptr(got[dy, dx]), None, _lib.stream_ptr())
     assert rel(got, want) <= 1e-4

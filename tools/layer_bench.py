@@ -48,8 +48,9 @@ def wgrad_hook(gy, x, gw, rows, cols, loop_hw, gw_ld, **kw_):
     _wgrad(gy, x, gw, rows, cols, loop_hw, gw_ld, **kw_)
     b.record()
     M = gy.shape[0] * loop_hw[0] * loop_hw[1]
-    records.append(('wgrad', (M, rows, cols, 'taps%d' % (gw_ld // cols)), a, b,
-                    2.0 * M * rows * cols))
+    t = kw_.get('taps', (1, 1))
+    records.append(('wgrad', (M, rows, cols, 'taps%d' % (t[0] * t[1])), a, b,
+                    2.0 * M * rows * cols * t[0] * t[1]))
 
 
 E.conv_gemm, E.wgrad_tap = conv_hook, wgrad_hook
