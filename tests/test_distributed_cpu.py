@@ -1,0 +1,129 @@
+"""World-size-2 `gloo` test of the data-parallel host logic:
+image sharding, the single flat-buffer gradient all-reduce and the mean it implies.
+
+The reference wires this at examples/train_common.py:96-104 (one rank per GPU,
+`batch_size_per_gpu` images each) and :176-178 (`chainermn.create_multi_node_optimizer`
+= all-reduce-mean of every gradient before the MomentumSGD update).  The SGD kernel
+itself is CUDA-only and is covered by the `-m gpu` tests; here the update rule is
+restated in NumPy so the two-rank result can be compared with the single-process
+result on the concatenated batch.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from chainer_mask_rcnn_b200 import optimizers
+from chainer_mask_rcnn_b200.models import engine as E
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _momentum_sgd(p, g, v, lr, momentum, wd, grad_scale):
+    """Upstream MomentumSGD + WeightDecay: the arithmetic of
+    cmr_sgd_momentum (include/cmr_b200.h)."""
+    g = grad_scale * g + wd * p
+    v = momentum * v - lr * g
+    return p + v, v
+
+
+class _Ctx(object):
+    """The slice of TrainContext the optimizer's exchange step touches."""
+
+    def __init__(self, store):
+        self.train = store
+        self.grads = torch.zeros_like(store.data)
+
+
+def _make_store():
+    s = E.FlatStore()
+    s.add('rpn/conv1/W', (8, 3, 3, 4))
+    s.add('rpn/conv1/b', (8,))
+    s.add('head/score/W', (5, 7))
+    return s.allocate('cpu')
+
+
+def _fake_grad(store, image_index):
+    """A deterministic per-image 'gradient' (what one image's backward pass would add)."""
+    rs = np.random.RandomState(100 + image_index)
+    g = torch.zeros_like(store.data)
+    for name in store.names():
+        v = store.view(name, g)
+        v += torch.from_numpy(rs.standard_normal(tuple(v.shape)).astype(np.float32))
+    return g
+
+
+def _worker(rank, world, port, n_images, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        comm = optimizers.create_communicator()
+        assert comm.size == world and comm.rank == rank
+        opt = optimizers.create_multi_node_optimizer(
+            optimizers.MomentumSGD(lr=0.00125 * n_images, momentum=0.9), comm)
+        store = _make_store()
+        opt.ctx = _Ctx(store)
+        # this rank's shard of the global batch; per-rank loss = mean over its own images
+        mine = optimizers.shard_indices(n_images, comm.size, comm.rank)
+        for i in mine:
+            opt.ctx.grads += _fake_grad(store, i) / len(mine)
+        opt.allreduce_grad()
+        np.save(os.path.join(out_dir, 'grads_%d.npy' % rank), opt.ctx.grads.numpy())
+        np.save(os.path.join(out_dir, 'shard_%d.npy' % rank), np.asarray(list(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_indices_partition():
+    for n, size in ((16, 8), (5, 2), (3, 4), (117266, 8)):
+        seen = []
+        sizes = []
+        for r in range(size):
+            idx = optimizers.shard_indices(n, size, r)
+            seen.extend(idx)
+            sizes.append(len(idx))
+        assert seen == list(range(n))
+        assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_allreduce_matches_single_process(tmp_path):
+    world, n_images = 2, 4
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_images, str(tmp_path)), nprocs=world, join=True)
+    g0 = np.load(tmp_path / 'grads_0.npy')
+    g1 = np.load(tmp_path / 'grads_1.npy')
+    # every rank holds the same summed buffer after the exchange
+    assert np.array_equal(g0, g1)
+    shards = [np.load(tmp_path / ('shard_%d.npy' % r)) for r in range(world)]
+    assert sorted(np.concatenate(shards).tolist()) == list(range(n_images))
+    # the update applies grad_scale = 1/world: that must equal the single-process
+    # gradient of the mean loss over the global batch
+    store = _make_store()
+    want = sum(_fake_grad(store, i) for i in range(n_images)).numpy() / n_images
+    np.testing.assert_allclose(g0 / world, want, rtol=1e-6, atol=1e-6)
+    # and the parameter after one MomentumSGD + WeightDecay step is then the same
+    p = np.linspace(-1, 1, g0.size).astype(np.float32)
+    v = np.zeros_like(p)
+    p_dp, _ = _momentum_sgd(p, g0, v, 0.005, 0.9, 1e-4, 1.0 / world)
+    p_sp, _ = _momentum_sgd(p, want, v, 0.005, 0.9, 1e-4, 1.0)
+    np.testing.assert_allclose(p_dp, p_sp, rtol=1e-6, atol=1e-7)
+
+
+def test_flat_store_slots_are_tma_aligned():
+    s = _make_store()
+    for name, shape, off in s.specs:
+        assert off % E.ALIGN == 0
+        assert tuple(s.view(name).shape) == tuple(shape)
+    assert s.size % E.ALIGN == 0
