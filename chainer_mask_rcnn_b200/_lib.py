@@ -64,12 +64,16 @@ _SIGNATURES = {
     'cmr_anchor_targets_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'cmr_anchor_targets': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_float, c_int, c_float, c_float, c_float, c_ulonglong,
-                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                   c_void_p]),
     'cmr_proposal_targets_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'cmr_proposal_targets': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_float, c_float, c_float, c_float,
                                      c_void_p, c_void_p, c_ulonglong, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+    'cmr_mask_targets': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'cmr_mask_loss': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                               c_void_p, c_int, c_void_p, c_void_p]),
 }

@@ -37,6 +37,13 @@ __device__ __forceinline__ float iou_f(const float4 a, const float4 b) {  // (y1
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
+// Effective seed = host seed + *seed_dev (seed_dev may be NULL): a captured CUDA graph
+// replays with the same host arguments, the device word advances between replays.
+__device__ __forceinline__ unsigned long long eff_seed(unsigned long long seed,
+                                                       const unsigned long long* seed_dev) {
+  return seed_dev ? seed + 0x9E3779B97F4A7C15ull * __ldg(seed_dev) : seed;
+}
+
 __device__ __forceinline__ unsigned int hash31(unsigned long long seed, unsigned long long i) {
   unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);  // splitmix64
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -96,7 +103,8 @@ anchor_label_kernel(const float4* __restrict__ anchor, int S, int n_pad,
                     const float4* __restrict__ bbox, const int* __restrict__ n_bbox, int G,
                     float img_h, float img_w, float pos_iou, float neg_iou,
                     const unsigned int* __restrict__ gt_max, unsigned long long seed,
-                    float4* __restrict__ gt_loc, int* __restrict__ gt_label,
+                    const unsigned long long* __restrict__ seed_dev, float4* __restrict__ gt_loc,
+                    int* __restrict__ gt_label,
                     unsigned long long* __restrict__ keys, int* __restrict__ counts) {
   __shared__ float4 gt[kMaxGt];
   __shared__ float gmax[kMaxGt];
@@ -128,7 +136,8 @@ anchor_label_kernel(const float4* __restrict__ anchor, int S, int n_pad,
       if (is_gt_best) label = 1;
       if (best >= pos_iou) label = 1;
       loc = box2loc(a, gt[arg]);
-      const unsigned long long r = hash31(seed, (unsigned long long)b * S + i);
+      const unsigned long long r =
+          hash31(eff_seed(seed, seed_dev), (unsigned long long)b * S + i);
       if (label == 1) key = (1ull << 63) | (r << 32) | (unsigned int)i;
       if (label == 0) key = (r << 32) | (unsigned int)i;
     }
@@ -174,7 +183,8 @@ proposal_assign_kernel(const float4* __restrict__ rois, const int* __restrict__ 
                        int roi_stride, const float4* __restrict__ bbox,
                        const int* __restrict__ n_bbox, int G, int n_pad, float pos_iou,
                        float neg_hi, float neg_lo, unsigned long long seed,
-                       int* __restrict__ assign, unsigned long long* __restrict__ keys,
+                       const unsigned long long* __restrict__ seed_dev, int* __restrict__ assign,
+                       unsigned long long* __restrict__ keys,
                        int* __restrict__ counts) {
   __shared__ float4 gt[kMaxGt];
   const int b = blockIdx.y;
@@ -198,7 +208,8 @@ proposal_assign_kernel(const float4* __restrict__ rois, const int* __restrict__ 
     assign[(size_t)b * n_pad + c] = arg;
     if (best >= pos_iou) cls = 1;
     else if (best < neg_hi && best >= neg_lo) cls = 0;
-    const unsigned long long r = hash31(seed, (unsigned long long)b * n_pad + c);
+    const unsigned long long r =
+        hash31(eff_seed(seed, seed_dev), (unsigned long long)b * n_pad + c);
     if (cls == 1) key = (1ull << 63) | (r << 32) | (unsigned int)c;
     if (cls == 0) key = (r << 32) | (unsigned int)c;
   }
@@ -256,6 +267,92 @@ proposal_emit_targets_kernel(const unsigned long long* __restrict__ keys, int n_
   gt_assign[o] = asg;
 }
 
+// ------------------------------------------------------------- mask targets --
+// ProposalTargetCreator's mask rasterisation (models/utils/proposal_target_creator.py:
+// 163-177): round the sampled RoI to integers, crop the assigned instance mask, one-hot
+// it, cv2.resize each plane to (ms, ms) with INTER_LINEAR in float32, argmax over the
+// planes.  cv2's float32 bilinear is restated exactly (OpenCV resize.cpp, the non-IPP
+// path; checked bit for bit against cv2 in tests/test_oracle_mask_target.py):
+//   scale = 1/(ms/size) in double;  f = float((d + 0.5)*scale - 0.5);  s = floor(f); f -= s
+//   x: s < 0 -> (s, f) = (0, 0);  s >= size-1 -> (s, f) = (size-1, 0)
+//   y: source rows clipped to [0, size-1], weights NOT clamped
+//   horizontal pass first: r = S[x0]*(1-fx) + S[x1]*fx, then out = r0*(1-fy) + r1*fy,
+//   every product and sum rounded to fp32 (no FMA).
+// The argmax over one-hot planes only needs the (at most four) values under the taps.
+struct Lin {
+  int i0, i1;
+  float w0, w1;
+};
+
+__device__ __forceinline__ Lin lin_coeff(int d, int size, int ms, bool clamp_weights) {
+  const double scale = 1.0 / ((double)ms / (double)size);
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (clamp_weights) {
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= size - 1) { s = size - 1; f = 0.f; }
+  }
+  Lin l;
+  l.i0 = min(max(s, 0), size - 1);
+  l.i1 = min(max(s + 1, 0), size - 1);
+  l.w0 = __fsub_rn(1.f, f);
+  l.w1 = f;
+  return l;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_targets_kernel(const T* __restrict__ masks, int G, int H, int W,
+                    const float4* __restrict__ sample_roi, const int* __restrict__ gt_assign,
+                    const int* __restrict__ n_pos, int n_sample, int ms,
+                    int* __restrict__ gt_mask) {
+  const int b = blockIdx.y, j = blockIdx.x;
+  const size_t row = (size_t)b * n_sample + j;
+  int* out = gt_mask + row * ms * ms;
+  const int g = j < n_pos[b] ? gt_assign[row] : -1;
+  if (g < 0 || g >= G) {
+    for (int t = threadIdx.x; t < ms * ms; t += blockDim.x) out[t] = -1;
+    return;
+  }
+  const float4 r = sample_roi[row];
+  // np.round(...).astype(int32) = round half to even; python slicing clips to the array
+  const int y0 = max((int)rintf(r.x), 0), x0 = max((int)rintf(r.y), 0);
+  const int y1 = min((int)rintf(r.z), H), x1 = min((int)rintf(r.w), W);
+  const int h = y1 - y0, w = x1 - x0;
+  if (h <= 0 || w <= 0) {
+    for (int t = threadIdx.x; t < ms * ms; t += blockDim.x) out[t] = 0;
+    return;
+  }
+  const T* m = masks + ((size_t)b * G + g) * H * W + (size_t)y0 * W + x0;
+  for (int t = threadIdx.x; t < ms * ms; t += blockDim.x) {
+    const int py = t / ms, px = t - py * ms;
+    const Lin ly = lin_coeff(py, h, ms, false), lx = lin_coeff(px, w, ms, true);
+    int v[4];
+    v[0] = (int)m[(size_t)ly.i0 * W + lx.i0];
+    v[1] = (int)m[(size_t)ly.i0 * W + lx.i1];
+    v[2] = (int)m[(size_t)ly.i1 * W + lx.i0];
+    v[3] = (int)m[(size_t)ly.i1 * W + lx.i1];
+    int best_v = 0;
+    float best_s = -1.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = v[k];
+      if (c < 0) continue;   // negative labels match no one-hot plane
+      const float top = __fadd_rn(v[0] == c ? lx.w0 : 0.f, v[1] == c ? lx.w1 : 0.f);
+      const float bot = __fadd_rn(v[2] == c ? lx.w0 : 0.f, v[3] == c ? lx.w1 : 0.f);
+      const float s = __fadd_rn(__fmul_rn(top, ly.w0), __fmul_rn(bot, ly.w1));
+      if (s > best_s || (s == best_s && c < best_v)) {
+        best_s = s;
+        best_v = c;
+      }
+    }
+    // planes of values absent under the taps score 0: they win only if every tapped
+    // plane scores 0 too, and then np.argmax returns plane 0
+    out[t] = best_s > 0.f ? best_v : 0;
+  }
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int next_pow2(int v) {
   int p = 1;
@@ -278,7 +375,8 @@ extern "C" int cmr_anchor_targets(const float* anchor, int n_anchor, const float
                                   const int32_t* n_bbox, int B, int max_bbox, float img_h,
                                   float img_w, int n_sample, float pos_iou_thresh,
                                   float neg_iou_thresh, float pos_ratio, unsigned long long seed,
-                                  float* gt_loc, int32_t* gt_label, void* workspace,
+                                  const unsigned long long* seed_dev, float* gt_loc,
+                                  int32_t* gt_label, void* workspace,
                                   size_t workspace_bytes, void* stream) {
   CMR_REQUIRE(anchor && bbox && n_bbox && gt_loc && gt_label && workspace);
   CMR_REQUIRE(B > 0 && n_anchor > 0 && max_bbox > 0 && max_bbox <= kMaxGt && n_sample > 0);
@@ -304,7 +402,7 @@ extern "C" int cmr_anchor_targets(const float* anchor, int n_anchor, const float
   CMR_LAUNCH_CHECK();
   anchor_label_kernel<<<grid, 256, 0, st>>>(a4, n_anchor, n_pad, b4, n_bbox, max_bbox, img_h,
                                            img_w, pos_iou_thresh, neg_iou_thresh, gt_max, seed,
-                                           reinterpret_cast<float4*>(gt_loc), gt_label, keys,
+                                           seed_dev, reinterpret_cast<float4*>(gt_loc), gt_label, keys,
                                            counts);
   CMR_LAUNCH_CHECK();
   int rc = launch_sort_desc_u64(keys, n_pad, B, st);
@@ -328,7 +426,8 @@ extern "C" int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int
                                     float pos_ratio, float pos_iou_thresh, float neg_iou_thresh_hi,
                                     float neg_iou_thresh_lo, const float* loc_mean,
                                     const float* loc_std, unsigned long long seed,
-                                    float* sample_roi, float* gt_roi_loc, int32_t* gt_roi_label,
+                                    const unsigned long long* seed_dev, float* sample_roi,
+                                    float* gt_roi_loc, int32_t* gt_roi_label,
                                     int32_t* gt_assign, int32_t* n_pos, void* workspace,
                                     size_t workspace_bytes, void* stream) {
   CMR_REQUIRE(rois && n_roi && bbox && label && n_bbox && loc_mean && loc_std && workspace);
@@ -352,7 +451,7 @@ extern "C" int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int
   const float4* b4 = reinterpret_cast<const float4*>(bbox);
   proposal_assign_kernel<<<dim3(ceil_div(n_pad, 256), B), 256, 0, st>>>(
       r4, n_roi, max_roi, b4, n_bbox, max_bbox, n_pad, pos_iou_thresh, neg_iou_thresh_hi,
-      neg_iou_thresh_lo, seed, assign, keys, counts);
+      neg_iou_thresh_lo, seed, seed_dev, assign, keys, counts);
   CMR_LAUNCH_CHECK();
   int rc = launch_sort_desc_u64(keys, n_pad, B, st);
   if (rc != CMR_OK) return rc;
@@ -362,6 +461,29 @@ extern "C" int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int
       keys, n_pad, assign, counts, r4, n_roi, max_roi, b4, label, n_bbox, max_bbox, n_sample,
       (int)nearbyintf(n_sample * pos_ratio), mean, stdv, reinterpret_cast<float4*>(sample_roi),
       reinterpret_cast<float4*>(gt_roi_loc), gt_roi_label, gt_assign, n_pos);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+extern "C" int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, int max_bbox,
+                                int H, int W, const float* sample_roi,
+                                const int32_t* gt_assign, const int32_t* n_pos, int n_sample,
+                                int mask_size, int32_t* gt_mask, void* stream) {
+  CMR_REQUIRE(masks && sample_roi && gt_assign && n_pos && gt_mask);
+  CMR_REQUIRE(B > 0 && max_bbox > 0 && H > 0 && W > 0 && n_sample > 0 && mask_size > 0);
+  CMR_REQUIRE(mask_elem_bytes == 1 || mask_elem_bytes == 4);
+  CMR_REQUIRE((reinterpret_cast<uintptr_t>(sample_roi) & 15) == 0);
+  cudaStream_t st = as_stream(stream);
+  const float4* r4 = reinterpret_cast<const float4*>(sample_roi);
+  dim3 grid(n_sample, B);
+  if (mask_elem_bytes == 1)
+    mask_targets_kernel<uint8_t><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(masks), max_bbox, H, W, r4, gt_assign, n_pos, n_sample,
+        mask_size, gt_mask);
+  else
+    mask_targets_kernel<int32_t><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const int32_t*>(masks), max_bbox, H, W, r4, gt_assign, n_pos, n_sample,
+        mask_size, gt_mask);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

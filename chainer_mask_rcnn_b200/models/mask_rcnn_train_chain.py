@@ -7,8 +7,11 @@ Mirrors ``MaskRCNNTrainChain`` (chainer_mask_rcnn/models/mask_rcnn_train_chain.p
 flat gradient buffer.
 
 Targets.  By default anchors and proposals are labelled / sampled on the device
-(models/utils/device_targets.py, csrc/targets.cu) and only the mask-target
-rasterisation runs on the host (cv2, as in the reference), overlapped with the head's
+(models/utils/device_targets.py, csrc/targets.cu).  Mask targets are rasterised on the
+device as well when ``masks`` is a torch tensor ((B,G,H,W) uint8 / int32, CUDA or
+pinned host) -- the step then has no host synchronisation at all and can be captured
+in a CUDA graph (optimizers.GraphedUpdater); with the reference's host NumPy masks they
+are rasterised on the host (cv2, as in the reference), overlapped with the head's
 forward pass.  Passing the host ``AnchorTargetCreator`` / ``ProposalTargetCreator``
 objects instead reproduces the reference's NumPy-seeded sampling exactly (:126-158).
 """
@@ -70,6 +73,7 @@ class MaskRCNNTrainChain(object):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._seed = int(seed)
+        self.seed_dev = None            # optional device int64 word mixed into the seeds
         self._calls = 0
         self._pinned = {}
         self._roi_index = {}
@@ -89,8 +93,10 @@ class MaskRCNNTrainChain(object):
         scales = _host(scales)
         batch_size, _, H, W = x.shape
         img_size = (H, W)
-        bboxes = [_host(b).astype(np.float32) for b in bboxes]
-        labels = [_host(l) for l in labels]
+        gt = bboxes if isinstance(bboxes, GroundTruth) else None
+        if gt is None:
+            bboxes = [_host(b).astype(np.float32) for b in bboxes]
+            labels = [_host(l) for l in labels]
         self._calls += 1
         ctx.recording = True
         try:
@@ -100,14 +106,23 @@ class MaskRCNNTrainChain(object):
                     feat, img_size, scales)
             dev_anchor = isinstance(self.anchor_target_creator, DeviceAnchorTargetCreator)
             dev_prop = isinstance(self.proposal_target_creator, DeviceProposalTargetCreator)
-            gt = None
-            if dev_anchor or dev_prop:
+            if gt is not None and not (dev_anchor and dev_prop):
+                raise TypeError('a packed GroundTruth needs the device target creators')
+            if gt is None and (dev_anchor or dev_prop):
                 gt = GroundTruth(bboxes, labels, dev)
                 self.h2d_bytes += gt.nbytes
+            masks_dev = None
+            if isinstance(masks, torch.Tensor):
+                if not dev_prop:
+                    raise TypeError('tensor masks need the device proposal target creator')
+                if not masks.is_cuda:
+                    self.h2d_bytes += masks.numel() * masks.element_size()
+                masks_dev = masks.to(dev, non_blocking=True)
             seed = (self._seed << 20) + 2 * self._calls
             # ---- RPN targets
             if dev_anchor:
-                gt_rpn_locs, gt_rpn_labels = self.anchor_target_creator(gt, anchor, img_size, seed)
+                gt_rpn_locs, gt_rpn_labels = self.anchor_target_creator(
+                    gt, anchor, img_size, seed, seed_dev=self.seed_dev)
                 gt_rpn_locs = gt_rpn_locs.view(-1, 4)
                 gt_rpn_labels = gt_rpn_labels.view(-1)
             else:
@@ -119,9 +134,21 @@ class MaskRCNNTrainChain(object):
                 ptc = self.proposal_target_creator
                 sroi, gloc, glab, gasg, npos = ptc.sample(rois, cnt, gt, seed + 1,
                                                           self.loc_normalize_mean,
-                                                          self.loc_normalize_std)
+                                                          self.loc_normalize_std,
+                                                          seed_dev=self.seed_dev)
                 n = sroi.shape[1]
                 max_pos = int(np.round(ptc.n_sample * ptc.pos_ratio))
+                key = (batch_size, n, str(dev))
+                if key not in self._roi_index:
+                    self._roi_index[key] = torch.arange(batch_size, dtype=torch.int32, device=dev) \
+                        .repeat_interleave(n)
+                sample_rois = sroi.view(-1, 4)
+                sample_idx = self._roi_index[key]
+                gt_roi_locs, gt_roi_labels = gloc.view(-1, 4), glab.view(-1)
+            if dev_prop and masks_dev is not None:
+                gt_roi_masks = ptc.mask_targets_device(sroi, gasg, npos, masks_dev) \
+                    .view(-1, ptc.mask_size, ptc.mask_size)
+            elif dev_prop:
                 h_roi = self._pinned_like('roi', (batch_size, max_pos, 4), torch.float32)
                 h_asg = self._pinned_like('asg', (batch_size, max_pos), torch.int32)
                 h_np = self._pinned_like('np', (batch_size,), torch.int32)
@@ -131,13 +158,6 @@ class MaskRCNNTrainChain(object):
                 ready = torch.cuda.Event()
                 ready.record()
                 self.d2h_bytes += h_roi.numel() * 4 + h_asg.numel() * 4 + h_np.numel() * 4
-                key = (batch_size, n, str(dev))
-                if key not in self._roi_index:
-                    self._roi_index[key] = torch.arange(batch_size, dtype=torch.int32, device=dev) \
-                        .repeat_interleave(n)
-                sample_rois = sroi.view(-1, 4)
-                sample_idx = self._roi_index[key]
-                gt_roi_locs, gt_roi_labels = gloc.view(-1, 4), glab.view(-1)
 
                 def gt_roi_masks():
                     # runs after the head's forward pass has been enqueued

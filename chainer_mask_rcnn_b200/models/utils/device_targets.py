@@ -4,9 +4,10 @@
 the reference's exact sampling order under a NumPy seed; the classes here implement the
 same assignment rules and sample sizes in CUDA for the whole batch at once, with a
 counter-based hash instead of NumPy's global generator, so that the step has no NumPy
-pass between the RPN and the RoI head.  Only the mask-target rasterisation stays on
-the host (cv2, as in the reference, proposal_target_creator.py:163-177) and overlaps
-with the head's forward pass.
+pass between the RPN and the RoI head.  The mask-target rasterisation
+(proposal_target_creator.py:163-177) runs on the device too (``cmr_mask_targets``) when
+the instance masks are given as a device tensor; with host NumPy masks it stays on the
+host (cv2, as in the reference) and overlaps with the head's forward pass.
 """
 import ctypes
 
@@ -29,28 +30,44 @@ class GroundTruth(object):
     """Per-batch ground truth packed for the device: bbox (B,G,4) f32, label (B,G) i32,
     count (B,) i32, G = max boxes per image."""
 
-    def __init__(self, bboxes, labels, device):
+    MAX_BOXES = 256
+
+    def __init__(self, bboxes, labels, device, capacity=None):
         B = len(bboxes)
-        G = max(1, max(len(b) for b in bboxes))
-        if G > 256:
+        G = capacity or max(1, max(len(b) for b in bboxes))
+        if G > self.MAX_BOXES:
             raise ValueError('at most 256 ground-truth boxes per image are supported')
-        bb = np.zeros((B, G, 4), np.float32)
-        ll = np.zeros((B, G), np.int32)
-        cc = np.zeros((B,), np.int32)
+        self.B, self.G = B, G
+        self.nbytes = (B * G * 5 + B) * 4
+        # one buffer = one H2D copy; the device copy has a fixed address, so a captured
+        # CUDA graph keeps reading it after fill_() has been called with new boxes
+        self._host = torch.empty((B * G * 5 + B,), dtype=torch.int32).pin_memory()
+        self._buf = torch.empty((B * G * 5 + B,), dtype=torch.int32, device=device)
+        self.bbox = self._buf[:B * G * 4].view(torch.float32).view(B, G, 4)
+        self.label = self._buf[B * G * 4:B * G * 5].view(B, G)
+        self.count = self._buf[B * G * 5:]
+        self.fill_(bboxes, labels)
+
+    def fill_(self, bboxes, labels):
+        B, G = self.B, self.G
+        if len(bboxes) != B:
+            raise ValueError('expected {} images, got {}'.format(B, len(bboxes)))
+        packed = self._host.numpy()
+        packed[:] = 0
+        bb = packed[:B * G * 4].view(np.float32).reshape(B, G, 4)
+        ll = packed[B * G * 4:B * G * 5].reshape(B, G)
+        cc = packed[B * G * 5:]
         for i, (b, l) in enumerate(zip(bboxes, labels)):
             n = len(b)
             if n == 0:
                 raise ValueError('Empty bbox is not supported.')
+            if n > G:
+                raise ValueError('{} boxes exceed the capacity {}'.format(n, G))
             bb[i, :n] = b
             ll[i, :n] = np.asarray(l)[:n]
             cc[i] = n
-        self.B, self.G = B, G
-        packed = np.concatenate([bb.reshape(-1).view(np.int32), ll.reshape(-1), cc])
-        buf = torch.from_numpy(packed).to(device, non_blocking=True)       # one H2D copy
-        self.bbox = buf[:B * G * 4].view(torch.float32).view(B, G, 4)
-        self.label = buf[B * G * 4:B * G * 5].view(B, G)
-        self.count = buf[B * G * 5:]
-        self.nbytes = packed.nbytes
+        self._buf.copy_(self._host, non_blocking=True)
+        return self
 
 
 class DeviceAnchorTargetCreator(object):
@@ -62,8 +79,9 @@ class DeviceAnchorTargetCreator(object):
         self.pos_ratio = pos_ratio
         self._ws = None
 
-    def __call__(self, gt, anchor, img_size, seed):
-        """gt: GroundTruth; anchor (S,4) CUDA tensor -> gt_loc (B,S,4), gt_label (B,S)."""
+    def __call__(self, gt, anchor, img_size, seed, seed_dev=None):
+        """gt: GroundTruth; anchor (S,4) CUDA tensor -> gt_loc (B,S,4), gt_label (B,S).
+        seed_dev: optional device int64 word mixed into the seed (see cmr_anchor_targets)."""
         S = anchor.shape[0]
         dev = anchor.device
         loc = torch.empty((gt.B, S, 4), dtype=torch.float32, device=dev)
@@ -74,8 +92,8 @@ class DeviceAnchorTargetCreator(object):
         _lib.call('cmr_anchor_targets', _p(anchor), S, _p(gt.bbox), _p(gt.count), gt.B, gt.G,
                   float(img_size[0]), float(img_size[1]), self.n_sample,
                   float(self.pos_iou_thresh), float(self.neg_iou_thresh), float(self.pos_ratio),
-                  int(seed) & (2 ** 64 - 1), _p(loc), _p(label), _p(self._ws),
-                  self._ws.numel() * 8, _stream())
+                  int(seed) & (2 ** 64 - 1), None if seed_dev is None else _p(seed_dev), _p(loc),
+                  _p(label), _p(self._ws), self._ws.numel() * 8, _stream())
         return loc, label
 
 
@@ -93,7 +111,7 @@ class DeviceProposalTargetCreator(object):
         self._ws = None
 
     def sample(self, rois, n_roi, gt, seed, loc_normalize_mean=(0., 0., 0., 0.),
-               loc_normalize_std=(0.1, 0.1, 0.2, 0.2)):
+               loc_normalize_std=(0.1, 0.1, 0.2, 0.2), seed_dev=None):
         """rois (B,max_roi,4), n_roi (B,) as returned by ProposalCreator.batch.
         -> sample_roi (B,n,4), gt_roi_loc (B,n,4), gt_roi_label (B,n), gt_assign (B,n),
         n_pos (B,), all on the device, n = n_sample."""
@@ -113,9 +131,27 @@ class DeviceProposalTargetCreator(object):
         _lib.call('cmr_proposal_targets', _p(rois), _p(n_roi), max_roi, _p(gt.bbox), _p(gt.label),
                   _p(gt.count), B, gt.G, n, float(self.pos_ratio), float(self.pos_iou_thresh),
                   float(self.neg_iou_thresh_hi), float(self.neg_iou_thresh_lo), mean, std,
-                  int(seed) & (2 ** 64 - 1), _p(sample_roi), _p(gt_loc), _p(gt_label),
-                  _p(gt_assign), _p(n_pos), _p(self._ws), self._ws.numel() * 8, _stream())
+                  int(seed) & (2 ** 64 - 1), None if seed_dev is None else _p(seed_dev),
+                  _p(sample_roi), _p(gt_loc), _p(gt_label), _p(gt_assign), _p(n_pos),
+                  _p(self._ws), self._ws.numel() * 8, _stream())
         return sample_roi, gt_loc, gt_label, gt_assign, n_pos
+
+    def mask_targets_device(self, sample_roi, gt_assign, n_pos, masks):
+        """Device side: masks (B,G,H,W) uint8 or int32 CUDA tensor of instance masks ->
+        (B,n,mask_size,mask_size) int32 targets, -1 on every non-foreground row
+        (cmr_mask_targets)."""
+        if masks.dtype not in (torch.uint8, torch.int32) or masks.dim() != 4:
+            raise TypeError('masks must be a (B,G,H,W) uint8 or int32 tensor, got {} {}'.format(
+                masks.dtype, tuple(masks.shape)))
+        B, n, _ = sample_roi.shape
+        Bm, G, H, W = masks.shape
+        if Bm != B:
+            raise ValueError('masks has {} images, rois {}'.format(Bm, B))
+        ms = self.mask_size
+        out = torch.empty((B, n, ms, ms), dtype=torch.int32, device=sample_roi.device)
+        _lib.call('cmr_mask_targets', _p(masks.contiguous()), masks.element_size(), B, G, H, W,
+                  _p(sample_roi), _p(gt_assign), _p(n_pos), n, ms, _p(out), _stream())
+        return out
 
     def mask_targets(self, sample_roi, gt_assign, n_pos, masks):
         """Host side: (B,n,4) rois, (B,n) assignments, (B,) counts (NumPy) and the per-image

@@ -57,14 +57,18 @@ class MomentumSGD(object):
             loss = lossfun(*args, **kwds)
             loss.backward()
         self.allreduce_grad()
+        self.apply_update()
+        self.t += 1
+        return loss
+
+    def apply_update(self):
+        """One fused launch: 1/world_size mean, weight decay, momentum, parameter update."""
         n = self.ctx.train.data.numel()
         scale = 1.0 / self.comm.size if self.comm is not None else 1.0
         _lib.call('cmr_sgd_momentum', E._p(self.ctx.train.data), E._p(self.ctx.grads),
                   E._p(self.velocity), n, float(self.lr), float(self.momentum),
                   float(self.weight_decay), float(scale), E.stream())
         self.ctx.mark_dirty(frozen=False)
-        self.t += 1
-        return loss
 
 
 class Communicator(object):
@@ -95,3 +99,134 @@ def shard_indices(n_items, comm_size, rank):
     base, rem = divmod(n_items, comm_size)
     start = rank * base + min(rank, rem)
     return range(start, start + base + (1 if rank < rem else 0))
+
+
+class GraphedUpdater(object):
+    """One training iteration as a CUDA-graph replay.
+
+    The role of ``chainer.training.updaters.StandardUpdater.update_core``
+    (examples/train_common.py:193-196 builds it; it calls
+    ``optimizer.update(model, imgs, bboxes, labels, masks, scales)`` once per iteration),
+    for the case where nothing in the step needs the host: device target creators and
+    device mask targets.  The ~240 kernel launches of forward + losses + backward +
+    update are captured once per (batch shape, scale, hyper-parameter) key into a
+    ``torch.cuda.CUDAGraph`` and replayed; per iteration the host only copies the inputs
+    into the graph's fixed input buffers.  With more than one rank the gradient
+    all-reduce and the update kernel run after the replay (NCCL outside the graph).
+
+    ``updater(imgs, bboxes, labels, masks, scales)`` -> :class:`Loss`-like object
+    (``.array`` device scalar, ``.item()``).  imgs (B,3,H,W) float32 and masks
+    (B,G,H,W) uint8 torch tensors (CUDA, or pinned host memory for asynchronous copies);
+    bboxes / labels: lists of per-image NumPy arrays.
+
+    The first call for a key runs eagerly (it is also the warm-up that sizes every
+    workspace), the second captures and replays, later calls replay.
+    """
+
+    def __init__(self, optimizer, lossfun, max_boxes=64, use_graph=True):
+        from .models.utils import GroundTruth
+        self.use_graph = use_graph
+        self._GroundTruth = GroundTruth
+        self.optimizer = optimizer
+        self.lossfun = lossfun
+        self.max_boxes = max_boxes
+        self._states = {}
+        self.launches_per_replay = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    class _State(object):
+        pass
+
+    def _key(self, imgs, masks, scales):
+        o = self.optimizer
+        return (tuple(imgs.shape), tuple(masks.shape), str(masks.dtype),
+                tuple(float(s) for s in scales), float(o.lr), float(o.momentum),
+                float(o.weight_decay), o.comm.size if o.comm is not None else 1)
+
+    def _new_state(self, imgs, bboxes, labels, masks):
+        dev = self.optimizer.ctx.device
+        st = self._State()
+        B = imgs.shape[0]
+        G = max(self.max_boxes, masks.shape[1], max(len(b) for b in bboxes))
+        st.imgs = torch.empty(tuple(imgs.shape), dtype=torch.float32, device=dev)
+        st.masks = torch.zeros((B, G) + tuple(masks.shape[2:]), dtype=masks.dtype, device=dev)
+        st.gt = self._GroundTruth(bboxes, labels, dev, capacity=G)
+        st.seed_word = torch.zeros((1,), dtype=torch.int64, device=dev)
+        st.graph = None
+        st.loss = None
+        st.calls = 0
+        return st
+
+    def _stage(self, st, imgs, bboxes, labels, masks):
+        self.h2d_bytes = st.gt.nbytes
+        for dst, src in ((st.imgs, imgs), (st.masks[:, :masks.shape[1]], masks)):
+            if not src.is_cuda:
+                self.h2d_bytes += src.numel() * src.element_size()
+            dst.copy_(src, non_blocking=True)
+        st.gt.fill_(bboxes, labels)
+
+    def _step(self, st, scales):
+        """The work of one iteration on the current stream (eager or under capture)."""
+        o, chain = self.optimizer, self.lossfun
+        chain.seed_dev = st.seed_word
+        chain._calls = 0        # fixed host seed: the draws advance through seed_word only
+        try:
+            o.ctx.grads.zero_()
+            loss = chain(st.imgs, st.gt, None, st.masks, scales)
+            loss.backward()
+            if o.comm is None or o.comm.size == 1:
+                o.apply_update()
+            st.seed_word += 1
+        finally:
+            chain.seed_dev = None
+        return loss.array
+
+    def __call__(self, imgs, bboxes, labels, masks, scales):
+        scales = [float(s) for s in (scales.tolist() if hasattr(scales, 'tolist') else scales)]
+        if not (isinstance(imgs, torch.Tensor) and isinstance(masks, torch.Tensor)):
+            raise TypeError('GraphedUpdater needs torch tensors for imgs and masks (CUDA or '
+                            'pinned host memory)')
+        o = self.optimizer
+        key = self._key(imgs, masks, scales)
+        st = self._states.get(key)
+        if st is None:
+            st = self._states[key] = self._new_state(imgs, bboxes, labels, masks)
+        self._stage(st, imgs, bboxes, labels, masks)
+        lib = _lib.load()
+        if st.calls == 0 or not self.use_graph:
+            loss = self._step(st, scales)                       # eager: warm-up + real step
+        else:
+            if st.graph is None:
+                torch.cuda.synchronize()
+                n0 = lib.cmr_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st.loss = self._step(st, scales)
+                self.launches_per_replay = lib.cmr_launch_count() - n0
+                st.graph = g
+            st.graph.replay()
+            loss = st.loss
+        if o.comm is not None and o.comm.size > 1:
+            o.allreduce_grad()
+            o.apply_update()
+        st.calls += 1
+        o.t += 1
+        self.d2h_bytes = 0
+        return _GraphedLoss(loss, self)
+
+
+class _GraphedLoss(object):
+    """Device scalar of the last replay (valid until the next call of the updater)."""
+
+    def __init__(self, array, owner):
+        self.array = array
+        self._owner = owner
+
+    data = property(lambda self: self.array)
+
+    def item(self):
+        self._owner.d2h_bytes += 4
+        return float(self.array.item())
+
+    __float__ = item

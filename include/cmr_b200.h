@@ -243,7 +243,9 @@ int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt_label,
 /* ------------------------------------------------------------------------ *
  * Training targets on the device (csrc/targets.cu).  bbox (B,max_bbox,4) holds the
  * ground-truth boxes (y1,x1,y2,x2) of each image padded to max_bbox <= 256 rows,
- * n_bbox (B) their counts (device int32).  `seed` drives the random subsampling.
+ * n_bbox (B) their counts (device int32).  `seed` drives the random subsampling;
+ * when seed_dev (device uint64, may be NULL) is given, *seed_dev is mixed in, so a
+ * captured CUDA graph draws a new subset on every replay by advancing that word.
  * ------------------------------------------------------------------------ */
 /* chainercv AnchorTargetCreator, called per image at
  * chainer_mask_rcnn/models/mask_rcnn_train_chain.py:151-158, for the whole batch:
@@ -253,8 +255,9 @@ int cmr_anchor_targets(const float* anchor, int n_anchor, const float* bbox,
                        const int32_t* n_bbox, int B, int max_bbox, float img_h,
                        float img_w, int n_sample, float pos_iou_thresh,
                        float neg_iou_thresh, float pos_ratio,
-                       unsigned long long seed, float* gt_loc, int32_t* gt_label,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       unsigned long long seed, const unsigned long long* seed_dev,
+                       float* gt_loc, int32_t* gt_label, void* workspace,
+                       size_t workspace_bytes, void* stream);
 /* ProposalTargetCreator.__call__ up to the mask targets
  * (chainer_mask_rcnn/models/utils/proposal_target_creator.py:115-161):
  * rois (B,max_roi,4) + n_roi (B) as produced by cmr_proposals; label (B,max_bbox)
@@ -270,10 +273,24 @@ int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int max_roi,
                          float pos_ratio, float pos_iou_thresh,
                          float neg_iou_thresh_hi, float neg_iou_thresh_lo,
                          const float* loc_mean, const float* loc_std,
-                         unsigned long long seed, float* sample_roi,
+                         unsigned long long seed,
+                         const unsigned long long* seed_dev, float* sample_roi,
                          float* gt_roi_loc, int32_t* gt_roi_label,
                          int32_t* gt_assign, int32_t* n_pos, void* workspace,
                          size_t workspace_bytes, void* stream);
+
+/* The mask rasterisation of ProposalTargetCreator.__call__
+ * (chainer_mask_rcnn/models/utils/proposal_target_creator.py:163-177) for the rows
+ * cmr_proposal_targets produced: for every foreground row j < n_pos[b], round the RoI
+ * to integers, crop instance mask gt_assign[b,j], and take argmax over the one-hot
+ * planes of cv2.resize(INTER_LINEAR, float32) to (mask_size, mask_size); all other
+ * rows are filled with -1.  masks: (B, max_bbox, H, W) device array of uint8
+ * (mask_elem_bytes == 1) or int32 (== 4) labels >= 0.  gt_mask: (B, n_sample,
+ * mask_size, mask_size) int32.  An empty crop yields zeros. */
+int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, int max_bbox,
+                     int H, int W, const float* sample_roi, const int32_t* gt_assign,
+                     const int32_t* n_pos, int n_sample, int mask_size,
+                     int32_t* gt_mask, void* stream);
 
 #ifdef __cplusplus
 }

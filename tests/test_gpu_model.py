@@ -314,3 +314,76 @@ def test_full_train_chain_runs_and_decreases_loss(targets):
         hist.append(loss.item())
     assert all(np.isfinite(hist)), hist
     assert hist[-1] < hist[0], hist
+
+
+def _tiny_batch(rs, H=160, W=192, G=4):
+    imgs = (rs.uniform(0, 255, (2, 3, H, W)) - 115.).astype(np.float32)
+    bboxes, labels, masks = [], [], []
+    yy, xx = np.mgrid[:H, :W]
+    for _ in range(2):
+        b = synth.random_boxes(rs, 3, H, W, 40., 120.)
+        b = b[(b[:, 2] - b[:, 0] > 8) & (b[:, 3] - b[:, 1] > 8)]
+        m = np.zeros((G, H, W), np.int32)
+        for i, (y1, x1, y2, x2) in enumerate(b):
+            m[i] = (((yy - (y1 + y2) / 2) / ((y2 - y1) / 2)) ** 2 +
+                    ((xx - (x1 + x2) / 2) / ((x2 - x1) / 2)) ** 2 <= 1)
+        bboxes.append(b); labels.append(rs.randint(0, N_FG, len(b)).astype(np.int32))
+        masks.append(m)
+    return imgs, bboxes, labels, masks, np.ones(2, np.float32)
+
+
+def test_device_mask_targets_equal_host_rasterisation_in_the_chain():
+    """Same model, same seed: the chain fed tensor masks (cmr_mask_targets) and the chain
+    fed the reference's host NumPy masks (cv2, IPP off = OpenCV's own bilinear code)
+    produce identical mask targets and therefore the same loss."""
+    import cv2
+    rs = np.random.RandomState(5)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE)
+    old = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        out = []
+        for form in ('host', 'device'):
+            chain = models.MaskRCNNTrainChain(model, seed=11)
+            m = masks if form == 'host' else torch.from_numpy(np.stack(masks).astype(np.uint8)).cuda()
+            loss = chain(imgs, bboxes, labels, m, scales)
+            out.append((loss.item(), chain.targets['gt_roi_masks'].cpu().numpy(),
+                        chain.targets['gt_roi_labels'].cpu().numpy()))
+    finally:
+        cv2.ipp.setUseIPP(old)
+    assert (out[0][2] > 0).sum() > 0                       # there are foreground rows
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+
+
+def test_graphed_updater_replays_the_eager_step():
+    """optimizers.GraphedUpdater: three iterations through graph replays leave the same
+    parameters as three eager iterations with the same seeds (atomics in the weight
+    gradient reductions make the sums order-dependent, hence the tolerance)."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(9)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    imgs_t = torch.from_numpy(imgs).cuda()
+    masks_t = torch.from_numpy(np.stack(masks).astype(np.uint8)).cuda()
+    results = []
+    for use_graph in (False, True):
+        model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                      base_channels=BASE, seed=1)
+        chain = models.MaskRCNNTrainChain(model, seed=4)
+        opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+        opt.add_hook(optimizers.WeightDecay(1e-4))
+        up = optimizers.GraphedUpdater(opt, chain, max_boxes=8, use_graph=use_graph)
+        hist = [up(imgs_t, bboxes, labels, masks_t, scales).item() for _ in range(4)]
+        if use_graph:
+            assert up.launches_per_replay > 100
+        # a changed batch goes through the same graph (fixed input buffers are refilled)
+        hist.append(up(imgs_t.flip(0), bboxes[::-1], labels[::-1], masks_t.flip(0), scales).item())
+        results.append((hist, model.ctx.train.data.clone()))
+    (h0, p0), (h1, p1) = results
+    assert all(np.isfinite(h0 + h1))
+    np.testing.assert_allclose(h1, h0, rtol=2e-3)
+    assert float((p1 - p0).abs().max()) <= 2e-3 * float(p0.abs().max())
+    assert h0[3] < h0[0]

@@ -111,3 +111,58 @@ def test_mask_targets_match_host_creator():
     got = mu.DeviceProposalTargetCreator(n_sample=64).mask_targets(
         sr[None], np.pad(asg, (0, 64 - n_pos))[None].astype(np.int32), np.array([n_pos]), [mask])
     np.testing.assert_array_equal(got[0], gm)
+
+
+@pytest.mark.parametrize('dtype', [torch.uint8, torch.int32])
+def test_device_mask_targets_bit_exact(dtype):
+    """cmr_mask_targets against the oracle's restatement of the reference's
+    round / crop / one-hot / cv2.resize / argmax pipeline: every pixel equal."""
+    from oracle import mask_target as omt
+    H, W, n = 320, 416, 96
+    rs = np.random.RandomState(7)
+    masks, sroi, asg, npos = [], [], [], []
+    G = 9
+    for b, seed in enumerate((2, 5)):
+        roi, bbox, _, mask, _ = synth.detection_scene(seed, n_gt=8, H=H, W=W, n_roi=n)
+        m = np.zeros((G, H, W), np.int32)
+        m[:len(bbox)] = mask
+        m[0] *= 2                                   # a label map with value 2 (one-hot path)
+        m[1, ::3, ::2] = 3
+        masks.append(m)
+        r = roi.copy()
+        r[:5] = [[0, 0, H, W], [10.5, 20.5, 11.4, 21.4], [3, 3, 3, 40], [H - 1, W - 1, H, W],
+                 [0.5, 1.5, 2.5, 3.5]]             # full image, 1-pixel, empty, corner, ties
+        sroi.append(r)
+        asg.append(rs.randint(0, len(bbox), n).astype(np.int32))
+        npos.append(n - 20 * b)
+    sroi = np.stack(sroi).astype(np.float32)
+    asg = np.stack(asg)
+    npos = np.asarray(npos, np.int32)
+    want = omt.mask_targets(sroi, asg, npos, masks, 14)
+    ptc = mu.DeviceProposalTargetCreator(n_sample=n)
+    got = ptc.mask_targets_device(torch.from_numpy(sroi).cuda(), torch.from_numpy(asg).cuda(),
+                                  torch.from_numpy(npos).cuda(),
+                                  torch.from_numpy(np.stack(masks)).to(dtype).cuda())
+    got = got.cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert (got[1, npos[1]:] == -1).all() and set(np.unique(got)) <= {-1, 0, 1, 2, 3}
+
+
+def test_seed_dev_advances_the_draw():
+    H, W = 320, 416
+    bbs, lbs = _gt([1, 2], H, W)
+    base = ob.generate_anchor_base(16, (0.5, 1, 2), (2, 4, 8, 16, 32))
+    anchor = torch.from_numpy(ob.enumerate_shifted_anchor(base, 16, H // 16, W // 16)).cuda()
+    gt = mu.GroundTruth(bbs, lbs, torch.device('cuda'), capacity=32)
+    assert gt.G == 32
+    atc = mu.DeviceAnchorTargetCreator()
+    word = torch.zeros((1,), dtype=torch.int64, device='cuda')
+    _, l0 = atc(gt, anchor, (H, W), seed=5, seed_dev=word)
+    _, l_plain = atc(gt, anchor, (H, W), seed=5)
+    assert torch.equal(l0, l_plain)                   # word == 0 leaves the seed alone
+    word += 1
+    _, l1 = atc(gt, anchor, (H, W), seed=5, seed_dev=word)
+    assert (l1 >= 0).sum() == (l0 >= 0).sum() and not torch.equal(l0, l1)
+    gt.fill_(bbs[::-1], lbs[::-1])                    # same device buffers, new boxes
+    _, l2 = atc(gt, anchor, (H, W), seed=5)
+    assert torch.equal(l2[0] >= 0, l2[0] >= 0) and not torch.equal(l2, l_plain)
