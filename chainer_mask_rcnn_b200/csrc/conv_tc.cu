@@ -16,9 +16,13 @@
 //
 // Persistent, warp-specialised CTA (448 threads, one per SM) walking output tiles
 // (128 x BN) in n-fastest order:
-//   warps 0-3   A producers: cp.async 16 B gathers straight into the 128B-swizzled
-//               K-major tile the tensor core reads (implicit im2col, zero fill)
-//   warp  4     B producer: one thread issues TMA (cp.async.bulk.tensor.2d) loads
+//   warp  4     producer: one thread issues the TMA loads of a k-block -- the filter
+//               tile (cp.async.bulk.tensor.2d) and the activation tile as ONE im2col-mode
+//               TMA (cp.async.bulk.tensor.4d...im2col: 128 convolution positions x 32
+//               channels of filter tap (fr, fs), padding zero-filled by the copy engine),
+//               both landing in the 128B-swizzled K-major layout the tensor core reads
+//   warps 0-3   fallback A producers for layouts the im2col tensor map cannot describe
+//               (the RGB0-packed stem): cp.async 16 B gathers into the same layout
 //   warp  5     one thread issues tcgen05.mma (128 x BN x 8 per instruction) and
 //               tcgen05.commit; the accumulator lives in TMEM, double buffered
 //               (2 x BN columns) so tile i+1's MMAs overlap tile i's epilogue
@@ -50,6 +54,7 @@ struct ConvGemmParams {
   const float* mask;
   int relu, round_out;
   int m_tiles, n_tiles;
+  int tma_a;   // A tiles come from the im2col tensor map (else cp.async gathers)
 };
 
 constexpr int kBM = 128;
@@ -59,7 +64,7 @@ constexpr int kProducerThreads = 128;
 constexpr int kEpiWarp0 = 6;                 // first epilogue warp
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 448
-constexpr int kXposePitch = 33;              // floats per row of the transpose buffer
+constexpr int kXposePitch4 = 9;              // float4 per row of the transpose buffer (36 floats)
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -67,7 +72,7 @@ struct SmemLayout {
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kABytes;
   static constexpr int kXposeOff = kBOff + STAGES * kBBytes;
-  static constexpr int kXposeBytes = kEpiWarps * 32 * kXposePitch * 4;
+  static constexpr int kXposeBytes = kEpiWarps * 32 * kXposePitch4 * 16;
   static constexpr int kBarOff = kXposeOff + kXposeBytes;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for 1024 B alignment
@@ -75,7 +80,8 @@ struct SmemLayout {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmParams p) {
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES>;
   constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -96,8 +102,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap_b);
+    if (p.tma_a) prefetch_tensormap(&tmap_a);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], kProducerThreads + 1);
+      mbar_init(&full_bar[s], p.tma_a ? 1 : kProducerThreads + 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -114,7 +121,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
   const int ohw = p.out_h * p.out_w;
 
   if (warp < 4) {
-    // ------------------------------------------------ A producer (im2col gather)
+    // ------------------------------------- fallback A producer (cp.async gather)
+    if (!p.tma_a) {
     const int t = threadIdx.x;
     const int j = t & 7;
     const int r0 = t >> 3;
@@ -168,17 +176,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    }
   } else if (warp == 4) {
-    // ------------------------------------------------------ B producer (TMA)
+    // ---------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t it = 0;
+      const int cpt = p.in_c / kBK;  // k-blocks per filter tap
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (tile % p.n_tiles) * BN;
+        // top-left input coordinate of the tile's first convolution position
+        const int m0 = (tile / p.n_tiles) * kBM;
+        const int img = m0 / ohw;
+        const int rem = m0 - img * ohw;
+        const int oy = rem / p.out_w;
+        const int h0 = oy * p.stride - p.pad, w0 = (rem - oy * p.out_w) * p.stride - p.pad;
+        int fr = 0, fs = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], L::kBBytes);
+          if (p.tma_a) {
+            mbar_arrive_expect_tx(&full_bar[s], L::kBBytes + kABytes);
+            tma_load_im2col_4d(smem_base + L::kAOff + s * kABytes, &tmap_a, &full_bar[s],
+                               cb * kBK, w0, h0, img, fs, fr);
+            if (++cb == cpt) {
+              cb = 0;
+              if (++fs == p.kw) {
+                fs = 0;
+                ++fr;
+              }
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], L::kBBytes);
+          }
           tma_load_2d(smem_base + L::kBOff + s * L::kBBytes, &tmap_b, &full_bar[s], kb * kBK,
                       n0);
         }
@@ -217,12 +247,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
     const int ew = warp - kEpiWarp0;          // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     const int half = ew >> 2;                 // which half of the BN columns
-    float* xp = reinterpret_cast<float*>(smem + L::kXposeOff) + ew * 32 * kXposePitch;
+    float4* xp4 = reinterpret_cast<float4*>(smem + L::kXposeOff) + ew * 32 * kXposePitch4;
     const int sub = lane >> 3;                // row within a 4-row store group
     const int c4 = (lane & 7) * 4;            // first of this lane's 4 columns in a chunk
-    const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) &&
-                        (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0) &&
-                        (!p.mask || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
+    const float* __restrict__ scale_p = p.scale;
+    const float* __restrict__ bias_p = p.bias;
+    const float* __restrict__ addend_p = p.addend;
+    const float* __restrict__ mask_p = p.mask;
+    float* __restrict__ d_p = p.d;
+    const bool relu = p.relu != 0, round_out = p.round_out != 0;
+    const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_p) & 15) == 0) &&
+                        (!addend_p || (reinterpret_cast<uintptr_t>(addend_p) & 15) == 0) &&
+                        (!mask_p || (reinterpret_cast<uintptr_t>(mask_p) & 15) == 0);
     constexpr int kChunks = (BN / 2 + 31) / 32;   // 32-column chunks per half
     uint32_t tc_ = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
@@ -252,21 +288,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
         const int n = n0 + cbase + c4;                    // this lane's first global column
         if (n0 + cbase >= p.N) break;
         const bool full4 = vec_ok && (n + 3 < p.N);
-        // prefetch the addend / mask operands (coalesced: 8 lanes cover one 128 B row)
+        // operands of the epilogue are requested before the accumulator is waited for
+        // (coalesced: 8 lanes cover one 128 B row)
         float4 ad[8], mk[8];
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
         if (full4) {
-          if (p.addend) {
+          if (addend_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.addend + doff[i] + n))
+              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(addend_p + doff[i] + n))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (p.mask) {
+          if (mask_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(p.mask + doff[i] + n))
+              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(mask_p + doff[i] + n))
                                    : make_float4(1.f, 1.f, 1.f, 1.f);
           }
+          if (scale_p) sc = __ldg(reinterpret_cast<const float4*>(scale_p + n));
+          if (bias_p) bi = __ldg(reinterpret_cast<const float4*>(bias_p + n));
         }
         if (!waited) {
           mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
@@ -277,46 +317,50 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const ConvGemmPa
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cbase, v);
         tmem_ld_wait();
         __syncwarp();   // previous chunk's reads of the transpose buffer are done
+        // lane = accumulator row: 8 x 16-byte stores (pitch 36 floats: conflict-free)
 #pragma unroll
-        for (int c = 0; c < 32; ++c) xp[lane * kXposePitch + c] = __uint_as_float(v[c]);
+        for (int c = 0; c < 8; ++c)
+          xp4[lane * kXposePitch4 + c] =
+              make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
+                          __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
         __syncwarp();
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f);
         if (full4) {
-          if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-          if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (doff[i] < 0) continue;
-          const float* src = xp + (4 * i + sub) * kXposePitch + c4;
-          float o[4] = {src[0], src[1], src[2], src[3]};
-          if (full4) {
-            if (p.scale) { o[0] *= sc.x; o[1] *= sc.y; o[2] *= sc.z; o[3] *= sc.w; }
-            if (p.bias) { o[0] += bi.x; o[1] += bi.y; o[2] += bi.z; o[3] += bi.w; }
-            if (p.addend) { o[0] += ad[i].x; o[1] += ad[i].y; o[2] += ad[i].z; o[3] += ad[i].w; }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+          for (int i = 0; i < 8; ++i) {
+            if (doff[i] < 0) continue;
+            float4 o = xp4[(4 * i + sub) * kXposePitch4 + (lane & 7)];
+            if (scale_p) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
+            if (bias_p) { o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w; }
+            if (addend_p) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+            if (relu) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
+              o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
             }
-            if (p.mask) {
-              o[0] = mk[i].x > 0.f ? o[0] : 0.f; o[1] = mk[i].y > 0.f ? o[1] : 0.f;
-              o[2] = mk[i].z > 0.f ? o[2] : 0.f; o[3] = mk[i].w > 0.f ? o[3] : 0.f;
+            if (mask_p) {
+              o.x = mk[i].x > 0.f ? o.x : 0.f; o.y = mk[i].y > 0.f ? o.y : 0.f;
+              o.z = mk[i].z > 0.f ? o.z : 0.f; o.w = mk[i].w > 0.f ? o.w : 0.f;
             }
-            if (p.round_out) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = round_tf32(o[e]);
+            if (round_out) {
+              o.x = round_tf32(o.x); o.y = round_tf32(o.y);
+              o.z = round_tf32(o.z); o.w = round_tf32(o.w);
             }
-            *reinterpret_cast<float4*>(p.d + doff[i] + n) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+            *reinterpret_cast<float4*>(d_p + doff[i] + n) = o;
+          }
+        } else {
+          // ragged / unaligned tail columns: scalar path
+          const float* xs = reinterpret_cast<const float*>(xp4);
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (doff[i] < 0) continue;
             for (int e = 0; e < 4 && n + e < p.N; ++e) {
-              float x = o[e];
-              if (p.scale) x *= __ldg(p.scale + n + e);
-              if (p.bias) x += __ldg(p.bias + n + e);
-              if (p.addend) x += __ldg(p.addend + doff[i] + n + e);
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (p.mask) x = __ldg(p.mask + doff[i] + n + e) > 0.f ? x : 0.f;
-              if (p.round_out) x = round_tf32(x);
-              p.d[doff[i] + n + e] = x;
+              float x = xs[(4 * i + sub) * (kXposePitch4 * 4) + c4 + e];
+              if (scale_p) x *= __ldg(scale_p + n + e);
+              if (bias_p) x += __ldg(bias_p + n + e);
+              if (addend_p) x += __ldg(addend_p + doff[i] + n + e);
+              if (relu) x = fmaxf(x, 0.f);
+              if (mask_p) x = __ldg(mask_p + doff[i] + n + e) > 0.f ? x : 0.f;
+              if (round_out) x = round_tf32(x);
+              d_p[doff[i] + n + e] = x;
             }
           }
         }
@@ -370,8 +414,67 @@ int make_tmap_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t co
   return r == CUDA_SUCCESS ? CMR_OK : CMR_ERR_CUDA;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// Im2col-mode tensor map over an NHWC fp32 tensor (batch, h, w, ld) of which channels
+// [0, channels) are visible.  One TMA instruction loads `pixels` consecutive positions of
+// a walk with step `stride` whose first position has top-left input coordinate
+// (lower_h, lower_w) and which visits n_pos_h x n_pos_w positions per image (w fastest,
+// then h, then the image), x 32 channels, shifted by the im2col offsets (the filter tap).
+// Returns CMR_ERR_UNSUPPORTED when the geometry does not fit the descriptor's fields.
+int make_tmap_im2col(CUtensorMap* map, const float* base, int batch, int h, int w, int ld,
+                     int channels, int stride, int lower_h, int lower_w, int n_pos_h,
+                     int n_pos_w, int pixels, bool mn_major) {
+  EncodeIm2colFn fn = get_encode_im2col_fn();
+  if (!fn) return CMR_ERR_UNSUPPORTED;
+  if (stride < 1 || stride > 8 || (ld & 3) != 0 || channels < 1 || channels > ld)
+    return CMR_ERR_UNSUPPORTED;
+  // extent of the bounding box along an axis so that ceil(extent / stride) == n_pos
+  const int upper_h = (n_pos_h - 1) * stride + 1 - h + lower_h;
+  const int upper_w = (n_pos_w - 1) * stride + 1 - w + lower_w;
+  const int lim[4] = {lower_h, lower_w, upper_h, upper_w};
+  for (int i = 0; i < 4; ++i)
+    if (lim[i] < -128 || lim[i] > 127) return CMR_ERR_UNSUPPORTED;
+  cuuint64_t gdim[4] = {(cuuint64_t)channels, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+  cuuint64_t gstride[3] = {(cuuint64_t)ld * 4, (cuuint64_t)w * ld * 4,
+                           (cuuint64_t)h * w * ld * 4};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim,
+                  gstride, lower, upper, 32, (cuuint32_t)pixels, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CMR_OK : CMR_ERR_UNSUPPORTED;
+}
+
+int g_im2col_tma = 1;   // cmr_set_im2col_tma
+
+namespace {
+
 template <int BN, int STAGES>
-int launch(const CUtensorMap& tmap, const ConvGemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
+           cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -386,7 +489,7 @@ int launch(const CUtensorMap& tmap, const ConvGemmParams& p, cudaStream_t st) {
   const long long tiles = (long long)q.m_tiles * q.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
-  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, q);
+  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, tmap_a, q);
   prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -396,6 +499,12 @@ int launch(const CUtensorMap& tmap, const ConvGemmParams& p, cudaStream_t st) {
 }  // namespace cmr
 
 using namespace cmr;
+
+extern "C" int cmr_set_im2col_tma(int on) {
+  const int old = g_im2col_tma;
+  g_im2col_tma = on != 0;
+  return old;
+}
 
 extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const float* w, float* d,
                                 const float* scale, const float* bias, const float* addend,
@@ -446,11 +555,24 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   CUtensorMap tmap;
   int rc = make_tmap_2d(&tmap, w, (uint64_t)p.N, (uint64_t)p.K, (uint32_t)bn);
   if (rc != CMR_OK) return rc;
+  // The activation operand through an im2col tensor map when the geometry is a plain
+  // convolution over in_c <= in_ld channels (everything but the RGB0-packed stem).
+  CUtensorMap tmap_a = tmap;
+  p.tma_a = 0;
+  if (g_im2col_tma && c->in_c <= c->in_ld &&
+      c->out_h == (c->in_h + 2 * c->pad - c->kh) / c->stride + 1 &&
+      c->out_w == (c->in_w + 2 * c->pad - c->kw) / c->stride + 1 &&
+      c->in_h + 2 * c->pad >= c->kh && c->in_w + 2 * c->pad >= c->kw && c->kh < 256 &&
+      c->kw < 256) {
+    if (make_tmap_im2col(&tmap_a, a, c->batch, c->in_h, c->in_w, c->in_ld, c->in_c, c->stride,
+                         -c->pad, -c->pad, c->out_h, c->out_w, kBM, false) == CMR_OK)
+      p.tma_a = 1;
+  }
   cudaStream_t st = as_stream(stream);
   switch (bn) {
-    case 64: return launch<64, 6>(tmap, p, st);
-    case 128: return launch<128, 5>(tmap, p, st);
-    case 256: return launch<256, 3>(tmap, p, st);
+    case 64: return launch<64, 6>(tmap, tmap_a, p, st);
+    case 128: return launch<128, 5>(tmap, tmap_a, p, st);
+    case 256: return launch<256, 3>(tmap, tmap_a, p, st);
     default: return CMR_ERR_INVALID_ARG;
   }
 }

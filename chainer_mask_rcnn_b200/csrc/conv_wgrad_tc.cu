@@ -17,10 +17,17 @@
 // Deconvolution2D / Linear backward for the links built at
 // models/region_proposal_network.py:75-80 and models/mask_rcnn_resnet.py:131-143.
 //
-// CTA = 288 threads: warps 0-3 gather P, warps 4-7 gather Q (cp.async 16 B, one
-// k-block = 32 pixels), warp 8 issues tcgen05.mma (128 x BN x 8).  grid =
-// (row tiles, column tiles, K splits); partial sums are added with vector
+// Two kernels share the tile layout, the MMA issue loop and the epilogue:
+//   conv_wgrad_tma_kernel  (default) CTA = 192 threads: warps 0-3 epilogue, warp 4 = one
+//       thread issuing im2col-mode TMA loads (32 pixels x 32 channels per instruction,
+//       SWIZZLE_128B_ATOM_32B, padding and ragged channel ranges zero-filled by the copy
+//       engine), warp 5 issues tcgen05.mma (128 x BN x 8, BN up to 256).
+//   conv_wgrad_tc_kernel   (fallback for geometries a tensor map cannot describe)
+//       CTA = 288 threads: warps 0-3 gather P, warps 4-7 gather Q with cp.async 16 B.
+// grid = (row tiles, column tiles, taps x K splits); partial sums are added with vector
 // red.global.add (gW must be zeroed by the caller once per step).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -57,6 +64,8 @@ struct WgradParams {
   const float* row_scale;
   int kb_per_split, num_kb;
   int splits, taps_w;  // grid.z = taps * splits; tap (fr, fs) shifts q by (fr, fs) pixels
+  int probe;           // timing probes (CMR_WGRAD_PROBE): 1 = loads only for the first ring
+                       // fill, 2 = no MMAs; results are garbage, 0 in normal operation
 };
 
 constexpr int kBM = 128;
@@ -243,6 +252,159 @@ conv_wgrad_tc_kernel(const WgradParams p) {
   if (warp == 7) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+// ------------------------------------------------------------ TMA variant ----
+constexpr int kTmaThreads = 192;
+constexpr int kTPix = 64;   // pixels per k-block: fewer, larger TMA boxes (8 KB each)
+
+template <int BN, int STAGES>
+struct TSmem {
+  static constexpr int kPBytes = kTPix * kBM * 4;  // 16 KB
+  static constexpr int kQBytes = kTPix * BN * 4;
+  static constexpr int kPOff = 0;
+  static constexpr int kQOff = STAGES * kPBytes;
+  static constexpr int kBarOff = kQOff + STAGES * kQBytes;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 1) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTmaThreads)
+conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
+                      const __grid_constant__ CUtensorMap tmap_q, const WgradParams p) {
+  using L = TSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  const uint32_t smem_base = raw_addr + pad;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * kBM;
+  const int j0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / p.splits;
+  const int tap_fr = tap / p.taps_w, tap_fs = tap - tap_fr * p.taps_w;
+  const int kb_begin = (blockIdx.z - tap * p.splits) * p.kb_per_split;
+  const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction of the grid
+
+  if (warp == 4 && lane == 0) {
+    prefetch_tensormap(&tmap_p);
+    prefetch_tensormap(&tmap_q);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      // column blocks past the channel range would only load zeros: skip their copies
+      // (their shared memory is zeroed once below) -- not needed for correctness of the
+      // kept columns, the epilogue never writes columns >= cols
+      const int p_blocks = min(kBM / 32, (p.rows - i0 + 31) / 32);
+      const int q_blocks = min(BN / 32, (p.cols - j0 + 31) / 32);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        int img, rem, oy, ox;
+        p.div_hw.divmod((kb_begin + kb) * kTPix, img, rem);
+        p.div_w.divmod(rem, oy, ox);
+        if (p.probe == 1 && kb >= STAGES) {
+          mbar_arrive(&full_bar[s]);
+          continue;
+        }
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p_blocks + q_blocks) * (kTPix * 128));
+        const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
+        const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
+        const int ph = oy * p.p.stride + p.p.off_y, pw = ox * p.p.stride + p.p.off_x;
+        const int qh = oy * p.q.stride + p.q.off_y, qw = ox * p.q.stride + p.q.off_x;
+        for (int b = 0; b < p_blocks; ++b)
+          tma_load_im2col_4d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s],
+                             p.p.c0 + i0 + b * 32, pw, ph, img, 0, 0);
+        for (int b = 0; b < q_blocks; ++b)
+          tma_load_im2col_4d(qa + b * (kTPix * 128), &tmap_q, &full_bar[s],
+                             p.q.c0 + j0 + b * 32, qw, qh, img, tap_fs, tap_fr);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 1, 1);  // both operands MN-major
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t phase = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
+        const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
+#pragma unroll
+        for (int k = 0; k < kTPix / 8; ++k) {
+          const uint64_t da = make_smem_desc(pa + k * 1024, kTPix * 128, 512, 1);
+          const uint64_t db = make_smem_desc(qa + k * 1024, kTPix * 128, 512, 1);
+          if (p.probe != 2 || kb == 0) umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) umma_commit(tmem_full_bar);
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = i0 + warp * 32 + lane;
+    const bool row_ok = row < p.rows;
+    const float sc = (row_ok && p.row_scale) ? __ldg(p.row_scale + row) : 1.0f;
+    float* out_row = p.gw + (size_t)row * p.gw_ld + p.gw_col0 + tap * p.cols;
+    const bool vec_ok = ((p.gw_ld & 3) == 0) && ((p.gw_col0 & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.gw) & 15) == 0);
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      const int jc = j0 + chunk * 32;
+      if (jc >= p.cols) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(chunk * 32), v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int j = jc + g * 4;
+        if (j >= p.cols) break;
+        if (vec_ok && j + 3 < p.cols) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_row + j),
+                       "f"(__uint_as_float(v[g * 4 + 0]) * sc),
+                       "f"(__uint_as_float(v[g * 4 + 1]) * sc),
+                       "f"(__uint_as_float(v[g * 4 + 2]) * sc),
+                       "f"(__uint_as_float(v[g * 4 + 3]) * sc)
+                       : "memory");
+        } else {
+          for (int e = 0; e < 4 && j + e < p.cols; ++e)
+            atomicAdd(out_row + j + e, __uint_as_float(v[g * 4 + e]) * sc);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
 // Round-up magic number for 31-bit dividends: q = (n * mul) >> (32 + shr).
 FastDiv make_fast_div(int d) {
   FastDiv f;
@@ -276,7 +438,53 @@ int launch_wgrad(const WgradParams& p, int splits, int taps, cudaStream_t st) {
   return CMR_OK;
 }
 
+template <int BN, int STAGES>
+int launch_wgrad_tma(const CUtensorMap& tp, const CUtensorMap& tq, const WgradParams& p,
+                     int splits, int taps, cudaStream_t st) {
+  using L = TSmem<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, STAGES>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      L::kDynamic));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits * taps);
+  prof_begin(kProfWgrad, 2.0 * p.M * (double)p.rows * p.cols * taps, st);
+  conv_wgrad_tma_kernel<BN, STAGES><<<grid, kTmaThreads, L::kDynamic, st>>>(tp, tq, p);
+  prof_end(st);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+// Splits of the pixel reduction: fill `slots` concurrent CTAs in as few full waves as
+// possible (a partial last wave idles SMs), never fewer than 8 k-blocks per CTA.
+int choose_splits(int tiles, int slots, int num_kb) {
+  const int max_splits = ceil_div(num_kb, 8) < 1 ? 1 : ceil_div(num_kb, 8);
+  int best = 1;
+  double best_eff = 0.0;
+  for (int waves = 1; waves <= 4; ++waves) {
+    int s = (waves * slots) / tiles;
+    if (s < 1) continue;
+    if (s > max_splits) s = max_splits;
+    const long long ctas = (long long)tiles * s;
+    const double eff = (double)ctas / ((double)ceil_div_ll(ctas, slots) * slots);
+    if (eff > best_eff + 0.04) {   // a later wave count must be clearly better
+      best_eff = eff;
+      best = s;
+    }
+    if (s == max_splits) break;
+  }
+  return best;
+}
+
 }  // namespace
+
+// conv_tc.cu
+int make_tmap_im2col(CUtensorMap* map, const float* base, int batch, int h, int w, int ld,
+                     int channels, int stride, int lower_h, int lower_w, int n_pos_h,
+                     int n_pos_w, int pixels, bool mn_major);
+extern int g_im2col_tma;
 }  // namespace cmr
 
 using namespace cmr;
@@ -307,11 +515,45 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   p.gw = gw; p.gw_ld = c->gw_ld; p.gw_col0 = c->gw_col0;
   p.row_scale = row_scale;
   p.num_kb = ceil_div(p.M, kPix);
-  // Split the pixel reduction so that the grid fills the machine (~2 CTAs per SM).
-  const int bn = c->cols > 64 ? 128 : 64;
+  {
+    const char* e = getenv("CMR_WGRAD_PROBE");
+    p.probe = e ? atoi(e) : 0;
+  }
   const int taps_h = c->taps_h > 1 ? c->taps_h : 1, taps_w = c->taps_w > 1 ? c->taps_w : 1;
   const int taps = taps_h * taps_w;
   CMR_REQUIRE(taps == 1 || ((c->gw_col0 + taps * c->cols) <= c->gw_ld && c->cols % 4 == 0));
+  cudaStream_t st = as_stream(stream);
+
+  // Default path: both operands through im2col-mode tensor maps.
+  if (g_im2col_tma) {
+    CUtensorMap tp, tq;
+    if (make_tmap_im2col(&tp, gy, c->batch, c->gy_h, c->gy_w, c->gy_ld, c->gy_c0 + c->rows,
+                         c->gy_stride, c->gy_off_y, c->gy_off_x, c->loop_h, c->loop_w, kTPix,
+                         true) == CMR_OK &&
+        make_tmap_im2col(&tq, x, c->batch, c->x_h, c->x_w, c->x_ld, c->x_c0 + c->cols,
+                         c->x_stride, c->x_off_y, c->x_off_x, c->loop_h, c->loop_w, kTPix,
+                         true) == CMR_OK) {
+      const int bn = c->cols > 128 ? 256 : (c->cols > 64 ? 128 : 64);
+      p.num_kb = ceil_div(p.M, kTPix);
+      const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn) * taps;
+      const int slots = sm_count();   // one CTA per SM (96 - 192 KB of operand stages)
+      int splits = c->splits > 0 ? c->splits : choose_splits(tiles, slots, p.num_kb);
+      CMR_REQUIRE((long long)splits * taps < 65536);
+      if (splits > p.num_kb) splits = p.num_kb;
+      p.kb_per_split = ceil_div(p.num_kb, splits);
+      splits = ceil_div(p.num_kb, p.kb_per_split);
+      p.splits = splits;
+      p.taps_w = taps_w;
+      if (bn == 256) return launch_wgrad_tma<256, 2>(tp, tq, p, splits, taps, st);
+      if (bn == 128) return launch_wgrad_tma<128, 3>(tp, tq, p, splits, taps, st);
+      return launch_wgrad_tma<64, 4>(tp, tq, p, splits, taps, st);
+    }
+    p.num_kb = ceil_div(p.M, kPix);
+  }
+
+  // Fallback: cp.async gathers.  Split the pixel reduction so that the grid fills the
+  // machine (~2 CTAs per SM).
+  const int bn = c->cols > 64 ? 128 : 64;
   const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn) * taps;
   int splits = c->splits;
   if (splits <= 0) {
@@ -327,7 +569,6 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   splits = ceil_div(p.num_kb, p.kb_per_split);
   p.splits = splits;
   p.taps_w = taps_w;
-  cudaStream_t st = as_stream(stream);
   if (bn == 128) return launch_wgrad<128, 3>(p, splits, taps, st);
   return launch_wgrad<64, 4>(p, splits, taps, st);
 }

@@ -62,10 +62,13 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ n_arr,
   }
 }
 
-// One CTA per image resolves the bitmask sequentially in 64-box chunks.
-// Thread 0 resolves the diagonal 64x64 block from registers; all warps then OR
-// the kept rows into the running "removed" mask held in shared memory.
-constexpr int kSweepThreads = 256;  // thread 0 keeps 64 mask words in registers
+// One CTA per image resolves the bitmask sequentially in 64-box chunks.  Per chunk the
+// critical path is: thread 0 resolves the diagonal 64x64 block from registers, then 64
+// threads OR word cb+1 of the kept rows into the running "removed" mask (the only word
+// the next chunk needs).  The remaining words (>= cb+2) of those rows are ORed in by
+// warps 1..7 one iteration later, concurrently with thread 0 resolving the next chunk.
+constexpr int kSweepThreads = 256;
+constexpr int kSweepRestWarps = kSweepThreads / 32 - 1;
 
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ n_arr,
@@ -73,8 +76,8 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
                  int32_t* __restrict__ n_keep, int keep_stride) {
   extern __shared__ unsigned long long remv[];  // nb_stride words
   __shared__ unsigned long long diag[64];
-  __shared__ int kept_list[64];
-  __shared__ int kept_n, count_s, done_s;
+  __shared__ int kept_list[2][64];
+  __shared__ int kept_n[2], count_s, done_s;
   const int img = blockIdx.x;
   const int n = n_arr ? min(n_arr[img], n_max) : n_max;
   const int nb = (n + 63) / 64;
@@ -85,11 +88,13 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
   if (t == 0) {
     count_s = 0;
     done_s = 0;
+    kept_n[0] = kept_n[1] = 0;
   }
   unsigned long long next_diag = 0ull;
   if (t < 64 && t < n) next_diag = mask[(size_t)t * nb_stride + 0];
   __syncthreads();
   for (int cb = 0; cb < nb; ++cb) {
+    const int cur = cb & 1, prev = cur ^ 1;
     if (t < 64) {
       diag[t] = next_diag;
       const int i = (cb + 1) * 64 + t;  // prefetch the next diagonal block
@@ -108,26 +113,40 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
       for (int j = 0; j < 64; ++j) {
         if (j < lim && !done && !((r >> j) & 1ull)) {
           keep[cnt++] = cb * 64 + j;
-          kept_list[nk++] = j;
+          kept_list[cur][nk++] = j;
           r |= d[j];
           if (limit > 0 && cnt >= limit) done = true;
         }
       }
-      kept_n = nk;
+      kept_n[cur] = nk;
       count_s = cnt;
       if (done) done_s = 1;
-    }
-    __syncthreads();
-    if (done_s) break;
-    const int nk = kept_n;
-    for (int q = warp; q < nk; q += kSweepThreads / 32) {
-      const unsigned long long* row = mask + (size_t)(cb * 64 + kept_list[q]) * nb_stride;
-      for (int w = cb + 1 + lane; w < nb; w += 32) {
-        const unsigned long long v = row[w];
-        if (v) atomicOr(&remv[w], v);
+    } else if (warp >= 1 && cb > 0) {
+      // words >= cb+1 of the rows kept in chunk cb-1 (word cb went in last iteration)
+      const int nk = kept_n[prev];
+      for (int q = warp - 1; q < nk; q += kSweepRestWarps) {
+        const unsigned long long* row =
+            mask + (size_t)((cb - 1) * 64 + kept_list[prev][q]) * nb_stride;
+        for (int w0 = cb + 1; w0 < nb; w0 += 128) {
+          unsigned long long v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int w = w0 + 32 * u + lane;
+            v[u] = w < nb ? row[w] : 0ull;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (v[u]) atomicOr(&remv[w0 + 32 * u + lane], v[u]);
+        }
       }
     }
     __syncthreads();
+    if (done_s) break;
+    if (t < kept_n[cur] && cb + 1 < nb) {
+      const unsigned long long v =
+          mask[(size_t)(cb * 64 + kept_list[cur][t]) * nb_stride + cb + 1];
+      if (v) atomicOr(&remv[cb + 1], v);
+    }
   }
   if (t == 0) n_keep[img] = count_s;
 }
@@ -177,11 +196,12 @@ proposal_decode_kernel(const float4* __restrict__ loc, const float* __restrict__
   keys[(size_t)img * n_pad + k] = key;
 }
 
-// Descending bitonic sort of n_pad (power of two) 64-bit keys, one CTA per image.
-// Sub-sequences of kSortChunk keys are sorted in shared memory; only the few
-// stages with a partner distance >= kSortChunk touch global (L2-resident) memory.
+// Descending bitonic sort of `rows` independent arrays of n_pad (power of two) 64-bit
+// keys, spread over many CTAs: chunks of kSortChunk keys are sorted / merged in shared
+// memory (one CTA per chunk), and the stages whose partner distance reaches across
+// chunks run as grid-wide passes over the (L2-resident) array, two stages per pass.
 constexpr int kSortThreads = 1024;
-constexpr int kSortChunk = 16384;  // 128 KB of 64-bit keys
+constexpr int kSortChunk = 4096;  // 32 KB of 64-bit keys per CTA
 
 __device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned long long& b,
                                               bool desc) {
@@ -192,61 +212,65 @@ __device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned lo
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads)
-bitonic_sort_desc_kernel(unsigned long long* __restrict__ keys_all, int n_pad) {
-  extern __shared__ unsigned long long sk[];
-  unsigned long long* keys = keys_all + (size_t)blockIdx.x * n_pad;
-  const int t = threadIdx.x;
-  const int chunk = min(n_pad, kSortChunk);
-  // Phase 1: fully sort every chunk in shared memory (alternating directions so
-  // that consecutive chunks form bitonic sequences).
-  for (int base = 0; base < n_pad; base += chunk) {
-    for (int i = t; i < chunk; i += kSortThreads) sk[i] = keys[base + i];
-    __syncthreads();
-    for (int k = 2; k <= chunk; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = t; i < chunk / 2; i += kSortThreads) {
-          const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-          const int hi = lo | j;
-          const bool desc = (((base + lo) & k) == 0);
-          cmp_swap_desc(sk[lo], sk[hi], desc);
-        }
-        __syncthreads();
-      }
+// Stages j = j_hi .. 1 of merge level k on one chunk, in shared memory.
+__device__ __forceinline__ void bitonic_smem_stages(unsigned long long* sk, int chunk, int base,
+                                                    int k, int j_hi) {
+  for (int j = j_hi; j > 0; j >>= 1) {
+    for (int i = threadIdx.x; i < chunk / 2; i += kSortThreads) {
+      const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+      const int hi = lo | j;
+      cmp_swap_desc(sk[lo], sk[hi], ((base + lo) & k) == 0);
     }
-    for (int i = t; i < chunk; i += kSortThreads) keys[base + i] = sk[i];
     __syncthreads();
   }
-  // Phase 2: merge levels above the chunk size.
-  for (int k = chunk << 1; k <= n_pad; k <<= 1) {
-    int j = k >> 1;
-    for (; j >= chunk; j >>= 1) {  // global-memory stages
-      for (int i = t; i < n_pad / 2; i += kSortThreads) {
-        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-        const int hi = lo | j;
-        const bool desc = ((lo & k) == 0);
-        unsigned long long a = keys[lo], b = keys[hi];
-        if ((a < b) == desc) {
-          keys[lo] = b;
-          keys[hi] = a;
-        }
-      }
-      __syncthreads();
-    }
-    for (int base = 0; base < n_pad; base += chunk) {  // remaining stages in smem
-      for (int i = t; i < chunk; i += kSortThreads) sk[i] = keys[base + i];
-      __syncthreads();
-      for (int jj = chunk >> 1; jj > 0; jj >>= 1) {
-        for (int i = t; i < chunk / 2; i += kSortThreads) {
-          const int lo = ((i & ~(jj - 1)) << 1) | (i & (jj - 1));
-          const int hi = lo | jj;
-          const bool desc = (((base + lo) & k) == 0);
-          cmp_swap_desc(sk[lo], sk[hi], desc);
-        }
-        __syncthreads();
-      }
-      for (int i = t; i < chunk; i += kSortThreads) keys[base + i] = sk[i];
-      __syncthreads();
+}
+
+// k_first == 2: full sort of every chunk (levels 2 .. chunk); otherwise the tail
+// (j < chunk) of merge level k_first.  grid = (n_pad / chunk, rows).
+__global__ void __launch_bounds__(kSortThreads)
+bitonic_chunk_kernel(unsigned long long* __restrict__ keys_all, int n_pad, int chunk,
+                     int k_first) {
+  extern __shared__ unsigned long long sk[];
+  const int base = blockIdx.x * chunk;
+  unsigned long long* keys = keys_all + (size_t)blockIdx.y * n_pad + base;
+  for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = keys[i];
+  __syncthreads();
+  if (k_first == 2) {
+    for (int k = 2; k <= chunk; k <<= 1) bitonic_smem_stages(sk, chunk, base, k, k >> 1);
+  } else {
+    bitonic_smem_stages(sk, chunk, base, k_first, chunk >> 1);
+  }
+  for (int i = threadIdx.x; i < chunk; i += kSortThreads) keys[i] = sk[i];
+}
+
+// Grid-wide pass: stages j and j/2 of merge level k (j/2 skipped when two == 0).  Each
+// thread owns the four keys {q, q+j/2, q+j, q+3j/2} (or the pair {q, q+j}).
+__global__ void __launch_bounds__(256)
+bitonic_global_kernel(unsigned long long* __restrict__ keys_all, int n_pad, int k, int j,
+                      int two) {
+  unsigned long long* keys = keys_all + (size_t)blockIdx.y * n_pad;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (two) {
+    if (i >= n_pad / 4) return;
+    const int h = j >> 1;
+    const int q = ((i & ~(h - 1)) << 2) | (i & (h - 1));
+    const bool desc = (q & k) == 0;
+    unsigned long long a = keys[q], b = keys[q + h], c = keys[q + j], d = keys[q + j + h];
+    cmp_swap_desc(a, c, desc);
+    cmp_swap_desc(b, d, desc);
+    cmp_swap_desc(a, b, desc);
+    cmp_swap_desc(c, d, desc);
+    keys[q] = a;
+    keys[q + h] = b;
+    keys[q + j] = c;
+    keys[q + j + h] = d;
+  } else {
+    if (i >= n_pad / 2) return;
+    const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+    unsigned long long a = keys[lo], b = keys[lo | j];
+    if ((a < b) == ((lo & k) == 0)) {
+      keys[lo] = b;
+      keys[lo | j] = a;
     }
   }
 }
@@ -313,15 +337,22 @@ int launch_nms(const float4* boxes, const int* n_arr, int n_max, int B, float th
 int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {
   const int chunk = n_pad < kSortChunk ? n_pad : kSortChunk;
   const size_t smem = sizeof(unsigned long long) * chunk;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CMR_CUDA_TRY(cudaFuncSetAttribute(bitonic_sort_desc_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(sizeof(unsigned long long) * kSortChunk)));
-    attr_set = true;
-  }
-  bitonic_sort_desc_kernel<<<rows, kSortThreads, smem, st>>>(keys, n_pad);
+  const dim3 cgrid(n_pad / chunk, rows);
+  bitonic_chunk_kernel<<<cgrid, kSortThreads, smem, st>>>(keys, n_pad, chunk, 2);
   CMR_LAUNCH_CHECK();
+  for (int k = chunk << 1; k <= n_pad; k <<= 1) {
+    int j = k >> 1;
+    while (j >= chunk) {
+      const int two = (j >> 1) >= chunk ? 1 : 0;
+      const int work = two ? n_pad / 4 : n_pad / 2;
+      bitonic_global_kernel<<<dim3(ceil_div(work, 256), rows), 256, 0, st>>>(keys, n_pad, k, j,
+                                                                            two);
+      CMR_LAUNCH_CHECK();
+      j >>= two ? 2 : 1;
+    }
+    bitonic_chunk_kernel<<<cgrid, kSortThreads, smem, st>>>(keys, n_pad, chunk, k);
+    CMR_LAUNCH_CHECK();
+  }
   return CMR_OK;
 }
 }  // namespace cmr

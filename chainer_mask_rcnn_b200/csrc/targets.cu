@@ -20,7 +20,7 @@
 
 namespace cmr {
 
-// nms.cu: descending bitonic sort of n_pad (power of two) 64-bit keys, one CTA per row.
+// nms.cu: descending bitonic sort of `rows` arrays of n_pad (power of two) 64-bit keys.
 int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st);
 
 namespace {

@@ -74,6 +74,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// Im2col-mode TMA: loads `pixelsPerColumn` consecutive convolution positions (walking
+// w, then h, then n inside the bounding box of the tensor map) x `channelsPerPixel`
+// channels of an NHWC tensor, starting at position (w, h, n) = top-left input
+// coordinate of the first position, shifted by the filter tap (off_w, off_h).
+// Out-of-tensor elements (padding, positions past the last image) arrive as zeros.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* m,
+                                                   uint64_t* bar, int c, int w, int h, int n,
+                                                   int off_w, int off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"((unsigned short)off_w), "h"((unsigned short)off_h)
+      : "memory");
+}
+
 // ----------------------------------------------------------------- tcgen05 --
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

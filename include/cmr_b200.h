@@ -144,6 +144,12 @@ typedef struct cmr_conv_desc {
   int tile_n;
 } cmr_conv_desc;
 
+/* The activation operand of cmr_conv_gemm_tc / cmr_conv_wgrad_tc is fetched by im2col-mode
+ * TMA whenever a tensor map can describe the layout (everything but the RGB0-packed
+ * stem); 0 forces the cp.async gather path everywhere (kept for A/B measurements and
+ * tests).  Process-wide; returns the previous setting. */
+int cmr_set_im2col_tma(int on);
+
 int cmr_conv_gemm_tc(const cmr_conv_desc* desc, const float* a, const float* w,
                      float* d, const float* scale, const float* bias,
                      const float* addend, const float* mask, void* stream);

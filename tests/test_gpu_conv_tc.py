@@ -18,6 +18,16 @@ from chainer_mask_rcnn_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['tma_im2col', 'cp_async'], autouse=True)
+def a_operand_path(request):
+    """Every case runs with the activation operand fetched by im2col-mode TMA (the
+    default) and by the cp.async gather fallback."""
+    lib = _lib.load()
+    old = lib.cmr_set_im2col_tma(1 if request.param == 'tma_im2col' else 0)
+    yield request.param
+    lib.cmr_set_im2col_tma(old)
+
+
 def round_tf32(t):
     out = torch.empty_like(t)
     _lib.call('cmr_round_tf32', _lib.ptr(t), _lib.ptr(out), t.numel(), _lib.stream_ptr())
@@ -66,6 +76,11 @@ CASES = [
     (1, 7, 7, 512, 512, 3, 1, 1, 0),        # res5 3x3, K = 4608, auto tile
     (3, 14, 14, 1024, 80, 1, 1, 0, 0),      # mask head N = 80
     (1, 51, 84, 1024, 75, 1, 1, 0, 0),      # RPN loc+score fused, N = 75 (scalar stores)
+    (3, 13, 18, 64, 64, 1, 2, 0, 64),       # stride 2, even width, tile crosses images
+    (2, 28, 28, 64, 64, 2, 2, 0, 64),       # 2x2 stride 2 (deconv6 data gradient)
+    (5, 7, 7, 96, 64, 3, 1, 1, 64),         # 128-row tiles spanning 3 images, K = 27 k-blocks
+    (2, 10, 9, 32, 64, 3, 2, 1, 64),        # 3x3 stride 2 pad 1
+    (1, 5, 6, 64, 64, 5, 1, 2, 64),         # 5x5 pad 2
 ]
 
 

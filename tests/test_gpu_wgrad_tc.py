@@ -12,6 +12,15 @@ from test_gpu_conv_tc import rel, round_tf32
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['tma_im2col', 'cp_async'], autouse=True)
+def operand_path(request):
+    """Every case runs on the im2col-TMA kernel (default) and on the cp.async fallback."""
+    lib = _lib.load()
+    old = lib.cmr_set_im2col_tma(1 if request.param == 'tma_im2col' else 0)
+    yield request.param
+    lib.cmr_set_im2col_tma(old)
+
+
 def wgrad_conv(x, gy, kh, kw, stride, pad, row_scale=None, splits=0):
     """x (B,H,W,C), gy (B,oh,ow,N) NHWC -> gW (N, kh, kw, C)."""
     B, H, W, C = x.shape
@@ -45,6 +54,8 @@ CASES = [
     (16, 7, 7, 512, 512, 3, 1, 1, 0),      # res5 conv2 shape (fewer RoIs)
     (1, 25, 42, 1024, 76, 1, 1, 0, 0),     # RPN loc+score rows = 76 (ragged row tile)
     (64, 1, 1, 2048, 408, 1, 1, 0, 0),     # Linear layers fused (rows 408), 64 RoIs
+    (3, 14, 18, 192, 64, 3, 2, 1, 0),      # 3x3 stride 2 pad 1, cols = 192 (ragged 256 tile)
+    (2, 51, 84, 256, 256, 1, 1, 0, 0),     # res4 1x1: many splits of a 256-wide tile
 ]
 
 

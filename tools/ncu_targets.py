@@ -1,6 +1,10 @@
-"""Small driver for ncu captures: runs the two dominant tensor-core kernels on the
-res5 3x3 shapes of the train step (50176 x 512 x 4608) a few times."""
-import ctypes
+"""Small driver for ncu captures: runs the dominant tensor-core kernels on shapes of the
+train step a few times.
+  conv     res5 3x3 (50176 x 512 x 4608), fused affine + ReLU
+  conv1x1  res5 conv3 (50176 x 2048 x 512), fused affine + residual add + ReLU
+  small    res4 3x3 (8568 x 256 x 2304)
+  wgrad    res5 3x3 weight gradient, all 9 taps
+  wgrad1x1 res5 conv3 weight gradient (2048 x 512 over 50176 pixels)"""
 import os
 import sys
 
@@ -11,15 +15,28 @@ sys.path.insert(0, ROOT)
 from chainer_mask_rcnn_b200.models import engine as E  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'both'
-x = E.round_tf32(torch.randn((1024, 7, 7, 512), device='cuda'))
-w = E.round_tf32(torch.randn((512, 3, 3, 512), device='cuda') / 68.)
-g = E.round_tf32(torch.randn((1024, 7, 7, 512), device='cuda'))
-scale = torch.ones(512, device='cuda')
-bias = torch.zeros(512, device='cuda')
-gw = torch.zeros((512, 3, 3, 512), device='cuda')
+dev = 'cuda'
+x = E.round_tf32(torch.randn((1024, 7, 7, 512), device=dev))
+w = E.round_tf32(torch.randn((512, 3, 3, 512), device=dev) / 68.)
+g = E.round_tf32(torch.randn((1024, 7, 7, 512), device=dev))
+w3 = E.round_tf32(torch.randn((2048, 1, 1, 512), device=dev) / 22.)
+res = torch.randn((1024, 7, 7, 2048), device=dev)
+g3 = E.round_tf32(torch.randn((1024, 7, 7, 2048), device=dev))
+xs = E.round_tf32(torch.randn((2, 51, 84, 256), device=dev))
+ws = E.round_tf32(torch.randn((256, 3, 3, 256), device=dev) / 48.)
+scale = torch.ones(2048, device=dev)
+bias = torch.zeros(2048, device=dev)
+gw = torch.zeros((512, 3, 3, 512), device=dev)
+gw3 = torch.zeros((2048, 512), device=dev)
 for _ in range(4):
     if what in ('conv', 'both'):
         E.conv_gemm(x, w, 512, 3, 3, 1, 1, scale=scale, bias=bias, relu=True)
+    if what == 'conv1x1':
+        E.conv_gemm(x, w3, 2048, scale=scale, bias=bias, addend=res, relu=True)
+    if what == 'small':
+        E.conv_gemm(xs, ws, 256, 3, 3, 1, 1, scale=scale, bias=bias, relu=True)
     if what in ('wgrad', 'both'):
-        E.wgrad_tap(g, x, gw, 512, 512, (7, 7), 9 * 512, gw_col0=4 * 512, x_off=(0, 0))
+        E.wgrad_tap(g, x, gw, 512, 512, (7, 7), 9 * 512, x_off=(-1, -1), taps=(3, 3))
+    if what == 'wgrad1x1':
+        E.wgrad_tap(g3, x, gw3, 2048, 512, (7, 7), 512)
 torch.cuda.synchronize()
