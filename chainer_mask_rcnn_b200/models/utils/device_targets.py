@@ -46,12 +46,15 @@ class GroundTruth(object):
         self.bbox = self._buf[:B * G * 4].view(torch.float32).view(B, G, 4)
         self.label = self._buf[B * G * 4:B * G * 5].view(B, G)
         self.count = self._buf[B * G * 5:]
+        self._copied = None
         self.fill_(bboxes, labels)
 
     def fill_(self, bboxes, labels):
         B, G = self.B, self.G
         if len(bboxes) != B:
             raise ValueError('expected {} images, got {}'.format(B, len(bboxes)))
+        if self._copied is not None:
+            self._copied.synchronize()     # the previous H2D copy has read the staging buffer
         packed = self._host.numpy()
         packed[:] = 0
         bb = packed[:B * G * 4].view(np.float32).reshape(B, G, 4)
@@ -67,6 +70,8 @@ class GroundTruth(object):
             ll[i, :n] = np.asarray(l)[:n]
             cc[i] = n
         self._buf.copy_(self._host, non_blocking=True)
+        self._copied = torch.cuda.Event()
+        self._copied.record()
         return self
 
 
