@@ -26,12 +26,16 @@
 //   warp  5     one thread issues tcgen05.mma (128 x BN x 8 per instruction) and
 //               tcgen05.commit; the accumulator lives in TMEM, double buffered
 //               (2 x BN columns) so tile i+1's MMAs overlap tile i's epilogue
-//   warps 6-13  epilogue: tcgen05.ld (lane = row) -> per-warp shared-memory
-//               transpose -> rows written as full 128 B lines (coalesced); the
-//               residual addend and the ReLU-mask operand are prefetched the same
-//               way before the accumulator is read
+//   warps 6-13  epilogue (plus warps 0-3 when the A tiles come by TMA: 12 warps, three
+//               per TMEM lane quarter, interleaved over the 32-column chunks):
+//               tcgen05.ld (lane = row) -> per-warp shared-memory transpose of 16
+//               columns at a time -> 64 B row segments written 8 rows per instruction;
+//               the residual addend, the ReLU-mask operand and the affine vectors are
+//               requested the same way before the accumulator is waited for
 // full/empty mbarrier ring of STAGES k-blocks (32 fp32 = one 128 B swizzle row)
 // shared by all tiles; tmem_full/tmem_empty barriers per accumulator buffer.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -55,6 +59,7 @@ struct ConvGemmParams {
   int relu, round_out;
   int m_tiles, n_tiles;
   int tma_a;   // A tiles come from the im2col tensor map (else cp.async gathers)
+  int epi_groups;   // epilogue warps per TMEM lane quarter: 3 with TMA A tiles, else 2
 };
 
 constexpr int kBM = 128;
@@ -64,22 +69,22 @@ constexpr int kProducerThreads = 128;
 constexpr int kEpiWarp0 = 6;                 // first epilogue warp
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 448
-constexpr int kXposePitch4 = 9;              // float4 per row of the transpose buffer (36 floats)
+constexpr int kMaxEpiWarps = 12;             // warps 0-3 join the epilogue in TMA mode
 
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kABytes;
-  static constexpr int kXposeOff = kBOff + STAGES * kBBytes;
-  static constexpr int kXposeBytes = kEpiWarps * 32 * kXposePitch4 * 16;
-  static constexpr int kBarOff = kXposeOff + kXposeBytes;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for 1024 B alignment
+  static constexpr int kBarOff = kBOff + STAGES * kBBytes;
+  static constexpr int kXposeOff = kBarOff + 256;   // (2 * STAGES + 4) barriers + TMEM slot
+  // + groups x 4 warps x 4 KB of transpose buffers + slack for 1024 B alignment
+  static constexpr int dynamic_bytes(int groups) { return kXposeOff + groups * 16384 + 1024; }
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier area");
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES>;
@@ -109,7 +114,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], kEpiWarps);
+      mbar_init(&tmem_empty_bar[b], p.epi_groups * 4);
     }
     fence_barrier_init();
   }
@@ -120,9 +125,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
   const uint32_t tmem_base = *tmem_slot;
   const int ohw = p.out_h * p.out_w;
 
-  if (warp < 4) {
+  if (warp < 4 && !p.tma_a) {
     // ------------------------------------- fallback A producer (cp.async gather)
-    if (!p.tma_a) {
     const int t = threadIdx.x;
     const int j = t & 7;
     const int r0 = t >> 3;
@@ -176,7 +180,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    }
   } else if (warp == 4) {
     // ---------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -244,10 +247,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     }
   } else {
     // ------------------------------------------------------------- epilogue
-    const int ew = warp - kEpiWarp0;          // 0..7
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                 // which half of the BN columns
-    float4* xp4 = reinterpret_cast<float4*>(smem + L::kXposeOff) + ew * 32 * kXposePitch4;
+    // column group of this warp; n_groups warps share a lane quarter
+    const int n_groups = p.epi_groups;
+    const int grp = warp < 4 ? 0 : (warp - kEpiWarp0) / 4 + (p.tma_a ? 1 : 0);
+    if (grp < n_groups) {
+    float4* xp4 = reinterpret_cast<float4*>(smem + L::kXposeOff) + (grp * 4 + q) * (32 * 8);
     const int sub = lane >> 3;                // row within a 4-row store group
     const int c4 = (lane & 7) * 4;            // first of this lane's 4 columns in a chunk
     const float* __restrict__ scale_p = p.scale;
@@ -259,14 +264,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_p) & 15) == 0) &&
                         (!addend_p || (reinterpret_cast<uintptr_t>(addend_p) & 15) == 0) &&
                         (!mask_p || (reinterpret_cast<uintptr_t>(mask_p) & 15) == 0);
-    constexpr int kChunks = (BN / 2 + 31) / 32;   // 32-column chunks per half
+    constexpr int kChunks = BN / 32;          // 32-column chunks of the tile
     uint32_t tc_ = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
       const int m0 = (tile / p.n_tiles) * kBM;
       const int n0 = (tile % p.n_tiles) * BN;
       const uint32_t buf = tc_ & 1;
-      // output offsets of this lane's 8 rows (row = 32q + 4i + sub)
-      long long doff[8];
+      // output element offsets of this lane's 8 rows (row = 32q + 4i + sub); the host
+      // checks that the output tensor has fewer than 2^31 elements
+      int doff[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = m0 + q * 32 + 4 * i + sub;
@@ -275,18 +281,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           const int rem = row - img * ohw;
           const int oy = rem / p.out_w;
           const int ox = rem - oy * p.out_w;
-          doff[i] = ((long long)(img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w +
-                     ox * p.d_stride + p.d_ox) * p.d_ld;
+          doff[i] = ((img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w + ox * p.d_stride +
+                     p.d_ox) * p.d_ld;
         } else {
           doff[i] = -1;
         }
       }
       bool waited = false;
 #pragma unroll 1
-      for (int chunk = 0; chunk < kChunks; ++chunk) {
-        const int cbase = half * (BN / 2) + chunk * 32;   // column of the tile
-        const int n = n0 + cbase + c4;                    // this lane's first global column
+      for (int chunk = grp; chunk < kChunks; chunk += n_groups) {
+        const int cbase = chunk * 32;                     // column of the tile
         if (n0 + cbase >= p.N) break;
+        const int n = n0 + cbase + c4;                    // this lane's first global column
         const bool full4 = vec_ok && (n + 3 < p.N);
         // operands of the epilogue are requested before the accumulator is waited for
         // (coalesced: 8 lanes cover one 128 B row)
@@ -317,10 +323,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cbase, v);
         tmem_ld_wait();
         __syncwarp();   // previous chunk's reads of the transpose buffer are done
-        // lane = accumulator row: 8 x 16-byte stores (pitch 36 floats: conflict-free)
+        // lane = accumulator row: 8 x 16-byte stores into a 32 x 128 B buffer whose 16-byte
+        // slots are XOR-swizzled with the row (conflict-free both ways, no padding)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          xp4[lane * kXposePitch4 + c] =
+          xp4[lane * 8 + (c ^ (lane & 7))] =
               make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
                           __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
         __syncwarp();
@@ -328,7 +335,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (doff[i] < 0) continue;
-            float4 o = xp4[(4 * i + sub) * kXposePitch4 + (lane & 7)];
+            const int r = 4 * i + sub;
+            float4 o = xp4[r * 8 + ((lane & 7) ^ (r & 7))];
             if (scale_p) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
             if (bias_p) { o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w; }
             if (addend_p) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
@@ -352,8 +360,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {
             if (doff[i] < 0) continue;
+            const int r = 4 * i + sub;
             for (int e = 0; e < 4 && n + e < p.N; ++e) {
-              float x = xs[(4 * i + sub) * (kXposePitch4 * 4) + c4 + e];
+              float x = xs[r * 32 + ((((lane & 7) ^ (r & 7))) << 2) + e];
               if (scale_p) x *= __ldg(scale_p + n + e);
               if (bias_p) x += __ldg(bias_p + n + e);
               if (addend_p) x += __ldg(addend_p + doff[i] + n + e);
@@ -372,6 +381,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
     }
   }
 
@@ -480,16 +490,19 @@ int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmPar
   if (!configured) {
     CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      L::kDynamic));
+                                      L::dynamic_bytes(3) <= 232448 ? L::dynamic_bytes(3)
+                                                                    : L::dynamic_bytes(2)));
     configured = true;
   }
+  CMR_REQUIRE(L::dynamic_bytes(p.epi_groups) <= 232448);
   ConvGemmParams q = p;
   q.m_tiles = ceil_div(p.M, kBM);
   q.n_tiles = ceil_div(p.N, BN);
   const long long tiles = (long long)q.m_tiles * q.n_tiles;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
-  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::kDynamic, st>>>(tmap, tmap_a, q);
+  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::dynamic_bytes(p.epi_groups), st>>>(
+      tmap, tmap_a, q);
   prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -519,7 +532,7 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   const long long M = (long long)c->batch * c->out_h * c->out_w;
   CMR_REQUIRE(M > 0 && M < (1ll << 31));
   CMR_REQUIRE((long long)c->batch * c->in_h * c->in_w < (1ll << 31));
-  CMR_REQUIRE((long long)c->batch * c->d_h * c->d_w < (1ll << 31));
+  CMR_REQUIRE((long long)c->batch * c->d_h * c->d_w * c->d_ld < (1ll << 31));
   ConvGemmParams p;
   p.a = a;
   p.in_h = c->in_h; p.in_w = c->in_w; p.in_c = c->in_c; p.in_ld = c->in_ld;
@@ -568,11 +581,19 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
                          -c->pad, -c->pad, c->out_h, c->out_w, kBM, false) == CMR_OK)
       p.tma_a = 1;
   }
+  // Epilogue warps per TMEM lane quarter: with TMA A tiles warps 0-3 join the epilogue
+  // (3 groups).  For 256-wide tiles the shared memory holds either 4 operand stages and 2
+  // groups (long reductions: the main loop dominates) or 3 stages and 3 groups (short
+  // reductions: the epilogue's HBM traffic dominates).
+  p.epi_groups = p.tma_a ? 3 : 2;
+  const bool deep = p.K >= 1024 || !p.tma_a;
+  if (bn == 256 && deep) p.epi_groups = 2;
   cudaStream_t st = as_stream(stream);
   switch (bn) {
     case 64: return launch<64, 6>(tmap, tmap_a, p, st);
     case 128: return launch<128, 5>(tmap, tmap_a, p, st);
-    case 256: return launch<256, 3>(tmap, tmap_a, p, st);
+    case 256:
+      return deep ? launch<256, 4>(tmap, tmap_a, p, st) : launch<256, 3>(tmap, tmap_a, p, st);
     default: return CMR_ERR_INVALID_ARG;
   }
 }

@@ -254,7 +254,7 @@ conv_wgrad_tc_kernel(const WgradParams p) {
 
 // ------------------------------------------------------------ TMA variant ----
 constexpr int kTmaThreads = 192;
-constexpr int kTPix = 64;   // pixels per k-block: fewer, larger TMA boxes (8 KB each)
+constexpr int kTPix = 48;   // pixels per k-block: TMA boxes of 6 KB, 3 stages of a 128 x 256 tile
 
 template <int BN, int STAGES>
 struct TSmem {
@@ -544,9 +544,9 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
       splits = ceil_div(p.num_kb, p.kb_per_split);
       p.splits = splits;
       p.taps_w = taps_w;
-      if (bn == 256) return launch_wgrad_tma<256, 2>(tp, tq, p, splits, taps, st);
-      if (bn == 128) return launch_wgrad_tma<128, 3>(tp, tq, p, splits, taps, st);
-      return launch_wgrad_tma<64, 4>(tp, tq, p, splits, taps, st);
+      if (bn == 256) return launch_wgrad_tma<256, 3>(tp, tq, p, splits, taps, st);
+      if (bn == 128) return launch_wgrad_tma<128, 4>(tp, tq, p, splits, taps, st);
+      return launch_wgrad_tma<64, 5>(tp, tq, p, splits, taps, st);
     }
     p.num_kb = ceil_div(p.M, kPix);
   }

@@ -150,7 +150,8 @@ class GraphedUpdater(object):
         B = imgs.shape[0]
         G = max(self.max_boxes, masks.shape[1], max(len(b) for b in bboxes))
         st.imgs = torch.empty(tuple(imgs.shape), dtype=torch.float32, device=dev)
-        st.masks = torch.zeros((B, G) + tuple(masks.shape[2:]), dtype=masks.dtype, device=dev)
+        # same shape as the caller's masks: staging them is one contiguous copy
+        st.masks = torch.zeros(tuple(masks.shape), dtype=masks.dtype, device=dev)
         st.gt = self._GroundTruth(bboxes, labels, dev, capacity=G)
         st.seed_word = torch.zeros((1,), dtype=torch.int64, device=dev)
         st.graph = None
@@ -160,7 +161,7 @@ class GraphedUpdater(object):
 
     def _stage(self, st, imgs, bboxes, labels, masks):
         self.h2d_bytes = st.gt.nbytes
-        for dst, src in ((st.imgs, imgs), (st.masks[:, :masks.shape[1]], masks)):
+        for dst, src in ((st.imgs, imgs), (st.masks, masks)):
             if not src.is_cuda:
                 self.h2d_bytes += src.numel() * src.element_size()
             dst.copy_(src, non_blocking=True)
