@@ -58,7 +58,8 @@ struct ConvGemmParams {
   const float* mask;
   int relu, round_out;
   int m_tiles, n_tiles;
-  int tma_a;   // A tiles come from the im2col tensor map (else cp.async gathers)
+  int tma_a;   // A tiles by TMA: 1 = im2col-mode map, 2 = tiled-mode map (plain matrix);
+               // 0 = cp.async gathers
   int epi_groups;   // epilogue warps per TMEM lane quarter: 3 with TMA A tiles, else 2
 };
 
@@ -200,8 +201,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           mbar_wait(&empty_bar[s], phase ^ 1);
           if (p.tma_a) {
             mbar_arrive_expect_tx(&full_bar[s], L::kBBytes + kABytes);
-            tma_load_im2col_4d(smem_base + L::kAOff + s * kABytes, &tmap_a, &full_bar[s],
-                               cb * kBK, w0, h0, img, fs, fr);
+            if (p.tma_a == 2)   // 1x1 stride 1: the activations are a plain (M, C) matrix
+              tma_load_2d(smem_base + L::kAOff + s * kABytes, &tmap_a, &full_bar[s], cb * kBK,
+                          m0);
+            else
+              tma_load_im2col_4d(smem_base + L::kAOff + s * kABytes, &tmap_a, &full_bar[s],
+                                 cb * kBK, w0, h0, img, fs, fr);
             if (++cb == cpt) {
               cb = 0;
               if (++fs == p.kw) {
@@ -482,6 +487,27 @@ int g_im2col_tma = 1;   // cmr_set_im2col_tma
 
 namespace {
 
+}  // namespace
+
+// 2-D fp32 matrix (rows, cols) with row pitch ld, box = (box_rows, 32 cols); 128 B swizzle
+// of 16 B units (K-major operands) or of 32 B units (atom32: MN-major operands).
+int make_tmap_tiled_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols,
+                       uint64_t ld, uint32_t box_rows, bool atom32) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn || (ld & 3) != 0 || cols > ld || box_rows > 256) return CMR_ERR_UNSUPPORTED;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim,
+                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? CMR_OK : CMR_ERR_UNSUPPORTED;
+}
+
+namespace {
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
            cudaStream_t st) {
@@ -577,8 +603,13 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
       c->out_w == (c->in_w + 2 * c->pad - c->kw) / c->stride + 1 &&
       c->in_h + 2 * c->pad >= c->kh && c->in_w + 2 * c->pad >= c->kw && c->kh < 256 &&
       c->kw < 256) {
-    if (make_tmap_im2col(&tmap_a, a, c->batch, c->in_h, c->in_w, c->in_ld, c->in_c, c->stride,
-                         -c->pad, -c->pad, c->out_h, c->out_w, kBM, false) == CMR_OK)
+    if (c->kh == 1 && c->kw == 1 && c->stride == 1 && c->pad == 0 &&
+        make_tmap_tiled_2d(&tmap_a, a, (uint64_t)p.M, (uint64_t)c->in_c, (uint64_t)c->in_ld, kBM,
+                           false) == CMR_OK)
+      p.tma_a = 2;
+    else if (make_tmap_im2col(&tmap_a, a, c->batch, c->in_h, c->in_w, c->in_ld, c->in_c,
+                              c->stride, -c->pad, -c->pad, c->out_h, c->out_w, kBM,
+                              false) == CMR_OK)
       p.tma_a = 1;
   }
   // Epilogue warps per TMEM lane quarter: with TMA A tiles warps 0-3 join the epilogue

@@ -64,6 +64,7 @@ struct WgradParams {
   const float* row_scale;
   int kb_per_split, num_kb;
   int splits, taps_w;  // grid.z = taps * splits; tap (fr, fs) shifts q by (fr, fs) pixels
+  int p_tiled, q_tiled;  // operand is a plain (pixels x channels) matrix: tiled-mode TMA
   int probe;           // timing probes (CMR_WGRAD_PROBE): 1 = loads only for the first ring
                        // fill, 2 = no MMAs; results are garbage, 0 in normal operation
 };
@@ -267,7 +268,11 @@ struct TSmem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
-template <int BN, int STAGES>
+// PAIR: launched as clusters of two CTAs along grid.x (adjacent row tiles, same column
+// tile, same pixel range).  The two CTAs read the same Q (layer input) tiles: each loads
+// half of the Q blocks and multicasts them into both shared memories, which cuts the
+// L2 -> SM traffic per CTA from P + Q to P + Q/2 (the kernel is bound by that traffic).
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kTmaThreads)
 conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
                       const __grid_constant__ CUtensorMap tmap_q, const WgradParams p) {
@@ -297,7 +302,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
     prefetch_tensormap(&tmap_q);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIR ? 2 : 1);   // the MMA issuers of both CTAs release it
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -307,39 +312,70 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything signals them
 
-  if (warp == 4) {
-    // ------------------------------------------------------------ producer
+  if (warp <= 4) {
+    // ------------------------------------------------------------ producers
+    // One thread of each of warps 0-4 issues a share of the k-block's TMA loads (a copy
+    // instruction occupies its issuing thread for ~50 cycles, which would otherwise sit on
+    // the critical path of every stage); warp 4 also arms the stage's barrier with the
+    // byte count of all of them.  Warps 0-3 turn into the epilogue afterwards.
     if (lane == 0) {
-      // column blocks past the channel range would only load zeros: skip their copies
-      // (their shared memory is zeroed once below) -- not needed for correctness of the
-      // kept columns, the epilogue never writes columns >= cols
+      // column blocks past the channel range would only load zeros: their copies are
+      // skipped (the epilogue never writes rows >= rows or columns >= cols)
       const int p_blocks = min(kBM / 32, (p.rows - i0 + 31) / 32);
       const int q_blocks = min(BN / 32, (p.cols - j0 + 31) / 32);
+      const int n_blocks = p_blocks + q_blocks;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], phase ^ 1);
+        if (warp == 4) {
+          if (p.probe == 1 && kb >= STAGES) {
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)n_blocks * (kTPix * 128));
+        } else if (p.probe == 1 && kb >= STAGES) {
+          continue;
+        }
         int img, rem, oy, ox;
         p.div_hw.divmod((kb_begin + kb) * kTPix, img, rem);
         p.div_w.divmod(rem, oy, ox);
-        if (p.probe == 1 && kb >= STAGES) {
-          mbar_arrive(&full_bar[s]);
-          continue;
-        }
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p_blocks + q_blocks) * (kTPix * 128));
         const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
         const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
         const int ph = oy * p.p.stride + p.p.off_y, pw = ox * p.p.stride + p.p.off_x;
         const int qh = oy * p.q.stride + p.q.off_y, qw = ox * p.q.stride + p.q.off_x;
-        for (int b = 0; b < p_blocks; ++b)
-          tma_load_im2col_4d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s],
-                             p.p.c0 + i0 + b * 32, pw, ph, img, 0, 0);
-        for (int b = 0; b < q_blocks; ++b)
-          tma_load_im2col_4d(qa + b * (kTPix * 128), &tmap_q, &full_bar[s],
-                             p.q.c0 + j0 + b * 32, qw, qh, img, tap_fs, tap_fr);
+        const int pix0 = (kb_begin + kb) * kTPix;
+        for (int b = warp; b < n_blocks; b += 5) {
+          if (b < p_blocks) {
+            if (p.p_tiled)
+              tma_load_2d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s], p.p.c0 + i0 + b * 32,
+                          pix0);
+            else
+              tma_load_im2col_4d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s],
+                                 p.p.c0 + i0 + b * 32, pw, ph, img, 0, 0);
+          } else if (!PAIR) {
+            if (p.q_tiled)
+              tma_load_2d(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
+                          p.q.c0 + j0 + (b - p_blocks) * 32, pix0);
+            else
+              tma_load_im2col_4d(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
+                                 p.q.c0 + j0 + (b - p_blocks) * 32, qw, qh, img, tap_fs,
+                                 tap_fr);
+          } else if ((uint32_t)((b - p_blocks) & 1) == cta_rank) {
+            tma_load_im2col_4d_mcast(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
+                                     p.q.c0 + j0 + (b - p_blocks) * 32, qw, qh, img, tap_fs,
+                                     tap_fr, (uint16_t)3);
+          }
+        }
       }
     }
+    __syncwarp();
+  }
+  if (warp == 4) {
+    // nothing else
   } else if (warp == 5) {
     // ---------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 1, 1);  // both operands MN-major
@@ -357,7 +393,8 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
           const uint64_t db = make_smem_desc(qa + k * 1024, kTPix * 128, 512, 1);
           if (p.probe != 2 || kb == 0) umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        if (PAIR) umma_commit_mcast(&empty_bar[s], (uint16_t)3);
+        else umma_commit(&empty_bar[s]);
       }
       __syncwarp();
     }
@@ -402,6 +439,7 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still write to it
   if (warp == 5) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
@@ -438,21 +476,33 @@ int launch_wgrad(const WgradParams& p, int splits, int taps, cudaStream_t st) {
   return CMR_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 int launch_wgrad_tma(const CUtensorMap& tp, const CUtensorMap& tq, const WgradParams& p,
                      int splits, int taps, cudaStream_t st) {
   using L = TSmem<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
-    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, STAGES>,
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, STAGES, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::kDynamic));
     configured = true;
   }
-  dim3 grid(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits * taps);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(p.rows, kBM), ceil_div(p.cols, BN), splits * taps);
+  cfg.blockDim = dim3(kTmaThreads);
+  cfg.dynamicSmemBytes = L::kDynamic;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   prof_begin(kProfWgrad, 2.0 * p.M * (double)p.rows * p.cols * taps, st);
-  conv_wgrad_tma_kernel<BN, STAGES><<<grid, kTmaThreads, L::kDynamic, st>>>(tp, tq, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_tma_kernel<BN, STAGES, PAIR>, tp, tq, p);
   prof_end(st);
+  CMR_CUDA_TRY(e);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -481,6 +531,8 @@ int choose_splits(int tiles, int slots, int num_kb) {
 }  // namespace
 
 // conv_tc.cu
+int make_tmap_tiled_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols,
+                       uint64_t ld, uint32_t box_rows, bool atom32);
 int make_tmap_im2col(CUtensorMap* map, const float* base, int batch, int h, int w, int ld,
                      int channels, int stride, int lower_h, int lower_w, int n_pos_h,
                      int n_pos_w, int pixels, bool mn_major);
@@ -527,12 +579,27 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   // Default path: both operands through im2col-mode tensor maps.
   if (g_im2col_tma) {
     CUtensorMap tp, tq;
-    if (make_tmap_im2col(&tp, gy, c->batch, c->gy_h, c->gy_w, c->gy_ld, c->gy_c0 + c->rows,
-                         c->gy_stride, c->gy_off_y, c->gy_off_x, c->loop_h, c->loop_w, kTPix,
-                         true) == CMR_OK &&
-        make_tmap_im2col(&tq, x, c->batch, c->x_h, c->x_w, c->x_ld, c->x_c0 + c->cols,
-                         c->x_stride, c->x_off_y, c->x_off_x, c->loop_h, c->loop_w, kTPix,
-                         true) == CMR_OK) {
+    // An operand that is read at every pixel of its tensor, in order, is a plain
+    // (pixels x channels) matrix: tiled-mode TMA (its rows stream ~1.5x faster through the
+    // copy engine than im2col-mode positions).  Everything else goes through im2col mode.
+    const bool multi_tap = taps > 1;
+    p.p_tiled = c->gy_h == c->loop_h && c->gy_w == c->loop_w && c->gy_stride == 1 &&
+                c->gy_off_y == 0 && c->gy_off_x == 0;
+    p.q_tiled = !multi_tap && c->x_h == c->loop_h && c->x_w == c->loop_w && c->x_stride == 1 &&
+                c->x_off_y == 0 && c->x_off_x == 0;
+    const int rc_p =
+        p.p_tiled ? make_tmap_tiled_2d(&tp, gy, (uint64_t)M, (uint64_t)(c->gy_c0 + c->rows),
+                                       (uint64_t)c->gy_ld, kTPix, true)
+                  : make_tmap_im2col(&tp, gy, c->batch, c->gy_h, c->gy_w, c->gy_ld,
+                                     c->gy_c0 + c->rows, c->gy_stride, c->gy_off_y, c->gy_off_x,
+                                     c->loop_h, c->loop_w, kTPix, true);
+    const int rc_q =
+        p.q_tiled ? make_tmap_tiled_2d(&tq, x, (uint64_t)M, (uint64_t)(c->x_c0 + c->cols),
+                                       (uint64_t)c->x_ld, kTPix, true)
+                  : make_tmap_im2col(&tq, x, c->batch, c->x_h, c->x_w, c->x_ld,
+                                     c->x_c0 + c->cols, c->x_stride, c->x_off_y, c->x_off_x,
+                                     c->loop_h, c->loop_w, kTPix, true);
+    if (rc_p == CMR_OK && rc_q == CMR_OK) {
       const int bn = c->cols > 128 ? 256 : (c->cols > 64 ? 128 : 64);
       p.num_kb = ceil_div(p.M, kTPix);
       const int tiles = ceil_div(p.rows, kBM) * ceil_div(p.cols, bn) * taps;
@@ -544,9 +611,20 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
       splits = ceil_div(p.num_kb, p.kb_per_split);
       p.splits = splits;
       p.taps_w = taps_w;
-      if (bn == 256) return launch_wgrad_tma<256, 3>(tp, tq, p, splits, taps, st);
-      if (bn == 128) return launch_wgrad_tma<128, 4>(tp, tq, p, splits, taps, st);
-      return launch_wgrad_tma<64, 5>(tp, tq, p, splits, taps, st);
+      // pairs of adjacent row tiles share their Q tiles by multicast
+      static int pair_ok = -1;
+      if (pair_ok < 0) {
+        const char* e = getenv("CMR_WGRAD_PAIR");
+        pair_ok = e ? atoi(e) : 0;   // measured: no gain (the copy engine's row rate binds)
+      }
+      const bool pair = pair_ok && (ceil_div(p.rows, kBM) % 2 == 0);
+      if (bn == 256)
+        return pair ? launch_wgrad_tma<256, 3, true>(tp, tq, p, splits, taps, st)
+                    : launch_wgrad_tma<256, 3, false>(tp, tq, p, splits, taps, st);
+      if (bn == 128)
+        return pair ? launch_wgrad_tma<128, 4, true>(tp, tq, p, splits, taps, st)
+                    : launch_wgrad_tma<128, 4, false>(tp, tq, p, splits, taps, st);
+      return launch_wgrad_tma<64, 5, false>(tp, tq, p, splits, taps, st);
     }
     p.num_kb = ceil_div(p.M, kPix);
   }
