@@ -73,6 +73,14 @@ _SIGNATURES = {
                                      c_void_p, c_void_p, c_ulonglong, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    'cmr_detections_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'cmr_detections': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                               c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                               c_void_p]),
+    'cmr_paste_masks': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_longlong,
+                                c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                c_void_p]),
     'cmr_mask_targets': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'cmr_mask_loss': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -30,34 +30,40 @@ __device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float
   return iou >= thresh;
 }
 
-// mask[i][cb] bit k  <=>  j = 64*cb + k > i  and  IoU(i, j) >= thresh.
+// mask[i][cb] bit k  <=>  j = 64*cb + k > i  and  IoU(i, j) >= thresh  (and, when class
+// labels are given, label[i] == label[j]: per-class suppression in one pass).
 // grid = (nb, nb, B); only the upper block triangle does work.
 __global__ void __launch_bounds__(64)
-nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ n_arr, int n_max,
-                float thresh, unsigned long long* __restrict__ mask, int nb_stride) {
+nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ labels,
+                const int* __restrict__ n_arr, int n_max, float thresh,
+                unsigned long long* __restrict__ mask, int nb_stride) {
   const int img = blockIdx.z;
   const int n = n_arr ? min(n_arr[img], n_max) : n_max;
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
   boxes += (size_t)img * n_max;
+  if (labels) labels += (size_t)img * n_max;
   mask += (size_t)img * n_max * nb_stride;
   __shared__ float4 cbox[64];
   __shared__ float carea[64];
+  __shared__ int clabel[64];
   const int t = threadIdx.x;
   const int j = cb * 64 + t;
   if (j < n) {
     cbox[t] = boxes[j];
     carea[t] = box_area(cbox[t]);
+    clabel[t] = labels ? labels[j] : 0;
   }
   __syncthreads();
   const int i = rb * 64 + t;
   if (i < n) {
     const float4 b = boxes[i];
     const float ai = box_area(b);
+    const int li = labels ? labels[i] : 0;
     const int ncol = min(64, n - cb * 64);
     unsigned long long bits = 0ull;
     for (int k = (rb == cb) ? t + 1 : 0; k < ncol; ++k)
-      if (iou_ge(b, ai, cbox[k], carea[k], thresh)) bits |= (1ull << k);
+      if (clabel[k] == li && iou_ge(b, ai, cbox[k], carea[k], thresh)) bits |= (1ull << k);
     mask[(size_t)i * nb_stride + cb] = bits;
   }
 }
@@ -319,10 +325,11 @@ int next_pow2(int v) {
 }
 
 int launch_nms(const float4* boxes, const int* n_arr, int n_max, int B, float thresh, int limit,
-               int32_t* keep, int32_t* n_keep, unsigned long long* mask, cudaStream_t st) {
+               int32_t* keep, int32_t* n_keep, unsigned long long* mask, cudaStream_t st,
+               const int* labels = nullptr) {
   const int nb = (n_max + 63) / 64;
   dim3 grid(nb, nb, B);
-  nms_mask_kernel<<<grid, 64, 0, st>>>(boxes, n_arr, n_max, thresh, mask, nb);
+  nms_mask_kernel<<<grid, 64, 0, st>>>(boxes, labels, n_arr, n_max, thresh, mask, nb);
   CMR_LAUNCH_CHECK();
   const size_t smem = sizeof(unsigned long long) * nb;
   nms_sweep_kernel<<<B, kSweepThreads, smem, st>>>(mask, n_arr, n_max, nb, limit, keep, n_keep,
@@ -332,6 +339,15 @@ int launch_nms(const float4* boxes, const int* n_arr, int n_max, int B, float th
 }
 
 }  // namespace
+
+// Shared with detect.cu: greedy NMS of B score-sorted box lists (n_arr[b] <= n_max boxes
+// each); with `labels` a box only suppresses boxes of its own class.
+int launch_nms_batch(const float* boxes, const int* labels, const int* n_arr, int n_max, int B,
+                     float thresh, int32_t* keep, int32_t* n_keep, unsigned long long* mask,
+                     cudaStream_t st) {
+  return launch_nms(reinterpret_cast<const float4*>(boxes), n_arr, n_max, B, thresh, 0, keep,
+                    n_keep, mask, st, labels);
+}
 
 // Shared with targets.cu: sorts `rows` independent key arrays of n_pad (power of two).
 int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {

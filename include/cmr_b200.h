@@ -298,6 +298,42 @@ int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, int max_bbox
                      const int32_t* n_pos, int n_sample, int mask_size,
                      int32_t* gt_mask, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Inference post-processing (csrc/detect.cu).
+ * ------------------------------------------------------------------------ */
+/* MaskRCNN._to_bboxes + _suppress (chainer_mask_rcnn/models/mask_rcnn.py:178-243) for a
+ * batch: softmax of the class logits, boxes of every (RoI, class >= 1) pair whose
+ * probability exceeds score_thresh decoded against roi / scale (loc * std + mean,
+ * loc2bbox) and clipped to the image, then per-class NMS -- done as ONE score-sorted,
+ * class-aware NMS pass per image.
+ * cls_loc (B*max_roi, ld_loc) holds 4*n_class offsets per RoI, score (B*max_roi,
+ * ld_score) n_class logits; rois (B, max_roi, 4) with n_roi (B) valid rows (device);
+ * img_info (B, 3) device floats = (scale, height, width) of each original image;
+ * loc_mean / loc_std: HOST double[4].
+ * Outputs per image, survivors in descending score order (rows >= n_det[b] are padding
+ * with label -1): det_bbox (B, max_cand, 4), det_label (B, max_cand) foreground class ids
+ * (class - 1), det_score (B, max_cand), n_det (B).  At most max_cand highest-scoring
+ * candidates per image enter the NMS. */
+size_t cmr_detections_workspace_bytes(int B, int max_roi, int n_class, int max_cand);
+int cmr_detections(const float* cls_loc, int ld_loc, const float* score, int ld_score,
+                   const float* rois, const int32_t* n_roi, int B, int max_roi,
+                   int n_class, const float* img_info, const double* loc_mean,
+                   const double* loc_std, float score_thresh, float nms_thresh,
+                   int max_cand, float* det_bbox, int32_t* det_label, float* det_score,
+                   int32_t* n_det, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* segm_results (chainer_mask_rcnn/models/mask_rcnn.py:63-107): for detection k, the
+ * (mask_size x mask_size) map of class label[k] in mask_prob -- element (k, c, y, x) at
+ * mask_prob[k*stride_n + c*stride_c + y*stride_y + x*stride_x], so NCHW and channels-last
+ * tensors both work; logits when apply_sigmoid != 0, else probabilities -- is zero-padded by
+ * one pixel, resized (cv2 INTER_LINEAR, fp32) to the integer box grown by
+ * (mask_size+2)/mask_size, thresholded at 0.5 and written into out (n, H, W) uint8
+ * (fully written: zeros elsewhere).  bbox (n, 4) = (y1, x1, y2, x2). */
+int cmr_paste_masks(const float* bbox, const int32_t* label, const float* mask_prob,
+                    long long stride_n, long long stride_c, long long stride_y,
+                    long long stride_x, int n, int mask_size, int H, int W,
+                    int apply_sigmoid, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ def _load(relpath, modname, extra_stubs=None):
     stubs = _stub_chainer()
     if extra_stubs:
         stubs.update(extra_stubs)
+    stubs.pop(modname, None)
     saved = {k: sys.modules.get(k) for k in stubs}
     sys.modules.update(stubs)
     try:
@@ -109,6 +110,57 @@ def load_proposal_target_creator_module():
     oracle/bbox.py), or None."""
     return _load('chainer_mask_rcnn/models/utils/proposal_target_creator.py',
                  '_ref_proposal_target_creator', _stub_chainercv())
+
+
+def load_mask_rcnn_module():
+    """-> module of chainer_mask_rcnn/models/mask_rcnn.py (``segm_results``, ``expand_boxes``
+    and the ``MaskRCNN`` class whose ``_suppress`` / ``_to_bboxes`` run verbatim on NumPy
+    arrays), or None.  chainer.Chain / Variable / F.softmax / F.sigmoid are two-line NumPy
+    stubs; ``loc2bbox`` and ``non_maximum_suppression`` (chainercv, absent) come from
+    oracle/bbox.py."""
+    import numpy
+    from . import bbox as ob
+    stubs = _stub_chainercv()
+    for n in ('chainercv.links.model.faster_rcnn.utils.loc2bbox',):
+        stubs[n] = types.ModuleType(n)
+    stubs['chainercv.links.model.faster_rcnn.utils.loc2bbox'].loc2bbox = ob.loc2bbox
+    stubs['chainercv.utils'].non_maximum_suppression = ob.non_maximum_suppression
+    for n in ('chainer_mask_rcnn', 'chainer_mask_rcnn.models', 'chainer_mask_rcnn.datasets'):
+        stubs[n] = types.ModuleType(n)
+        stubs[n].__path__ = []
+    stubs['chainer_mask_rcnn.datasets'].concat_examples = lambda *a, **k: None
+
+    class _Arr(object):
+        def __init__(self, a):
+            self.array = a
+
+    def _softmax(x):
+        e = numpy.exp(x - x.max(axis=1, keepdims=True))
+        return _Arr((e / e.sum(axis=1, keepdims=True)).astype(numpy.float32))
+
+    mod_stubs = _stub_chainer()
+    mod_stubs['chainer'].Chain = object
+    mod_stubs['chainer'].Variable = _Arr
+    mod_stubs['chainer.functions'].softmax = _softmax
+    mod_stubs['chainer.functions'].sigmoid = lambda x: _Arr(
+        (1 / (1 + numpy.exp(-x))).astype(numpy.float32))
+    stubs.update(mod_stubs)
+    return _load('chainer_mask_rcnn/models/mask_rcnn.py', 'chainer_mask_rcnn.models.mask_rcnn',
+                 stubs)
+
+
+def ref_to_bboxes(roi_cls_locs, roi_scores, rois, roi_indices, sizes, scales, n_class,
+                  mean, std, score_thresh, nms_thresh, detections_per_im):
+    """MaskRCNN._to_bboxes (mask_rcnn.py:203-261) run verbatim on NumPy arrays."""
+    import numpy
+    mod = load_mask_rcnn_module()
+    m = mod.MaskRCNN.__new__(mod.MaskRCNN)
+    m.xp = numpy
+    m.head = types.SimpleNamespace(n_class=n_class)     # MaskRCNN.n_class reads head.n_class
+    m.loc_normalize_mean, m.loc_normalize_std = mean, std
+    m.score_thresh, m.nms_thresh = score_thresh, nms_thresh
+    m._detections_per_im = detections_per_im
+    return m._to_bboxes(roi_cls_locs, roi_scores, rois.copy(), roi_indices, sizes, scales)
 
 
 def ref_roi_align_forward(x, rois_xy, outh, outw, spatial_scale, sampling_ratio):

@@ -15,6 +15,10 @@ small .npz fixtures committed next to this script:
                         hides sampling-ratio errors): feature-stride-16 boxes,
                         7x7 and 14x14 outputs, sampling_ratio 0 and 2
   affine_channel.npz    functions/affine_channel_2d.py forward/backward
+  proposal_targets.npz  models/utils/proposal_target_creator.py on a seeded scene
+  detect.npz            MaskRCNN._to_bboxes (+ _suppress) and segm_results of
+                        models/mask_rcnn.py on seeded head outputs (tests/synth.py
+                        head_outputs); loc2bbox / NMS served by oracle/bbox.py
 """
 import os
 import sys
@@ -125,6 +129,34 @@ def proposal_target_fixture():
                 gt_roi_loc=gl.astype(np.float32), gt_roi_label=glab, gt_roi_mask=gm)
 
 
+def detect_fixture():
+    """MaskRCNN._to_bboxes / segm_results (models/mask_rcnn.py:63-107,178-261) verbatim."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import cv2
+    import synth
+    seed, n_roi, n_class = 11, 500, 21
+    sizes, scales = [(300, 400), (280, 390)], np.array([1.6, 1.3], np.float32)
+    rs = np.random.RandomState(seed)
+    locs, logits, rois, idx = synth.head_outputs(rs, n_roi, n_class, 2, 300, 400)
+    bboxes, labels, scores = ref_loader.ref_to_bboxes(
+        locs, logits, rois, idx, sizes, scales, n_class, (0., 0., 0., 0.), (0.1, 0.1, 0.2, 0.2),
+        0.05, 0.5, 100)
+    out = dict(seed=seed, n_roi=n_roi, n_class=n_class, sizes=np.asarray(sizes), scales=scales)
+    mod = ref_loader.load_mask_rcnn_module()
+    had = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)       # OpenCV's own bilinear code (see oracle/mask_target.py)
+    for i in range(2):
+        out['bbox_%d' % i], out['label_%d' % i], out['score_%d' % i] = \
+            bboxes[i], labels[i], scores[i]
+        n = min(len(bboxes[i]), 12)
+        prob = (1 / (1 + np.exp(-rs.standard_normal((n, n_class - 1, 14, 14))))).astype(np.float32)
+        out['mask_prob_%d' % i] = prob
+        out['masks_%d' % i] = np.packbits(mod.segm_results(
+            bboxes[i][:n], labels[i][:n], prob, sizes[i][0], sizes[i][1]), axis=-1)
+    cv2.ipp.setUseIPP(had)
+    return out
+
+
 def main():
     assert ref_loader.reference_available(), 'needs /root/reference'
     np.savez_compressed(os.path.join(HERE, 'roi_align_unit.npz'), **unit_fixture())
@@ -132,6 +164,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'roi_align_random.npz'), **random_fixture())
     np.savez_compressed(os.path.join(HERE, 'affine_channel.npz'), **affine_fixture())
     np.savez_compressed(os.path.join(HERE, 'proposal_targets.npz'), **proposal_target_fixture())
+    np.savez_compressed(os.path.join(HERE, 'detect.npz'), **detect_fixture())
     print('golden vectors written to', HERE)
 
 

@@ -71,3 +71,18 @@ def detection_scene(seed, n_gt=6, H=320, W=416, n_roi=300):
     roi[:, 0::2] = np.clip(roi[:, 0::2], 0, H)
     roi[:, 1::2] = np.clip(roi[:, 1::2], 0, W)
     return roi.astype(np.float32), bbox, label, mask, (H, W)
+
+
+def head_outputs(rs, n_roi, n_class, n_img, img_h, img_w, scale=1.6):
+    """Box-head outputs for the inference post-processing: clustered RoIs (in the scaled
+    image), per-class offsets ~ N(0, 0.5) (normalised units) and logits in which a few
+    object classes stand out per cluster, so that per-class NMS has overlapping boxes.
+    -> roi_cls_locs (R,4C), roi_scores (R,C), rois (R,4), roi_indices (R,) sorted."""
+    rois = clustered_boxes(rs, n_roi, img_h * scale, img_w * scale, n_centers=12)
+    idx = np.sort(rs.randint(0, n_img, n_roi)).astype(np.int32)
+    locs = (rs.standard_normal((n_roi, 4 * n_class)) * 0.5).astype(np.float32)
+    logits = rs.standard_normal((n_roi, n_class)).astype(np.float32)
+    hot = rs.randint(1, n_class, n_roi)
+    logits[np.arange(n_roi), hot % 4 + 1] += rs.uniform(2, 6, n_roi).astype(np.float32)
+    logits[np.arange(n_roi), hot] += rs.uniform(0, 4, n_roi).astype(np.float32)
+    return locs, logits, rois.astype(np.float32), idx
