@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 METRIC = 'images/sec Mask R-CNN R50-C4 train step (3x800x1333)'
 H, W, BS, N_INST, N_FG = 800, 1333, 2, 40, 80
 MEAN = (123.152, 115.903, 103.063)
-FLOPS_PER_IMAGE = 3.157e12        # conv/GEMM FLOPs of one R50-C4 train step / 2
+FLOPS_PER_IMAGE = {50: 3.157e12, 101: 3.644e12}   # GEMM FLOPs of one train step / 2
 
 
 def peaks():
@@ -125,11 +125,11 @@ class ClockSampler(object):
         return out
 
 
-def cpu_baseline(budget_s=12.0):
+def cpu_baseline(budget_s=12.0, n_layers=50):
     """The oracle port of the reference CPU path on a bounded sample (oracle/cpu_step.py)."""
     from oracle import cpu_step
     f = cpu_step.calibrate_fraction(budget_s)
-    s = cpu_step.CpuStepSample(f)
+    s = cpu_step.CpuStepSample(f, n_layers=n_layers)
     s.step()                                   # warm the BLAS threads / page in buffers
     t = s.step()
     return {'value': s.images_per_second(t), 'unit': 'images/s', 'cores': os.cpu_count(),
@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
     total = max(args.steps + args.warmup, 1)
     budget = min(15.0, 150.0 / total)
     f = cpu_step.calibrate_fraction(budget)
-    s = cpu_step.CpuStepSample(f)
+    s = cpu_step.CpuStepSample(f, n_layers=args.layers)
     for _ in range(args.warmup):
         s.step()
     ts = [s.step() for _ in range(args.steps)]
@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args.gpus),
+        'config': workload_config(args.gpus, args.layers),
         'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -171,10 +171,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
-    return {'workload': 'R50-C4 COCO train step, bs=2 per GPU, 3x800x1333 synthetic images + '
+def workload_config(n_gpus, layers=50):
+    return {'workload': 'R%d-C4 COCO train step, bs=2 per GPU, 3x800x1333 synthetic images + ' % layers +
                         '40 instances/image, 12000->2000 proposals, 512 sampled RoIs/image, '
-                        'roi_size 14 (BASELINE.json configs[1])',
+                        'roi_size 14 (BASELINE.json configs[%d])' % (1 if layers == 50 else 3),
             'global_batch': BS * n_gpus, 'parallelism': 'dp%d' % n_gpus,
             'l2': 'per-step working set (>4 GB of activations) exceeds the 126 MB L2; no flush'}
 
@@ -187,6 +187,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--layers', type=int, default=50, choices=[50, 101],
+                    help='backbone depth: 50 = BASELINE configs[1] (default), 101 = configs[3]')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -209,7 +211,7 @@ def main():
     lib = _lib.load()
     warmup = max(args.warmup, 3)
 
-    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=(2, 4, 8, 16, 32), roi_size=14,
+    model = models.MaskRCNNResNet(args.layers, N_FG, anchor_scales=(2, 4, 8, 16, 32), roi_size=14,
                                   min_size=800, max_size=1333, seed=0)
     chain = models.MaskRCNNTrainChain(model)
     opt = optimizers.MomentumSGD(lr=0.00125 * BS * world, momentum=0.9)
@@ -317,11 +319,15 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32',
-            'data': 'synthetic', 'config': workload_config(world),
+            'data': 'synthetic', 'config': workload_config(world, args.layers),
             'roofline': {
                 'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel (fprop + dgrad implicit GEMM)',
                 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / tf32_peak if tf32_peak else None, 'traffic': None,
+                'frac': achieved / tf32_peak if tf32_peak else None,
+                # dram__bytes_read + write of ONE representative launch (res5 3x3 forward,
+                # 236.8 GFLOP) from the ncu --set full capture profiles/r1_ncu_conv_v9_raw.csv;
+                # `achieved` sums all 108 launches of the step
+                'traffic': 177.1e6,
                 'peak_source': '%s bf16_tflops_sustained / 2: kind::tf32 issues at half the '
                                'bf16 rate (cuBLAS TF32 8192^3 on this pool: 763 burst / 622 '
                                'sustained TFLOP/s)' % pk['source'],
@@ -334,7 +340,7 @@ def main():
                           'launches_per_step': cnt_w / args.steps,
                           'share_of_step': ms_w / ms_total if ms_total else None},
             },
-            'step_tflops': FLOPS_PER_IMAGE * BS * world / (ms_per_step * 1e-3) / 1e12,
+            'step_tflops': FLOPS_PER_IMAGE[args.layers] * BS * world / (ms_per_step * 1e-3) / 1e12,
             'gpu_launches': int(launches.item()),
             'clocks': clk,
             'loss_first': float(losses[0].item()), 'loss_last': float(losses[-1].item()),
@@ -343,7 +349,7 @@ def main():
         if e2e:
             line['e2e'] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline()
+            line['cpu_baseline'] = cpu_baseline(n_layers=args.layers)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

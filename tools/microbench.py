@@ -1,5 +1,6 @@
-"""Kernel microbenchmarks (BASELINE config 5 and conv GEMM shapes), CUDA-event timed.
-Usage: python tools/microbench.py [roi|nms|conv|all] [--out FILE]"""
+"""Kernel microbenchmarks (BASELINE config 5 and conv GEMM shapes) and the inference
+throughput of BASELINE config 3, CUDA-event timed.
+Usage: python tools/microbench.py [roi|nms|conv|peaks|infer|all] [--out FILE]"""
 import argparse
 import ctypes
 import json
@@ -196,6 +197,44 @@ def bench_peaks(out):
     print(json.dumps(rec)); out.append(rec)
 
 
+def bench_infer(out):
+    """BASELINE config 3: R50-C4 inference on a 1333x800 image, 6000 -> 1000 proposals ->
+    100 detections with masks (MaskRCNN.predict: both head passes, per-class NMS, mask
+    paste), images/s at batch 1 and 2.  Weights are random (flat class probabilities), so
+    score_thresh is lowered until ~100 detections survive, like a trained model's output."""
+    from chainer_mask_rcnn_b200 import models
+    rs = np.random.RandomState(0)
+    model = models.MaskRCNNResNet(50, 80, anchor_scales=(2, 4, 8, 16, 32), roi_size=14,
+                                  min_size=800, max_size=1333)
+    model.score_thresh = 1. / 81. * 1.02
+    for bs in (1, 2):
+        imgs = [rs.uniform(0, 255, (3, 800, 1333)).astype(np.float32) for _ in range(bs)]
+        model.predict(imgs)
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        iters = 5
+        for _ in range(iters):
+            bboxes, masks, labels, scores = model.predict(imgs)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3 / iters
+        # device part only (network + detections), without the host mask download
+        from chainer_mask_rcnn_b200.utils import config
+        x = torch.from_numpy(np.stack(model.prepare(imgs)[0])).cuda()
+        sizes = [(800, 1333)] * bs
+        scales = np.ones(bs, np.float32)
+
+        def dev_only():
+            with config.using_config('train', False):
+                feat, rois, cnt, cl, sc, _ = model._forward_padded(x, scales, False)
+                model._detect(cl, sc, rois, cnt, sizes, scales)
+        med, best = time_ms(dev_only, iters=10, warmup=2, flush=False)
+        rec = dict(kernel='predict_r50_c4', batch=bs, n_det=[len(b) for b in bboxes],
+                   ms_per_batch_e2e=ms, images_per_s_e2e=bs / ms * 1e3,
+                   ms_per_batch_box_pass=med, images_per_s_box_pass=bs / med * 1e3)
+        print(json.dumps(rec)); out.append(rec)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('what', nargs='?', default='all')
@@ -210,6 +249,8 @@ if __name__ == '__main__':
         bench_conv(out)
     if args.what in ('peaks', 'all'):
         bench_peaks(out)
+    if args.what in ('infer', 'all'):
+        bench_infer(out)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         with open(args.out, 'w') as f:

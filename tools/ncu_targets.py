@@ -1,20 +1,23 @@
-"""Small driver for ncu captures: runs the dominant tensor-core kernels on shapes of the
-train step a few times.
-  conv     res5 3x3 (50176 x 512 x 4608), fused affine + ReLU
-  conv1x1  res5 conv3 (50176 x 2048 x 512), fused affine + residual add + ReLU
-  small    res4 3x3 (8568 x 256 x 2304)
-  wgrad    res5 3x3 weight gradient, all 9 taps
-  wgrad1x1 res5 conv3 weight gradient (2048 x 512 over 50176 pixels)"""
+"""Small driver for ncu captures: runs one kernel of the train step on its real shape a
+few times.
+  conv      res5 3x3 forward (50176 x 512 x 4608), fused affine + ReLU   [<256,4>, 8 epi warps]
+  conv1x1   res5 conv3 (50176 x 2048 x 512), affine + residual + ReLU    [<256,3>, 12 epi warps]
+  small     res4 3x3 (8568 x 256 x 2304)
+  wgrad     res5 3x3 weight gradient, all 9 taps (512 x 512 over 50176 pixels)
+  wgrad1x1  res5 conv3 weight gradient (2048 x 512 over 50176 pixels)
+  roi       ROIAlign NHWC forward + backward, train shape (1024 RoIs, 2x51x84x1024, 7x7 bins)"""
 import os
 import sys
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from chainer_mask_rcnn_b200.models import engine as E  # noqa: E402
 
-what = sys.argv[1] if len(sys.argv) > 1 else 'both'
+what = sys.argv[1] if len(sys.argv) > 1 else 'conv'
 dev = 'cuda'
 x = E.round_tf32(torch.randn((1024, 7, 7, 512), device=dev))
 w = E.round_tf32(torch.randn((512, 3, 3, 512), device=dev) / 68.)
@@ -28,15 +31,23 @@ scale = torch.ones(2048, device=dev)
 bias = torch.zeros(2048, device=dev)
 gw = torch.zeros((512, 3, 3, 512), device=dev)
 gw3 = torch.zeros((2048, 512), device=dev)
+if what == 'roi':
+    import synth
+    rs = np.random.RandomState(0)
+    feat = torch.randn((2, 51, 84, 1024), device=dev)
+    rois = torch.from_numpy(synth.rois_xy(rs, 1024, 2, 800, 1333)).cuda()
 for _ in range(4):
-    if what in ('conv', 'both'):
+    if what == 'conv':
         E.conv_gemm(x, w, 512, 3, 3, 1, 1, scale=scale, bias=bias, relu=True)
     if what == 'conv1x1':
         E.conv_gemm(x, w3, 2048, scale=scale, bias=bias, addend=res, relu=True)
     if what == 'small':
         E.conv_gemm(xs, ws, 256, 3, 3, 1, 1, scale=scale, bias=bias, relu=True)
-    if what in ('wgrad', 'both'):
+    if what == 'wgrad':
         E.wgrad_tap(g, x, gw, 512, 512, (7, 7), 9 * 512, x_off=(-1, -1), taps=(3, 3))
     if what == 'wgrad1x1':
         E.wgrad_tap(g3, x, gw3, 2048, 512, (7, 7), 512)
+    if what == 'roi':
+        y = E.roi_align_nhwc(feat, rois, 14, 14, 2, 1. / 16)
+        E.roi_align_nhwc_bwd(y, rois, tuple(feat.shape), 14, 14, 2, 1. / 16)
 torch.cuda.synchronize()
