@@ -35,6 +35,7 @@
 // full/empty mbarrier ring of STAGES k-blocks (32 fp32 = one 128 B swizzle row)
 // shared by all tiles; tmem_full/tmem_empty barriers per accumulator buffer.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -70,11 +71,10 @@ constexpr int kProducerThreads = 128;
 constexpr int kEpiWarp0 = 6;                 // first epilogue warp
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;  // 448
-constexpr int kMaxEpiWarps = 12;             // warps 0-3 join the epilogue in TMA mode
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR = false>
 struct SmemLayout {
-  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBK * 4;   // a CTA of a pair holds N/2 rows
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kABytes;
   static constexpr int kBarOff = kBOff + STAGES * kBBytes;
@@ -84,11 +84,18 @@ struct SmemLayout {
   static_assert((2 * STAGES + 4) * 8 + 16 <= 256, "barrier area");
 };
 
-template <int BN, int STAGES>
+// PAIR: clusters of two CTAs (one SM pair) run ONE 256 x BN tile with tcgen05.mma
+// .cta_group::2: each CTA loads its 128 rows of A and BN/2 rows of B (32 KB instead of 48 KB
+// per k-block and SM -- the kernel is bound by operand delivery, not by the tensor core),
+// the leader CTA issues the MMAs for both, each CTA's TMEM receives its 128 rows and each
+// CTA runs its own epilogue.  TMA loads of both CTAs complete on the leader's barriers;
+// tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both.
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
+  constexpr int kTileM = PAIR ? 2 * kBM : kBM;
   constexpr uint32_t kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -105,6 +112,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
   const int lane = threadIdx.x & 31;
   const int num_kb = p.K / kBK;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap_b);
@@ -115,13 +125,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], p.epi_groups * 4);
+      mbar_init(&tmem_empty_bar[b], p.epi_groups * 4 * (PAIR ? 2 : 1));
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 5) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int ohw = p.out_h * p.out_w;
@@ -135,7 +149,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
     const int cpt = p.in_c / kBK;  // k-blocks per filter tap
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const int m0 = (tile / p.n_tiles) * kBM;
       int pix_base[8], iy0[8], ix0[8];
 #pragma unroll
@@ -186,10 +200,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     if (lane == 0) {
       uint32_t it = 0;
       const int cpt = p.in_c / kBK;  // k-blocks per filter tap
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % p.n_tiles) * BN;
-        // top-left input coordinate of the tile's first convolution position
-        const int m0 = (tile / p.n_tiles) * kBM;
+        // top-left input coordinate of the first convolution position of this CTA's rows
+        const int m0 = (tile / p.n_tiles) * kTileM + (int)cta_rank * kBM;
         const int img = m0 / ohw;
         const int rem = m0 - img * ohw;
         const int oy = rem / p.out_w;
@@ -199,6 +213,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           const uint32_t s = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1);
+          if (PAIR) {
+            // both CTAs' boxes complete on the leader's barrier, armed with all their bytes
+            const uint32_t bar = mapa_cluster(smem_u32(&full_bar[s]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (L::kBBytes + kABytes));
+            if (p.tma_a == 2)
+              tma_load_2d_pair(smem_base + L::kAOff + s * kABytes, &tmap_a, bar, cb * kBK, m0);
+            else
+              tma_load_im2col_4d_pair(smem_base + L::kAOff + s * kABytes, &tmap_a, bar, cb * kBK,
+                                      w0, h0, img, fs, fr);
+            if (++cb == cpt) {
+              cb = 0;
+              if (++fs == p.kw) {
+                fs = 0;
+                ++fr;
+              }
+            }
+            tma_load_2d_pair(smem_base + L::kBOff + s * L::kBBytes, &tmap_b, bar, kb * kBK,
+                             n0 + (int)cta_rank * (BN / 2));
+            continue;
+          }
           if (p.tma_a) {
             mbar_arrive_expect_tx(&full_bar[s], L::kBBytes + kABytes);
             if (p.tma_a == 2)   // 1x1 stride 1: the activations are a plain (M, C) matrix
@@ -224,9 +258,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_tf32(kTileM, BN, 0, 0);
     uint32_t it = 0, tc_ = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
+    if (!PAIR || cta_rank == 0) {   // the leader CTA issues for the pair
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
       const uint32_t buf = tc_ & 1;
       mbar_wait(&tmem_empty_bar[buf], ((tc_ >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -241,14 +276,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           const uint64_t db =
               make_smem_desc_sw128(smem_base + L::kBOff + s * L::kBBytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k)  // 8 tf32 = 32 bytes per MMA -> +2 (16 B units)
-            umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          for (int k = 0; k < kBK / 8; ++k) {  // 8 tf32 = 32 bytes per MMA -> +2 (16 B units)
+            if (PAIR) umma_tf32_pair(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_pair(&empty_bar[s], (uint16_t)3);
+          else umma_commit(&empty_bar[s]);
         }
         __syncwarp();
       }
-      if (lane == 0) umma_commit(&tmem_full_bar[buf]);
+      if (lane == 0) {
+        if (PAIR) umma_commit_pair(&tmem_full_bar[buf], (uint16_t)3);
+        else umma_commit(&tmem_full_bar[buf]);
+      }
       __syncwarp();
+    }
     }
   } else {
     // ------------------------------------------------------------- epilogue
@@ -271,8 +313,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                         (!mask_p || (reinterpret_cast<uintptr_t>(mask_p) & 15) == 0);
     constexpr int kChunks = BN / 32;          // 32-column chunks of the tile
     uint32_t tc_ = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc_) {
-      const int m0 = (tile / p.n_tiles) * kBM;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
+      const int m0 = (tile / p.n_tiles) * kTileM + (int)cta_rank * kBM;
       const int n0 = (tile % p.n_tiles) * BN;
       const uint32_t buf = tc_ & 1;
       // output element offsets of this lane's 8 rows (row = 32q + 4i + sub); the host
@@ -385,14 +427,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty_bar[buf]), 0));
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
     }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+  if (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer still works
+  if (warp == 5) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // ------------------------------------------------------------------ host ----
@@ -508,13 +557,13 @@ int make_tmap_tiled_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
 
 namespace {
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
            cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, PAIR>;
   static bool configured = false;
   if (!configured) {
-    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES>,
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::dynamic_bytes(3) <= 232448 ? L::dynamic_bytes(3)
                                                                     : L::dynamic_bytes(2)));
@@ -522,14 +571,27 @@ int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmPar
   }
   CMR_REQUIRE(L::dynamic_bytes(p.epi_groups) <= 232448);
   ConvGemmParams q = p;
-  q.m_tiles = ceil_div(p.M, kBM);
+  q.m_tiles = ceil_div(p.M, PAIR ? 2 * kBM : kBM);
   q.n_tiles = ceil_div(p.N, BN);
   const long long tiles = (long long)q.m_tiles * q.n_tiles;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  const int slots = PAIR ? sm_count() / 2 : sm_count();
+  const int grid = (int)(tiles < slots ? tiles : slots) * (PAIR ? 2 : 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::dynamic_bytes(p.epi_groups);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
-  conv_gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::dynamic_bytes(p.epi_groups), st>>>(
-      tmap, tmap_a, q);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR>, tmap, tmap_a, q);
   prof_end(st);
+  CMR_CUDA_TRY(e);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -591,12 +653,10 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
       }
     }
   }
-  CUtensorMap tmap;
-  int rc = make_tmap_2d(&tmap, w, (uint64_t)p.N, (uint64_t)p.K, (uint32_t)bn);
-  if (rc != CMR_OK) return rc;
   // The activation operand through an im2col tensor map when the geometry is a plain
   // convolution over in_c <= in_ld channels (everything but the RGB0-packed stem).
-  CUtensorMap tmap_a = tmap;
+  CUtensorMap tmap_a;
+  memset(&tmap_a, 0, sizeof(tmap_a));
   p.tma_a = 0;
   if (g_im2col_tma && c->in_c <= c->in_ld &&
       c->out_h == (c->in_h + 2 * c->pad - c->kh) / c->stride + 1 &&
@@ -619,12 +679,26 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   p.epi_groups = p.tma_a ? 3 : 2;
   const bool deep = p.K >= 1024 || !p.tma_a;
   if (bn == 256 && deep) p.epi_groups = 2;
+  // CTA pairs (tcgen05.mma.cta_group::2) for the long reductions with enough 256-row tiles
+  // to fill the 74 SM pairs
+  static int pair_ok = -1;
+  if (pair_ok < 0) {
+    const char* e = getenv("CMR_CONV_PAIR");
+    pair_ok = e ? atoi(e) : 1;
+  }
+  const bool pair = pair_ok && bn == 256 && deep && p.tma_a &&
+                    (long long)ceil_div(p.M, 2 * kBM) * ceil_div(p.N, bn) >= sm_count() / 2;
+  CUtensorMap tmap;
+  int rc = make_tmap_2d(&tmap, w, (uint64_t)p.N, (uint64_t)p.K, (uint32_t)(pair ? bn / 2 : bn));
+  if (rc != CMR_OK) return rc;
   cudaStream_t st = as_stream(stream);
   switch (bn) {
-    case 64: return launch<64, 6>(tmap, tmap_a, p, st);
-    case 128: return launch<128, 5>(tmap, tmap_a, p, st);
+    case 64: return launch<64, 6, false>(tmap, tmap_a, p, st);
+    case 128: return launch<128, 5, false>(tmap, tmap_a, p, st);
     case 256:
-      return deep ? launch<256, 4>(tmap, tmap_a, p, st) : launch<256, 3>(tmap, tmap_a, p, st);
+      if (pair) return launch<256, 6, true>(tmap, tmap_a, p, st);
+      return deep ? launch<256, 4, false>(tmap, tmap_a, p, st)
+                  : launch<256, 3, false>(tmap, tmap_a, p, st);
     default: return CMR_ERR_INVALID_ARG;
   }
 }

@@ -255,12 +255,13 @@ conv_wgrad_tc_kernel(const WgradParams p) {
 
 // ------------------------------------------------------------ TMA variant ----
 constexpr int kTmaThreads = 192;
-constexpr int kTPix = 48;   // pixels per k-block: TMA boxes of 6 KB, 3 stages of a 128 x 256 tile
+constexpr int kTPix = 48;   // pixels per k-block: TMA boxes of 6 KB
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 struct TSmem {
-  static constexpr int kPBytes = kTPix * kBM * 4;  // 16 KB
-  static constexpr int kQBytes = kTPix * BN * 4;
+  static constexpr int kQCols = PAIR ? BN / 2 : BN;  // a CTA of a pair holds half the columns
+  static constexpr int kPBytes = kTPix * kBM * 4;    // 24 KB
+  static constexpr int kQBytes = kTPix * kQCols * 4;
   static constexpr int kPOff = 0;
   static constexpr int kQOff = STAGES * kPBytes;
   static constexpr int kBarOff = kQOff + STAGES * kQBytes;
@@ -268,15 +269,16 @@ struct TSmem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
-// PAIR: launched as clusters of two CTAs along grid.x (adjacent row tiles, same column
-// tile, same pixel range).  The two CTAs read the same Q (layer input) tiles: each loads
-// half of the Q blocks and multicasts them into both shared memories, which cuts the
-// L2 -> SM traffic per CTA from P + Q to P + Q/2 (the kernel is bound by that traffic).
+// PAIR: clusters of two CTAs along grid.x (adjacent 128-row tiles, same column tile, same
+// pixel range) compute ONE 256 x BN tile with tcgen05.mma.cta_group::2: each CTA loads its
+// 128 rows of P and BN/2 columns of Q (48 KB instead of 72 KB per 48-pixel k-block and SM:
+// the single-CTA kernel is bound by operand delivery), the leader issues the MMAs, each
+// CTA's TMEM receives its 128 rows x BN columns and each CTA runs its own epilogue.
 template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(kTmaThreads)
 conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
                       const __grid_constant__ CUtensorMap tmap_q, const WgradParams p) {
-  using L = TSmem<BN, STAGES>;
+  using L = TSmem<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -289,118 +291,139 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * kBM;
-  const int j0 = blockIdx.y * BN;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
+  const int i0 = blockIdx.x * kBM;                 // this CTA's rows (pairs: 2 adjacent tiles)
+  const int j0 = blockIdx.y * BN;                  // the tile's first column
+  const int jq = j0 + (int)cta_rank * L::kQCols;   // first column this CTA loads
   const int tap = blockIdx.z / p.splits;
   const int tap_fr = tap / p.taps_w, tap_fs = tap - tap_fr * p.taps_w;
   const int kb_begin = (blockIdx.z - tap * p.splits) * p.kb_per_split;
   const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
   const int nkb = kb_end - kb_begin;  // >= 1 by construction of the grid
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap_p);
     prefetch_tensormap(&tmap_q);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], PAIR ? 2 : 1);   // the MMA issuers of both CTAs release it
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 5) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
-  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything signals them
+
+  // 32-channel blocks that hold data: blocks past the channel range would only load zeros,
+  // their copies are skipped (the epilogue never writes rows >= rows or columns >= cols)
+  auto blocks_in = [](int first, int limit, int max_blocks) {
+    const int b = (limit - first + 31) / 32;
+    return b < 0 ? 0 : (b > max_blocks ? max_blocks : b);
+  };
+  const int p_blocks = blocks_in(i0, p.rows, kBM / 32);
+  const int q_blocks = blocks_in(jq, p.cols, L::kQCols / 32);
 
   if (warp <= 4) {
     // ------------------------------------------------------------ producers
     // One thread of each of warps 0-4 issues a share of the k-block's TMA loads (a copy
     // instruction occupies its issuing thread for ~50 cycles, which would otherwise sit on
-    // the critical path of every stage); warp 4 also arms the stage's barrier with the
-    // byte count of all of them.  Warps 0-3 turn into the epilogue afterwards.
+    // the critical path of every stage); warp 4 (of the leader CTA) also arms the stage's
+    // barrier with the byte count of all of them.  Warps 0-3 turn into the epilogue
+    // afterwards.
     if (lane == 0) {
-      // column blocks past the channel range would only load zeros: their copies are
-      // skipped (the epilogue never writes rows >= rows or columns >= cols)
-      const int p_blocks = min(kBM / 32, (p.rows - i0 + 31) / 32);
-      const int q_blocks = min(BN / 32, (p.cols - j0 + 31) / 32);
       const int n_blocks = p_blocks + q_blocks;
+      // bytes of the peer CTA's boxes, which complete on the leader's barrier too
+      int all_blocks = n_blocks;
+      if (PAIR)
+        all_blocks += blocks_in(i0 + kBM, p.rows, kBM / 32) +
+                      blocks_in(j0 + L::kQCols, p.cols, L::kQCols / 32);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], phase ^ 1);
-        if (warp == 4) {
+        if (warp == 4 && cta_rank == 0) {
           if (p.probe == 1 && kb >= STAGES) {
             mbar_arrive(&full_bar[s]);
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)n_blocks * (kTPix * 128));
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)all_blocks * (kTPix * 128));
         } else if (p.probe == 1 && kb >= STAGES) {
           continue;
         }
         int img, rem, oy, ox;
-        p.div_hw.divmod((kb_begin + kb) * kTPix, img, rem);
+        const int pix0 = (kb_begin + kb) * kTPix;
+        p.div_hw.divmod(pix0, img, rem);
         p.div_w.divmod(rem, oy, ox);
         const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
         const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
         const int ph = oy * p.p.stride + p.p.off_y, pw = ox * p.p.stride + p.p.off_x;
         const int qh = oy * p.q.stride + p.q.off_y, qw = ox * p.q.stride + p.q.off_x;
-        const int pix0 = (kb_begin + kb) * kTPix;
+        const uint32_t bar_pair = PAIR ? mapa_cluster(smem_u32(&full_bar[s]), 0) : 0;
         for (int b = warp; b < n_blocks; b += 5) {
-          if (b < p_blocks) {
-            if (p.p_tiled)
-              tma_load_2d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s], p.p.c0 + i0 + b * 32,
-                          pix0);
-            else
-              tma_load_im2col_4d(pa + b * (kTPix * 128), &tmap_p, &full_bar[s],
-                                 p.p.c0 + i0 + b * 32, pw, ph, img, 0, 0);
-          } else if (!PAIR) {
-            if (p.q_tiled)
-              tma_load_2d(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
-                          p.q.c0 + j0 + (b - p_blocks) * 32, pix0);
-            else
-              tma_load_im2col_4d(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
-                                 p.q.c0 + j0 + (b - p_blocks) * 32, qw, qh, img, tap_fs,
-                                 tap_fr);
-          } else if ((uint32_t)((b - p_blocks) & 1) == cta_rank) {
-            tma_load_im2col_4d_mcast(qa + (b - p_blocks) * (kTPix * 128), &tmap_q, &full_bar[s],
-                                     p.q.c0 + j0 + (b - p_blocks) * 32, qw, qh, img, tap_fs,
-                                     tap_fr, (uint16_t)3);
+          const bool is_p = b < p_blocks;
+          const int bb = is_p ? b : b - p_blocks;
+          const uint32_t dst = (is_p ? pa : qa) + bb * (kTPix * 128);
+          const CUtensorMap* map = is_p ? &tmap_p : &tmap_q;
+          const int c = is_p ? p.p.c0 + i0 + bb * 32 : p.q.c0 + jq + bb * 32;
+          const bool tiled = is_p ? p.p_tiled != 0 : p.q_tiled != 0;
+          if (PAIR) {
+            if (tiled) tma_load_2d_pair(dst, map, bar_pair, c, pix0);
+            else if (is_p) tma_load_im2col_4d_pair(dst, map, bar_pair, c, pw, ph, img, 0, 0);
+            else tma_load_im2col_4d_pair(dst, map, bar_pair, c, qw, qh, img, tap_fs, tap_fr);
+          } else {
+            if (tiled) tma_load_2d(dst, map, &full_bar[s], c, pix0);
+            else if (is_p) tma_load_im2col_4d(dst, map, &full_bar[s], c, pw, ph, img, 0, 0);
+            else tma_load_im2col_4d(dst, map, &full_bar[s], c, qw, qh, img, tap_fs, tap_fr);
           }
         }
       }
     }
     __syncwarp();
   }
-  if (warp == 4) {
-    // nothing else
-  } else if (warp == 5) {
+  if (warp == 5) {
     // ---------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = make_idesc_tf32(kBM, BN, 1, 1);  // both operands MN-major
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t phase = (kb / STAGES) & 1;
-      mbar_wait(&full_bar[s], phase);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
-        const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
+    // both operands MN-major; a pair's MMA spans 256 rows (128 per CTA)
+    constexpr uint32_t idesc = make_idesc_tf32(PAIR ? 2 * kBM : kBM, BN, 1, 1);
+    if (!PAIR || cta_rank == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t pa = smem_base + L::kPOff + s * L::kPBytes;
+          const uint32_t qa = smem_base + L::kQOff + s * L::kQBytes;
 #pragma unroll
-        for (int k = 0; k < kTPix / 8; ++k) {
-          const uint64_t da = make_smem_desc(pa + k * 1024, kTPix * 128, 512, 1);
-          const uint64_t db = make_smem_desc(qa + k * 1024, kTPix * 128, 512, 1);
-          if (p.probe != 2 || kb == 0) umma_tf32(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kTPix / 8; ++k) {
+            // 8 pixels = two 4-row (512 B) swizzle atoms per 32-channel block (stride byte
+            // offset); blocks are kTPix * 128 bytes apart (leading byte offset)
+            const uint64_t da = make_smem_desc(pa + k * 1024, kTPix * 128, 512, 1);
+            const uint64_t db = make_smem_desc(qa + k * 1024, kTPix * 128, 512, 1);
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            if (p.probe == 2 && kb != 0) continue;
+            if (PAIR) umma_tf32_pair(tmem_base, da, db, idesc, accum);
+            else umma_tf32(tmem_base, da, db, idesc, accum);
+          }
+          if (PAIR) umma_commit_pair(&empty_bar[s], (uint16_t)3);
+          else umma_commit(&empty_bar[s]);
         }
-        if (PAIR) umma_commit_mcast(&empty_bar[s], (uint16_t)3);
-        else umma_commit(&empty_bar[s]);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        if (PAIR) umma_commit_pair(tmem_full_bar, (uint16_t)3);
+        else umma_commit(tmem_full_bar);
       }
       __syncwarp();
     }
-    if (lane == 0) umma_commit(tmem_full_bar);
-    __syncwarp();
-  } else {
+  } else if (warp < 4) {
     // ------------------------------------------------------------ epilogue
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -439,8 +462,11 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // no CTA leaves while its peer may still write to it
-  if (warp == 5) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  if (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer still works
+  if (warp == 5) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
+  }
 }
 
 // Round-up magic number for 31-bit dividends: q = (n * mul) >> (32 + shr).
@@ -479,7 +505,7 @@ int launch_wgrad(const WgradParams& p, int splits, int taps, cudaStream_t st) {
 template <int BN, int STAGES, bool PAIR>
 int launch_wgrad_tma(const CUtensorMap& tp, const CUtensorMap& tq, const WgradParams& p,
                      int splits, int taps, cudaStream_t st) {
-  using L = TSmem<BN, STAGES>;
+  using L = TSmem<BN, STAGES, PAIR>;
   static bool configured = false;
   if (!configured) {
     CMR_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_tma_kernel<BN, STAGES, PAIR>,
@@ -611,18 +637,18 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
       splits = ceil_div(p.num_kb, p.kb_per_split);
       p.splits = splits;
       p.taps_w = taps_w;
-      // pairs of adjacent row tiles share their Q tiles by multicast
+      // CTA pairs (tcgen05.mma.cta_group::2) over two adjacent row tiles
       static int pair_ok = -1;
       if (pair_ok < 0) {
         const char* e = getenv("CMR_WGRAD_PAIR");
-        pair_ok = e ? atoi(e) : 0;   // measured: no gain (the copy engine's row rate binds)
+        pair_ok = e ? atoi(e) : 1;
       }
       const bool pair = pair_ok && (ceil_div(p.rows, kBM) % 2 == 0);
       if (bn == 256)
-        return pair ? launch_wgrad_tma<256, 3, true>(tp, tq, p, splits, taps, st)
+        return pair ? launch_wgrad_tma<256, 4, true>(tp, tq, p, splits, taps, st)
                     : launch_wgrad_tma<256, 3, false>(tp, tq, p, splits, taps, st);
       if (bn == 128)
-        return pair ? launch_wgrad_tma<128, 4, true>(tp, tq, p, splits, taps, st)
+        return pair ? launch_wgrad_tma<128, 5, true>(tp, tq, p, splits, taps, st)
                     : launch_wgrad_tma<128, 4, false>(tp, tq, p, splits, taps, st);
       return launch_wgrad_tma<64, 5, false>(tp, tq, p, splits, taps, st);
     }

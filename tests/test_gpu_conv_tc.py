@@ -81,6 +81,8 @@ CASES = [
     (5, 7, 7, 96, 64, 3, 1, 1, 64),         # 128-row tiles spanning 3 images, K = 27 k-blocks
     (2, 10, 9, 32, 64, 3, 2, 1, 64),        # 3x3 stride 2 pad 1
     (1, 5, 6, 64, 64, 5, 1, 2, 64),         # 5x5 pad 2
+    (8, 48, 50, 1024, 256, 1, 1, 0, 256),   # CTA-pair path (cta_group::2): 75 x 1 tiles of 256 rows
+    (4, 70, 70, 128, 512, 3, 1, 1, 256),    # CTA-pair path, 3x3, ragged last tile, 2 column tiles
 ]
 
 
