@@ -301,9 +301,26 @@ __device__ __forceinline__ Lin lin_coeff(int d, int size, int ms, bool clamp_wei
   return l;
 }
 
+// Mask pixel readers: one value per element (uint8 / int32) or one bit per pixel
+// (rows of ceil(W/8) bytes, bit x & 7 of byte x >> 3 = pixel x: numpy.packbits(...,
+// bitorder='little') along the width).
 template <typename T>
+struct MaskElems {
+  const T* base;
+  size_t row_pitch;
+  __device__ __forceinline__ int at(int y, int x) const { return (int)base[(size_t)y * row_pitch + x]; }
+};
+struct MaskBits {
+  const uint8_t* base;
+  size_t row_pitch;
+  __device__ __forceinline__ int at(int y, int x) const {
+    return (base[(size_t)y * row_pitch + (x >> 3)] >> (x & 7)) & 1;
+  }
+};
+
+template <typename Reader, typename T>
 __global__ void __launch_bounds__(256)
-mask_targets_kernel(const T* __restrict__ masks, int G, int H, int W,
+mask_targets_kernel(const T* __restrict__ masks, size_t row_pitch, int G, int H, int W,
                     const float4* __restrict__ sample_roi, const int* __restrict__ gt_assign,
                     const int* __restrict__ n_pos, int n_sample, int ms,
                     int* __restrict__ gt_mask) {
@@ -324,15 +341,17 @@ mask_targets_kernel(const T* __restrict__ masks, int G, int H, int W,
     for (int t = threadIdx.x; t < ms * ms; t += blockDim.x) out[t] = 0;
     return;
   }
-  const T* m = masks + ((size_t)b * G + g) * H * W + (size_t)y0 * W + x0;
+  Reader m;
+  m.base = masks + ((size_t)b * G + g) * H * row_pitch;
+  m.row_pitch = row_pitch;
   for (int t = threadIdx.x; t < ms * ms; t += blockDim.x) {
     const int py = t / ms, px = t - py * ms;
     const Lin ly = lin_coeff(py, h, ms, false), lx = lin_coeff(px, w, ms, true);
     int v[4];
-    v[0] = (int)m[(size_t)ly.i0 * W + lx.i0];
-    v[1] = (int)m[(size_t)ly.i0 * W + lx.i1];
-    v[2] = (int)m[(size_t)ly.i1 * W + lx.i0];
-    v[3] = (int)m[(size_t)ly.i1 * W + lx.i1];
+    v[0] = m.at(y0 + ly.i0, x0 + lx.i0);
+    v[1] = m.at(y0 + ly.i0, x0 + lx.i1);
+    v[2] = m.at(y0 + ly.i1, x0 + lx.i0);
+    v[3] = m.at(y0 + ly.i1, x0 + lx.i1);
     int best_v = 0;
     float best_s = -1.f;
 #pragma unroll
@@ -471,19 +490,23 @@ extern "C" int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, i
                                 int mask_size, int32_t* gt_mask, void* stream) {
   CMR_REQUIRE(masks && sample_roi && gt_assign && n_pos && gt_mask);
   CMR_REQUIRE(B > 0 && max_bbox > 0 && H > 0 && W > 0 && n_sample > 0 && mask_size > 0);
-  CMR_REQUIRE(mask_elem_bytes == 1 || mask_elem_bytes == 4);
+  CMR_REQUIRE(mask_elem_bytes == 0 || mask_elem_bytes == 1 || mask_elem_bytes == 4);
   CMR_REQUIRE((reinterpret_cast<uintptr_t>(sample_roi) & 15) == 0);
   cudaStream_t st = as_stream(stream);
   const float4* r4 = reinterpret_cast<const float4*>(sample_roi);
   dim3 grid(n_sample, B);
-  if (mask_elem_bytes == 1)
-    mask_targets_kernel<uint8_t><<<grid, 256, 0, st>>>(
-        reinterpret_cast<const uint8_t*>(masks), max_bbox, H, W, r4, gt_assign, n_pos, n_sample,
-        mask_size, gt_mask);
+  if (mask_elem_bytes == 0)
+    mask_targets_kernel<MaskBits, uint8_t><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(masks), (size_t)((W + 7) / 8), max_bbox, H, W, r4,
+        gt_assign, n_pos, n_sample, mask_size, gt_mask);
+  else if (mask_elem_bytes == 1)
+    mask_targets_kernel<MaskElems<uint8_t>, uint8_t><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const uint8_t*>(masks), (size_t)W, max_bbox, H, W, r4, gt_assign, n_pos,
+        n_sample, mask_size, gt_mask);
   else
-    mask_targets_kernel<int32_t><<<grid, 256, 0, st>>>(
-        reinterpret_cast<const int32_t*>(masks), max_bbox, H, W, r4, gt_assign, n_pos, n_sample,
-        mask_size, gt_mask);
+    mask_targets_kernel<MaskElems<int32_t>, int32_t><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const int32_t*>(masks), (size_t)W, max_bbox, H, W, r4, gt_assign, n_pos,
+        n_sample, mask_size, gt_mask);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -9,7 +9,7 @@ flat gradient buffer.
 Targets.  By default anchors and proposals are labelled / sampled on the device
 (models/utils/device_targets.py, csrc/targets.cu).  Mask targets are rasterised on the
 device as well when ``masks`` is a torch tensor ((B,G,H,W) uint8 / int32, CUDA or
-pinned host) -- the step then has no host synchronisation at all and can be captured
+pinned host) or a bit-packed ``models.utils.PackedMasks`` -- the step then has no host synchronisation at all and can be captured
 in a CUDA graph (optimizers.GraphedUpdater); with the reference's host NumPy masks they
 are rasterised on the host (cv2, as in the reference), overlapped with the head's
 forward pass.  Passing the host ``AnchorTargetCreator`` / ``ProposalTargetCreator``
@@ -25,6 +25,7 @@ from .mask_rcnn import as_device_f32
 from .utils import DeviceAnchorTargetCreator
 from .utils import DeviceProposalTargetCreator
 from .utils import GroundTruth
+from .utils import PackedMasks
 
 LOSS_NAMES = ('rpn_loc_loss', 'rpn_cls_loss', 'roi_loc_loss', 'roi_cls_loss', 'roi_mask_loss')
 
@@ -112,11 +113,12 @@ class MaskRCNNTrainChain(object):
                 gt = GroundTruth(bboxes, labels, dev)
                 self.h2d_bytes += gt.nbytes
             masks_dev = None
-            if isinstance(masks, torch.Tensor):
+            if isinstance(masks, (torch.Tensor, PackedMasks)):
                 if not dev_prop:
                     raise TypeError('tensor masks need the device proposal target creator')
                 if not masks.is_cuda:
-                    self.h2d_bytes += masks.numel() * masks.element_size()
+                    self.h2d_bytes += masks.numel() * masks.element_size() \
+                        if isinstance(masks, torch.Tensor) else masks.nbytes
                 masks_dev = masks.to(dev, non_blocking=True)
             seed = (self._seed << 20) + 2 * self._calls
             # ---- RPN targets

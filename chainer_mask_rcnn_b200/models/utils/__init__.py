@@ -7,3 +7,4 @@ from .proposal_target_creator import ProposalTargetCreator
 from .device_targets import DeviceAnchorTargetCreator
 from .device_targets import DeviceProposalTargetCreator
 from .device_targets import GroundTruth
+from .device_targets import PackedMasks

@@ -116,7 +116,8 @@ class GraphedUpdater(object):
 
     ``updater(imgs, bboxes, labels, masks, scales)`` -> :class:`Loss`-like object
     (``.array`` device scalar, ``.item()``).  imgs (B,3,H,W) float32 and masks
-    (B,G,H,W) uint8 torch tensors (CUDA, or pinned host memory for asynchronous copies);
+    (B,G,H,W) uint8 torch tensors or bit-packed ``models.utils.PackedMasks`` (CUDA, or
+    pinned host memory for asynchronous copies);
     bboxes / labels: lists of per-image NumPy arrays.
 
     The first call for a key runs eagerly (it is also the warm-up that sizes every
@@ -138,9 +139,15 @@ class GraphedUpdater(object):
     class _State(object):
         pass
 
+    @staticmethod
+    def _mask_tensor(masks):
+        return masks.data if hasattr(masks, 'width') else masks
+
     def _key(self, imgs, masks, scales):
         o = self.optimizer
-        return (tuple(imgs.shape), tuple(masks.shape), str(masks.dtype),
+        packed = hasattr(masks, 'width')
+        masks = self._mask_tensor(masks)
+        return (tuple(imgs.shape), tuple(masks.shape), str(masks.dtype), packed,
                 tuple(float(s) for s in scales), float(o.lr), float(o.momentum),
                 float(o.weight_decay), o.comm.size if o.comm is not None else 1)
 
@@ -148,10 +155,12 @@ class GraphedUpdater(object):
         dev = self.optimizer.ctx.device
         st = self._State()
         B = imgs.shape[0]
-        G = max(self.max_boxes, masks.shape[1], max(len(b) for b in bboxes))
+        mt = self._mask_tensor(masks)
+        G = max(self.max_boxes, mt.shape[1], max(len(b) for b in bboxes))
         st.imgs = torch.empty(tuple(imgs.shape), dtype=torch.float32, device=dev)
         # same shape as the caller's masks: staging them is one contiguous copy
-        st.masks = torch.zeros(tuple(masks.shape), dtype=masks.dtype, device=dev)
+        st.masks = torch.zeros(tuple(mt.shape), dtype=mt.dtype, device=dev)
+        st.masks_arg = type(masks)(st.masks, masks.width) if hasattr(masks, 'width') else st.masks
         st.gt = self._GroundTruth(bboxes, labels, dev, capacity=G)
         st.seed_word = torch.zeros((1,), dtype=torch.int64, device=dev)
         st.graph = None
@@ -161,7 +170,7 @@ class GraphedUpdater(object):
 
     def _stage(self, st, imgs, bboxes, labels, masks):
         self.h2d_bytes = st.gt.nbytes
-        for dst, src in ((st.imgs, imgs), (st.masks, masks)):
+        for dst, src in ((st.imgs, imgs), (st.masks, self._mask_tensor(masks))):
             if not src.is_cuda:
                 self.h2d_bytes += src.numel() * src.element_size()
             dst.copy_(src, non_blocking=True)
@@ -174,7 +183,7 @@ class GraphedUpdater(object):
         chain._calls = 0        # fixed host seed: the draws advance through seed_word only
         try:
             o.ctx.grads.zero_()
-            loss = chain(st.imgs, st.gt, None, st.masks, scales)
+            loss = chain(st.imgs, st.gt, None, st.masks_arg, scales)
             loss.backward()
             if o.comm is None or o.comm.size == 1:
                 o.apply_update()
@@ -185,9 +194,10 @@ class GraphedUpdater(object):
 
     def __call__(self, imgs, bboxes, labels, masks, scales):
         scales = [float(s) for s in (scales.tolist() if hasattr(scales, 'tolist') else scales)]
-        if not (isinstance(imgs, torch.Tensor) and isinstance(masks, torch.Tensor)):
-            raise TypeError('GraphedUpdater needs torch tensors for imgs and masks (CUDA or '
-                            'pinned host memory)')
+        if not (isinstance(imgs, torch.Tensor) and
+                isinstance(self._mask_tensor(masks), torch.Tensor)):
+            raise TypeError('GraphedUpdater needs torch tensors (or PackedMasks) for imgs and '
+                            'masks (CUDA or pinned host memory)')
         o = self.optimizer
         key = self._key(imgs, masks, scales)
         st = self._states.get(key)

@@ -291,8 +291,10 @@ int cmr_proposal_targets(const float* rois, const int32_t* n_roi, int max_roi,
  * to integers, crop instance mask gt_assign[b,j], and take argmax over the one-hot
  * planes of cv2.resize(INTER_LINEAR, float32) to (mask_size, mask_size); all other
  * rows are filled with -1.  masks: (B, max_bbox, H, W) device array of uint8
- * (mask_elem_bytes == 1) or int32 (== 4) labels >= 0.  gt_mask: (B, n_sample,
- * mask_size, mask_size) int32.  An empty crop yields zeros. */
+ * (mask_elem_bytes == 1) or int32 (== 4) labels >= 0, or (mask_elem_bytes == 0) binary
+ * masks packed one bit per pixel: (B, max_bbox, H, ceil(W/8)) bytes, pixel x = bit x & 7
+ * of byte x >> 3 (numpy.packbits(..., axis=-1, bitorder='little')).  gt_mask: (B,
+ * n_sample, mask_size, mask_size) int32.  An empty crop yields zeros. */
 int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, int max_bbox,
                      int H, int W, const float* sample_roi, const int32_t* gt_assign,
                      const int32_t* n_pos, int n_sample, int mask_size,

@@ -146,6 +146,15 @@ def test_device_mask_targets_bit_exact(dtype):
     got = got.cpu().numpy()
     np.testing.assert_array_equal(got, want)
     assert (got[1, npos[1]:] == -1).all() and set(np.unique(got)) <= {-1, 0, 1, 2, 3}
+    if dtype == torch.uint8:
+        # the same binary masks packed one bit per pixel
+        binary = (np.stack(masks) > 0).astype(np.uint8)
+        want_b = omt.mask_targets(sroi, asg, npos, list(binary), 14)
+        packed = mu.PackedMasks.from_numpy(binary).to('cuda')
+        assert packed.data.shape == (2, G, H, (W + 7) // 8)
+        got_b = ptc.mask_targets_device(torch.from_numpy(sroi).cuda(), torch.from_numpy(asg).cuda(),
+                                        torch.from_numpy(npos).cuda(), packed).cpu().numpy()
+        np.testing.assert_array_equal(got_b, want_b)
 
 
 def test_seed_dev_advances_the_draw():
