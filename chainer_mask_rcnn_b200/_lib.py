@@ -56,6 +56,7 @@ _SIGNATURES = {
     'cmr_col_sum': (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]),
     'cmr_prep_dgrad_weight': (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
                                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    'cmr_prep_dgrad_weight_batch': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'cmr_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
                                  c_float, c_float, c_void_p]),
     'cmr_rpn_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_longlong,
@@ -94,6 +95,14 @@ class ConvDesc(ctypes.Structure):
         'batch', 'in_h', 'in_w', 'in_c', 'in_ld', 'out_h', 'out_w', 'kh', 'kw', 'stride',
         'pad', 'n', 'd_h', 'd_w', 'd_ld', 'd_stride', 'd_oy', 'd_ox', 'relu', 'round_tf32',
         'tile_n')]
+
+
+class PrepDesc(ctypes.Structure):
+    """struct cmr_prep_desc (include/cmr_b200.h)."""
+    _fields_ = [('w', c_void_p), ('scale', c_void_p), ('out', c_void_p),
+                ('stride_o', c_longlong), ('stride_t', c_longlong)] + \
+               [(n, c_int) for n in ('O', 'T', 'I', 'flip', 'ld_out', 'col0', 'tile_begin',
+                                     'reserved')]
 
 
 class WgradDesc(ctypes.Structure):

@@ -170,6 +170,46 @@ prep_dgrad_weight_kernel(const float* __restrict__ w, int O, int T, int I, long 
   }
 }
 
+// All layers' re-layouts in one launch: CTA -> (descriptor, 32x32 tile, tap).
+__global__ void __launch_bounds__(256)
+prep_dgrad_weight_batch_kernel(const cmr_prep_desc* __restrict__ descs, int n_desc) {
+  __shared__ float tile[32][33];
+  __shared__ int which;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_desc - 1;             // last descriptor with tile_begin <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (descs[mid].tile_begin <= (int)blockIdx.x) lo = mid;
+      else hi = mid - 1;
+    }
+    which = lo;
+  }
+  __syncthreads();
+  const cmr_prep_desc d = descs[which];
+  int local = blockIdx.x - d.tile_begin;
+  const int ti = (d.I + 31) / 32, to_ = (d.O + 31) / 32;
+  const int t = local / (ti * to_);
+  local -= t * ti * to_;
+  const int i0 = (local % ti) * 32, o0 = (local / ti) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int o = o0 + r, i = i0 + tx;
+    float v = 0.f;
+    if (o < d.O && i < d.I) {
+      v = __ldg(d.w + o * d.stride_o + t * d.stride_t + i);
+      if (d.scale) v *= __ldg(d.scale + o);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  const int tt = d.flip ? d.T - 1 - t : t;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = i0 + r, o = o0 + tx;
+    if (i < d.I && o < d.O)
+      d.out[((size_t)i * d.T + tt) * d.ld_out + d.col0 + o] = tc::round_tf32(tile[tx][r]);
+  }
+}
+
 // ------------------------------------------------------------------- SGD ---
 // chainer.optimizers.MomentumSGD + optimizer_hooks.WeightDecay
 // (examples/train_common.py:176-180):  g' = grad_scale*g + wd*p;
@@ -277,6 +317,14 @@ extern "C" int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long l
   CMR_REQUIRE(grid.y < 65536);
   prep_dgrad_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(w, O, T, I, stride_o, stride_t,
                                                                 scale, flip, out, ld_out, col0);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+extern "C" int cmr_prep_dgrad_weight_batch(const cmr_prep_desc* descs_dev, int n_desc,
+                                           int total_tiles, void* stream) {
+  CMR_REQUIRE(descs_dev && n_desc > 0 && total_tiles > 0);
+  prep_dgrad_weight_batch_kernel<<<total_tiles, 256, 0, as_stream(stream)>>>(descs_dev, n_desc);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

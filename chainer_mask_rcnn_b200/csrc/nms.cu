@@ -26,8 +26,17 @@ __device__ __forceinline__ bool iou_ge(const float4 a, float area_a, const float
   const float br_y = fminf(a.z, b.z), br_x = fminf(a.w, b.w);
   float inter = __fmul_rn(__fsub_rn(br_y, tl_y), __fsub_rn(br_x, tl_x));
   if (!(tl_y < br_y && tl_x < br_x)) inter = __fmul_rn(inter, 0.0f);
-  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-  return iou >= thresh;
+  const float denom = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // The decision is that of the correctly rounded quotient.  An approximate reciprocal
+  // (one MUFU, relative error < 2^-21) settles every pair whose quotient is not within
+  // 2^-20 of the threshold; only those few take the IEEE division.  (0/0 and other
+  // non-finite cases fail both quick tests and are decided by the division as before.)
+  float rcp;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(denom));
+  const float q = inter * rcp;
+  if (q > thresh * 1.000001f) return true;
+  if (q < thresh * 0.999999f) return false;
+  return __fdiv_rn(inter, denom) >= thresh;
 }
 
 // mask[i][cb] bit k  <=>  j = 64*cb + k > i  and  IoU(i, j) >= thresh  (and, when class
@@ -68,11 +77,12 @@ nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ labels
   }
 }
 
-// One CTA per image resolves the bitmask sequentially in 64-box chunks.  Per chunk the
-// critical path is: thread 0 resolves the diagonal 64x64 block from registers, then 64
-// threads OR word cb+1 of the kept rows into the running "removed" mask (the only word
-// the next chunk needs).  The remaining words (>= cb+2) of those rows are ORed in by
-// warps 1..7 one iteration later, concurrently with thread 0 resolving the next chunk.
+// One CTA per image resolves the bitmask sequentially in 64-box chunks.  The critical
+// path per chunk is thread 0 resolving the diagonal 64x64 block from registers; while it
+// walks the 64 boxes it also ORs word cb+1 of every kept row (prefetched speculatively
+// for all 64 rows) into the running "removed" mask, which is all the next chunk needs.
+// The remaining words (>= cb+2) of the kept rows are ORed in by warps 1..7 one iteration
+// later, concurrently with thread 0 resolving the next chunk.
 constexpr int kSweepThreads = 256;
 constexpr int kSweepRestWarps = kSweepThreads / 32 - 1;
 
@@ -81,7 +91,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
                  int n_max, int nb_stride, int limit, int32_t* __restrict__ keep,
                  int32_t* __restrict__ n_keep, int keep_stride) {
   extern __shared__ unsigned long long remv[];  // nb_stride words
-  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long diag[64], nextw[64];
   __shared__ int kept_list[2][64];
   __shared__ int kept_n[2], count_s, done_s;
   const int img = blockIdx.x;
@@ -96,22 +106,29 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
     done_s = 0;
     kept_n[0] = kept_n[1] = 0;
   }
-  unsigned long long next_diag = 0ull;
-  if (t < 64 && t < n) next_diag = mask[(size_t)t * nb_stride + 0];
+  // thread t < 64 fetches, for row cb*64 + t, the diagonal word (cb) and the next one
+  unsigned long long next_diag = 0ull, next_next = 0ull;
+  if (t < 64 && t < n) {
+    next_diag = mask[(size_t)t * nb_stride + 0];
+    if (nb > 1) next_next = mask[(size_t)t * nb_stride + 1];
+  }
   __syncthreads();
   for (int cb = 0; cb < nb; ++cb) {
     const int cur = cb & 1, prev = cur ^ 1;
     if (t < 64) {
       diag[t] = next_diag;
-      const int i = (cb + 1) * 64 + t;  // prefetch the next diagonal block
-      next_diag = (cb + 1 < nb && i < n) ? mask[(size_t)i * nb_stride + cb + 1] : 0ull;
+      nextw[t] = next_next;
+      const int i = (cb + 1) * 64 + t;  // prefetch the next chunk's two words
+      const bool ok = cb + 1 < nb && i < n;
+      next_diag = ok ? mask[(size_t)i * nb_stride + cb + 1] : 0ull;
+      next_next = (ok && cb + 2 < nb) ? mask[(size_t)i * nb_stride + cb + 2] : 0ull;
     }
     __syncthreads();
     if (t == 0) {
       unsigned long long d[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) d[j] = diag[j];
-      unsigned long long r = remv[cb];
+      unsigned long long r = remv[cb], rn = 0ull;
       int cnt = count_s, nk = 0;
       const int lim = min(64, n - cb * 64);
       bool done = false;
@@ -121,9 +138,11 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
           keep[cnt++] = cb * 64 + j;
           kept_list[cur][nk++] = j;
           r |= d[j];
+          rn |= nextw[j];
           if (limit > 0 && cnt >= limit) done = true;
         }
       }
+      if (rn && cb + 1 < nb) atomicOr(&remv[cb + 1], rn);
       kept_n[cur] = nk;
       count_s = cnt;
       if (done) done_s = 1;
@@ -148,11 +167,6 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
     }
     __syncthreads();
     if (done_s) break;
-    if (t < kept_n[cur] && cb + 1 < nb) {
-      const unsigned long long v =
-          mask[(size_t)(cb * 64 + kept_list[cur][t]) * nb_stride + cb + 1];
-      if (v) atomicOr(&remv[cb + 1], v);
-    }
   }
   if (t == 0) n_keep[img] = count_s;
 }

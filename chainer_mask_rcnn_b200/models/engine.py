@@ -74,10 +74,47 @@ def column_sums(g, c0, n, out):
     return out
 
 
+_prep_recorder = None   # list collecting descriptors while a batch table is being built
+
+
 def prep_dgrad_weight(w, O, T, I, stride_o, stride_t, scale, flip, out, ld_out=None, col0=0):
+    ld_out = O if ld_out is None else ld_out
+    if _prep_recorder is not None:
+        _prep_recorder.append((w, scale, out, stride_o, stride_t, O, T, I, int(flip), ld_out, col0))
+        return out
     _lib.call('cmr_prep_dgrad_weight', _p(w), O, T, I, stride_o, stride_t, _p(scale), int(flip),
-              _p(out), O if ld_out is None else ld_out, col0, stream())
+              _p(out), ld_out, col0, stream())
     return out
+
+
+class PrepTable(object):
+    """Every layer's data-gradient filter re-layout as one launch
+    (cmr_prep_dgrad_weight_batch).  Built once: the descriptors point into the flat
+    parameter buffers and the layers' persistent w_dgrad banks."""
+
+    def __init__(self, layers, device):
+        global _prep_recorder
+        _prep_recorder = []
+        try:
+            for l in layers:
+                l.prep_backward()
+            recs = _prep_recorder
+        finally:
+            _prep_recorder = None
+        self.keep = recs                       # keeps the tensors alive
+        arr = (_lib.PrepDesc * max(len(recs), 1))()
+        tiles = 0
+        for k, (w, scale, out, so, st, O, T, I, flip, ld_out, col0) in enumerate(recs):
+            arr[k] = _lib.PrepDesc(w.data_ptr(), scale.data_ptr() if scale is not None else None,
+                                   out.data_ptr(), so, st, O, T, I, flip, ld_out, col0, tiles, 0)
+            tiles += ((I + 31) // 32) * ((O + 31) // 32) * T
+        self.n, self.tiles = len(recs), tiles
+        raw = bytes(arr)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+    def run(self):
+        if self.n:
+            _lib.call('cmr_prep_dgrad_weight_batch', _p(self.table), self.n, self.tiles, stream())
 
 
 def max_pool(x, k, stride, pad, cover_all=True):

@@ -35,6 +35,7 @@ class Context(object):
         self._train_dirty = True
         self._frozen_dirty = True
         self._dgrad_dirty = True
+        self._prep_table = None
 
     # -- construction -------------------------------------------------------
     def add_param(self, name, shape, kind, ref_shape, trainable):
@@ -83,8 +84,9 @@ class Context(object):
             E.round_tf32(self.train.data, self.rounded)
             self._train_dirty = False
         if backward and self._dgrad_dirty:
-            for l in self.layers:
-                l.prep_backward()
+            if self._prep_table is None:
+                self._prep_table = E.PrepTable(self.layers, self.device)
+            self._prep_table.run()
             self._dgrad_dirty = False
 
     # -- reference-layout import / export (Chainer npz naming) ----------------

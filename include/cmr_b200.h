@@ -215,6 +215,21 @@ int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, float* out,
 int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long long stride_o,
                           long long stride_t, const float* scale, int flip,
                           float* out, int ld_out, int col0, void* stream);
+/* The same re-layout for many layers in ONE launch.  descs_dev: DEVICE array of n_desc
+ * descriptors whose tile_begin fields are the running sum of
+ * ceil(I/32) * ceil(O/32) * T over the preceding descriptors (first = 0);
+ * total_tiles = that sum over all of them. */
+typedef struct cmr_prep_desc {
+  const float* w;
+  const float* scale;   /* may be NULL */
+  float* out;
+  long long stride_o, stride_t;
+  int O, T, I, flip, ld_out, col0;
+  int tile_begin;
+  int reserved;
+} cmr_prep_desc;
+int cmr_prep_dgrad_weight_batch(const cmr_prep_desc* descs_dev, int n_desc,
+                                int total_tiles, void* stream);
 /* MomentumSGD + WeightDecay (examples/train_common.py:176-180) on a flat buffer:
  * g' = grad_scale*g + wd*p;  v = momentum*v - lr*g';  p += v.  n % 4 == 0. */
 int cmr_sgd_momentum(float* param, const float* grad, float* velocity, size_t n,
