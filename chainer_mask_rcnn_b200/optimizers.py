@@ -132,6 +132,8 @@ class GraphedUpdater(object):
         self.lossfun = lossfun
         self.max_boxes = max_boxes
         self._states = {}
+        self._copy_stream = None
+        self._prefetched = None
         self.launches_per_replay = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -192,18 +194,20 @@ class GraphedUpdater(object):
             chain.seed_dev = None
         return loss.array
 
-    def __call__(self, imgs, bboxes, labels, masks, scales):
+    def _lookup(self, imgs, bboxes, labels, masks, scales):
         scales = [float(s) for s in (scales.tolist() if hasattr(scales, 'tolist') else scales)]
         if not (isinstance(imgs, torch.Tensor) and
                 isinstance(self._mask_tensor(masks), torch.Tensor)):
             raise TypeError('GraphedUpdater needs torch tensors (or PackedMasks) for imgs and '
                             'masks (CUDA or pinned host memory)')
-        o = self.optimizer
         key = self._key(imgs, masks, scales)
         st = self._states.get(key)
         if st is None:
             st = self._states[key] = self._new_state(imgs, bboxes, labels, masks)
-        self._stage(st, imgs, bboxes, labels, masks)
+        return st, scales
+
+    def _run(self, st, scales):
+        o = self.optimizer
         lib = _lib.load()
         if st.calls == 0 or not self.use_graph:
             loss = self._step(st, scales)                       # eager: warm-up + real step
@@ -225,6 +229,52 @@ class GraphedUpdater(object):
         o.t += 1
         self.d2h_bytes = 0
         return _GraphedLoss(loss, self)
+
+    def __call__(self, imgs, bboxes, labels, masks, scales):
+        st, scales = self._lookup(imgs, bboxes, labels, masks, scales)
+        self._stage(st, imgs, bboxes, labels, masks)
+        return self._run(st, scales)
+
+    # -- input pipelining: copy iteration i+1's inputs while iteration i computes --
+    def prefetch(self, imgs, bboxes, labels, masks, scales):
+        """Start the host -> device copies of the NEXT iteration's inputs on a side stream
+        (into staging buffers), so that they overlap the iteration that is running;
+        ``step()`` then moves them into the graph's input buffers with device-to-device
+        copies (tens of microseconds) and runs the iteration."""
+        st, scales = self._lookup(imgs, bboxes, labels, masks, scales)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        if getattr(st, 'imgs_s', None) is None:
+            st.imgs_s = torch.empty_like(st.imgs)
+            st.masks_s = torch.empty_like(st.masks)
+            st.gt_s = self._GroundTruth(bboxes, labels, st.imgs.device, capacity=st.gt.G)
+            st.staging_free = torch.cuda.Event()
+            st.staging_free.record()
+            st.staged = torch.cuda.Event()
+        cs = self._copy_stream
+        cs.wait_event(st.staging_free)          # the previous step() has drained the staging
+        self.h2d_bytes = st.gt.nbytes
+        with torch.cuda.stream(cs):
+            for dst, src in ((st.imgs_s, imgs), (st.masks_s, self._mask_tensor(masks))):
+                if not src.is_cuda:
+                    self.h2d_bytes += src.numel() * src.element_size()
+                dst.copy_(src, non_blocking=True)
+            st.gt_s.fill_(bboxes, labels)
+            st.staged.record(cs)
+        self._prefetched = (st, scales)
+
+    def step(self):
+        """Run one iteration on the inputs given to the last ``prefetch()``."""
+        if self._prefetched is None:
+            raise RuntimeError('step() needs a preceding prefetch()')
+        (st, scales), self._prefetched = self._prefetched, None
+        main = torch.cuda.current_stream()
+        main.wait_event(st.staged)
+        st.imgs.copy_(st.imgs_s, non_blocking=True)
+        st.masks.copy_(st.masks_s, non_blocking=True)
+        st.gt._buf.copy_(st.gt_s._buf, non_blocking=True)
+        st.staging_free.record(main)
+        return self._run(st, scales)
 
 
 class _GraphedLoss(object):

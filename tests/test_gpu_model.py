@@ -390,3 +390,37 @@ def test_graphed_updater_replays_the_eager_step():
     np.testing.assert_allclose(h1, h0, rtol=5e-2)
     assert float((p1 - p0).abs().max()) <= 2e-3 * float(p0.abs().max())
     assert h0[3] < h0[0] and h1[3] < h1[0]
+
+
+def test_prefetch_step_matches_direct_call():
+    """GraphedUpdater.prefetch() + step() (inputs copied on a side stream into staging
+    buffers, then device-to-device into the graph's inputs) runs the same iterations as
+    calling the updater with the inputs directly -- from pinned host memory too."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(12)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    imgs_p = torch.from_numpy(imgs).pin_memory()
+    masks_p = models.utils.PackedMasks.from_numpy(np.stack(masks), pin=True)
+    hists = []
+    for mode in ('direct', 'prefetch'):
+        model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                      base_channels=BASE, seed=2)
+        chain = models.MaskRCNNTrainChain(model, seed=6)
+        opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+        up = optimizers.GraphedUpdater(opt, chain, max_boxes=8)
+        hist = []
+        if mode == 'prefetch':
+            up.prefetch(imgs_p, bboxes, labels, masks_p, scales)
+        for _ in range(4):
+            if mode == 'direct':
+                loss = up(imgs_p, bboxes, labels, masks_p, scales)
+            else:
+                loss = up.step()
+                up.prefetch(imgs_p, bboxes, labels, masks_p, scales)
+            hist.append(loss.item())
+        hists.append(hist)
+    assert all(np.isfinite(hists[0] + hists[1]))
+    np.testing.assert_allclose(hists[1][0], hists[0][0], rtol=1e-5)
+    np.testing.assert_allclose(hists[1], hists[0], rtol=5e-2)
+    with pytest.raises(RuntimeError):
+        up.step(); up.step()
