@@ -686,6 +686,8 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
     const char* e = getenv("CMR_CONV_PAIR");
     pair_ok = e ? atoi(e) : 1;
   }
+  // (128-wide pair tiles were measured on the res3 / res4 3x3 layers: no gain, those
+  // single-wave launches are bound by their prologue / epilogue, not by operand delivery)
   const bool pair = pair_ok && bn == 256 && deep && p.tma_a &&
                     (long long)ceil_div(p.M, 2 * kBM) * ceil_div(p.N, bn) >= sm_count() / 2;
   CUtensorMap tmap;

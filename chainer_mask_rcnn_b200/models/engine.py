@@ -47,6 +47,51 @@ def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=N
     return out
 
 
+class _GradSideStream(object):
+    """Weight (and bias) gradients on a second stream during the backward pass.
+
+    A layer's weight gradient and its data gradient both only need the layer's output
+    gradient; the weight gradients are needed by nobody until the optimizer runs.  Issuing
+    them on a side stream lets their CTAs fill the SMs that the data-gradient chain leaves
+    idle (the partial last wave of every persistent GEMM launch), and vice versa.  Works
+    eagerly and under CUDA-graph capture (the event waits become graph edges)."""
+
+    def __init__(self):
+        self.stream = None
+        self.active = False
+        self.keep = []          # operands stay referenced until the join: the caching
+                                # allocator must not hand their memory to the main stream
+
+    def begin(self):
+        import os
+        if os.environ.get('CMR_GRAD_SIDE', '1') == '0':     # A/B measurement knob
+            return
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        self.active = True
+
+    def run(self, fn, *tensors):
+        if not self.active:
+            return fn()
+        ev = torch.cuda.Event()
+        ev.record()                              # everything the main stream produced so far
+        self.keep.extend(t for t in tensors if t is not None)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            return fn()
+
+    def join(self):
+        if self.active:
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            torch.cuda.current_stream().wait_event(done)
+        self.active = False
+        self.keep = []
+
+
+grad_side = _GradSideStream()
+
+
 def wgrad_tap(gy, x, gw, rows, cols, loop_hw, gw_ld, gw_col0=0, gy_stride=1, gy_off=(0, 0),
               gy_c0=0, x_stride=1, x_off=(0, 0), x_c0=0, row_scale=None, taps=(1, 1)):
     """gw[i, gw_col0 + j] += row_scale[i] * sum_pix gy[pix_gy, gy_c0+i] * x[pix_x, x_c0+j]
@@ -56,8 +101,8 @@ def wgrad_tap(gy, x, gw, rows, cols, loop_hw, gw_ld, gw_col0=0, gy_stride=1, gy_
     d = _lib.WgradDesc(B, loop_hw[0], loop_hw[1], gh, gww, gld, gy_stride, gy_off[0], gy_off[1],
                        gy_c0, xh, xw, xld, x_stride, x_off[0], x_off[1], x_c0, rows, cols,
                        gw_ld, gw_col0, 0, taps[0], taps[1])
-    _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _p(gy), _p(x), _p(gw), _p(row_scale),
-              stream())
+    grad_side.run(lambda: _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _p(gy), _p(x), _p(gw),
+                                    _p(row_scale), stream()), gy, x)
 
 
 def round_tf32(src, dst=None):
@@ -70,7 +115,7 @@ def column_sums(g, c0, n, out):
     """out[:n] = sum over all leading axes of g[..., c0:c0+n] (g contiguous)."""
     ld = g.shape[-1]
     rows = g.numel() // ld
-    _lib.call('cmr_col_sum', _p(g), rows, ld, c0, n, _p(out), stream())
+    grad_side.run(lambda: _lib.call('cmr_col_sum', _p(g), rows, ld, c0, n, _p(out), stream()), g)
     return out
 
 

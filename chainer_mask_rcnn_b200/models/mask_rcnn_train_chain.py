@@ -240,8 +240,13 @@ class MaskRCNNTrainChain(object):
                             roi_scores=scores, roi_masks=masks)
 
         def backward():
-            g_feat = head.backward(g_lin, g_mask)
-            g_feat = rpn.backward(g_rpn, g_feat)
-            m.extractor.backward(g_feat)
+            # weight / bias gradients run on a side stream next to the data-gradient chain
+            E.grad_side.begin()
+            try:
+                g_feat = head.backward(g_lin, g_mask)
+                g_feat = rpn.backward(g_rpn, g_feat)
+                m.extractor.backward(g_feat)
+            finally:
+                E.grad_side.join()
 
         return Loss(loss, backward)

@@ -83,6 +83,7 @@ CASES = [
     (1, 5, 6, 64, 64, 5, 1, 2, 64),         # 5x5 pad 2
     (8, 48, 50, 1024, 256, 1, 1, 0, 256),   # CTA-pair path (cta_group::2): 75 x 1 tiles of 256 rows
     (4, 70, 70, 128, 512, 3, 1, 1, 256),    # CTA-pair path, 3x3, ragged last tile, 2 column tiles
+    (2, 51, 84, 128, 256, 3, 1, 1, 128),    # res4 3x3 geometry, 128-wide tiles
 ]
 
 
