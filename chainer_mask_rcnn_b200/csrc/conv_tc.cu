@@ -57,6 +57,9 @@ struct ConvGemmParams {
   const float* bias;
   const float* addend;
   const float* mask;
+  const float* bcast;       // (M / bcast_group, N): v += bcast[row / bcast_group][n] * bcast_scale
+  int bcast_group;
+  float bcast_scale;
   int relu, round_out;
   int m_tiles, n_tiles;
   int tma_a;   // A tiles by TMA: 1 = im2col-mode map, 2 = tiled-mode map (plain matrix);
@@ -90,7 +93,9 @@ struct SmemLayout {
 // the leader CTA issues the MMAs for both, each CTA's TMEM receives its 128 rows and each
 // CTA runs its own epilogue.  TMA loads of both CTAs complete on the leader's barriers;
 // tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both.
-template <int BN, int STAGES, bool PAIR>
+// BCAST: the epilogue has the extra row-group broadcast term of cmr_conv_gemm_tc_ex (its own
+// instantiation, so that the common epilogue keeps its register budget).
+template <int BN, int STAGES, bool PAIR, bool BCAST>
 __global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
@@ -387,6 +392,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
             if (scale_p) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
             if (bias_p) { o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w; }
             if (addend_p) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
+            if (BCAST) {
+              const int grp_row = (m0 + q * 32 + r) / p.bcast_group;
+              const float4 bv =
+                  __ldg(reinterpret_cast<const float4*>(p.bcast + (size_t)grp_row * p.N + n));
+              o.x += bv.x * p.bcast_scale; o.y += bv.y * p.bcast_scale;
+              o.z += bv.z * p.bcast_scale; o.w += bv.w * p.bcast_scale;
+            }
             if (relu) {
               o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
               o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
@@ -413,6 +425,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
               if (scale_p) x *= __ldg(scale_p + n + e);
               if (bias_p) x += __ldg(bias_p + n + e);
               if (addend_p) x += __ldg(addend_p + doff[i] + n + e);
+              if (BCAST)
+                x += __ldg(p.bcast + (size_t)((m0 + q * 32 + r) / p.bcast_group) * p.N + n + e) *
+                     p.bcast_scale;
               if (relu) x = fmaxf(x, 0.f);
               if (mask_p) x = __ldg(mask_p + doff[i] + n + e) > 0.f ? x : 0.f;
               if (round_out) x = round_tf32(x);
@@ -557,13 +572,13 @@ int make_tmap_tiled_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
 
 namespace {
 
-template <int BN, int STAGES, bool PAIR>
-int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
-           cudaStream_t st) {
+template <int BN, int STAGES, bool PAIR, bool BCAST>
+int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
+             cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, PAIR>;
   static bool configured = false;
   if (!configured) {
-    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR>,
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR, BCAST>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::dynamic_bytes(3) <= 232448 ? L::dynamic_bytes(3)
                                                                     : L::dynamic_bytes(2)));
@@ -589,11 +604,19 @@ int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmPar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR>, tmap, tmap_a, q);
+  cudaError_t e =
+      cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, BCAST>, tmap, tmap_a, q);
   prof_end(st);
   CMR_CUDA_TRY(e);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
+}
+
+template <int BN, int STAGES, bool PAIR>
+int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
+           cudaStream_t st) {
+  return p.bcast ? launch_b<BN, STAGES, PAIR, true>(tmap, tmap_a, p, st)
+                 : launch_b<BN, STAGES, PAIR, false>(tmap, tmap_a, p, st);
 }
 
 }  // namespace
@@ -610,7 +633,16 @@ extern "C" int cmr_set_im2col_tma(int on) {
 extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const float* w, float* d,
                                 const float* scale, const float* bias, const float* addend,
                                 const float* mask, void* stream) {
+  return cmr_conv_gemm_tc_ex(c, a, w, d, scale, bias, addend, mask, nullptr, 1, 0.f, stream);
+}
+
+extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const float* w,
+                                   float* d, const float* scale, const float* bias,
+                                   const float* addend, const float* mask, const float* bcast,
+                                   int bcast_group, float bcast_scale, void* stream) {
   CMR_REQUIRE(c && a && w && d);
+  CMR_REQUIRE(!bcast || (bcast_group >= 1 && (reinterpret_cast<uintptr_t>(bcast) & 15) == 0 &&
+                         c->n % 4 == 0));
   CMR_REQUIRE(c->batch > 0 && c->in_h > 0 && c->in_w > 0 && c->out_h > 0 && c->out_w > 0);
   CMR_REQUIRE(c->kh > 0 && c->kw > 0 && c->stride > 0 && c->pad >= 0 && c->n > 0);
   if (c->in_c <= 0 || c->in_c % kBK != 0) return CMR_ERR_UNSUPPORTED;
@@ -631,6 +663,7 @@ extern "C" int cmr_conv_gemm_tc(const cmr_conv_desc* c, const float* a, const fl
   p.d_h = c->d_h; p.d_w = c->d_w; p.d_ld = c->d_ld; p.d_stride = c->d_stride;
   p.d_oy = c->d_oy; p.d_ox = c->d_ox;
   p.scale = scale; p.bias = bias; p.addend = addend; p.mask = mask;
+  p.bcast = bcast; p.bcast_group = bcast_group; p.bcast_scale = bcast_scale;
   p.relu = c->relu; p.round_out = c->round_tf32;
   CMR_REQUIRE(p.d_ld >= p.N && p.d_stride >= 1);
   CMR_REQUIRE((c->out_h - 1) * c->d_stride + c->d_oy < c->d_h);

@@ -50,8 +50,10 @@ class _Deconv2x2(object):
                         d_off=(t // 2, t % 2))
         return out
 
-    def backward(self, g, x):
-        """g = dL/dy * [y > 0] (R,2h,2w,cout); returns dL/dx (not masked, not rounded)."""
+    def backward(self, g, x, bcast=None, mask=None):
+        """g = dL/dy * [y > 0] (R,2h,2w,cout); returns dL/dx -- not masked, not rounded --
+        or, with ``bcast`` (R, cin) and ``mask``: relu_mask(dL/dx + bcast / (h*w)), rounded
+        (the average-pooling branch's gradient folded into the same epilogue)."""
         c = self.ctx
         gw = c.grad(self.W)
         hw = x.shape[1:3]
@@ -59,7 +61,10 @@ class _Deconv2x2(object):
             E.wgrad_tap(g, x, gw[t], self.cout, self.cin, hw, self.cin, gy_stride=2,
                         gy_off=(t // 2, t % 2))
         E.column_sums(g, 0, self.cout, c.grad(self.b))
-        return E.conv_gemm(g, self.w_dgrad, self.cin, 2, 2, 2, 0, round_out=False)
+        if bcast is None:
+            return E.conv_gemm(g, self.w_dgrad, self.cin, 2, 2, 2, 0, round_out=False)
+        return E.conv_gemm(g, self.w_dgrad, self.cin, 2, 2, 2, 0, mask=mask, bcast=bcast,
+                           bcast_group=hw[0] * hw[1], bcast_scale=1.0 / (hw[0] * hw[1]))
 
 
 class ResNetRoIHead(object):
@@ -183,7 +188,6 @@ class ResNetRoIHead(object):
                     self.mask.cin)
         E.column_sums(g_mask, 0, self.n_fg, c.grad(self.mask.b))
         gd6 = E.conv_gemm(g_mask, self.w_dgrad_mask, self.mask.cin, mask=d6)
-        g_res5 = self.deconv6.backward(gd6, res5)
         # box branch
         p4 = pool5.view(R, 1, 1, self.feat)
         g4 = g_lin.view(R, 1, 1, self.lin_ld)
@@ -192,7 +196,10 @@ class ResNetRoIHead(object):
         E.column_sums(g_lin, 0, 4 * nc, c.grad(self.cls_loc.b))
         E.column_sums(g_lin, 4 * nc, nc, c.grad(self.score.b))
         g_pool5 = E.conv_gemm(g4, self.w_dgrad_lin, self.feat, round_out=False).view(R, self.feat)
-        E.avg_pool_bwd_accum(g_pool5, g_res5, res5)
+        # both branches meet at res5's output: the mask branch's data gradient is produced
+        # with the pooled box-branch gradient (g_pool5 / 49 per pixel), res5's ReLU mask and
+        # the tf32 rounding already applied in its epilogue
+        g_res5 = self.deconv6.backward(gd6, res5, bcast=g_pool5, mask=res5)
         g_pool = self.res5.backward(g_res5, input_is_relu=False)
         return E.roi_align_nhwc_bwd(g_pool, s['rois_xy'], s['feat_shape'], self.roi_size,
                                     self.roi_size, self.bin_stride, self.spatial_scale)

@@ -154,6 +154,18 @@ int cmr_conv_gemm_tc(const cmr_conv_desc* desc, const float* a, const float* w,
                      float* d, const float* scale, const float* bias,
                      const float* addend, const float* mask, void* stream);
 
+/* Same, with one more epilogue term between `addend` and `relu`:
+ *     v += bcast[(row / bcast_group) * n + column] * bcast_scale
+ * where row = (b, oy, ox) is the GEMM row.  With bcast_group = oh*ow and bcast_scale =
+ * 1/(oh*ow) this is the backward of average_pooling_2d over the whole window
+ * (chainer_mask_rcnn/models/mask_rcnn_resnet.py:187) fused into the data-gradient GEMM that
+ * produces the other gradient flowing into the same tensor.  bcast == NULL disables it;
+ * n % 4 == 0 and 16-byte alignment are required otherwise. */
+int cmr_conv_gemm_tc_ex(const cmr_conv_desc* desc, const float* a, const float* w,
+                        float* d, const float* scale, const float* bias,
+                        const float* addend, const float* mask, const float* bcast,
+                        int bcast_group, float bcast_scale, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Weight gradient on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate):
  *   gw[i, gw_col0 + j] += row_scale[i] * sum over pixels (b, oy, ox) of

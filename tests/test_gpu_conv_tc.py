@@ -156,3 +156,20 @@ def test_unsupported_channels_is_an_error_not_a_fallback():
     w = torch.zeros((8, 1, 1, 3), device='cuda')
     with pytest.raises(_lib.CmrError):
         conv_tc(x, w, 1, 0)
+
+
+def test_row_group_broadcast_epilogue():
+    """cmr_conv_gemm_tc_ex: v += bcast[row // group] * scale between the addend and the ReLU
+    mask (the average-pooling backward fused into a data-gradient GEMM)."""
+    g = torch.Generator(device='cuda').manual_seed(8)
+    B, H, W, C, N = 6, 7, 7, 64, 128
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    w = round_tf32(torch.randn((N, 1, 1, C), device='cuda', generator=g) / 8)
+    bc = torch.randn((B, N), device='cuda', generator=g)
+    mask = torch.randn((B, H, W, N), device='cuda', generator=g)
+    want = (ref_conv(x, w, 1, 0) + bc.view(B, 1, 1, N) / 49.) * (mask > 0)
+    d = torch.zeros((B, H, W, N), device='cuda')
+    desc = _lib.ConvDesc(B, H, W, C, C, H, W, 1, 1, 1, 0, N, H, W, N, 1, 0, 0, 0, 0, 0)
+    _lib.call('cmr_conv_gemm_tc_ex', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w), _lib.ptr(d),
+              None, None, None, _lib.ptr(mask), _lib.ptr(bc), 49, 1.0 / 49, _lib.stream_ptr())
+    assert rel(d, want) <= 1e-4
