@@ -158,32 +158,40 @@ roi_loss_kernel(const float* __restrict__ cls_loc, int ld_cl, const float* __res
   block_atomic_add(l_cls, losses + 3);
 }
 
-// One thread per element of the (R, HW, ld_g) gradient buffer.
+// One thread per channel quad of the (R, HW, ld_g) gradient buffer (ld_g % 4 == 0): a
+// 16-byte store each; only the quad holding the RoI's class reads a logit.
 __global__ void __launch_bounds__(256)
 mask_loss_kernel(const float* __restrict__ masks, int ld_m, const int* __restrict__ gt_label,
-                 const int* __restrict__ gt_mask, size_t total, int HW, int n_fg,
-                 float* __restrict__ g, int ld_g, float* __restrict__ losses,
+                 const int* __restrict__ gt_mask, size_t total4, int HW, int n_fg,
+                 float4* __restrict__ g, int ld_g4, float* __restrict__ losses,
                  const int* __restrict__ count) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
-  if (e < total) {
-    const int c = (int)(e % ld_g);
-    const size_t pix = e / ld_g;
+  if (e < total4) {
+    const int c4 = (int)(e % ld_g4);
+    const size_t pix = e / ld_g4;
     const int r = (int)(pix / HW);
     int sel = __ldg(gt_label + r) - 1;  // roi_masks[arange, label - 1]: -1 wraps to the last class
     if (sel < 0) sel += n_fg;
-    float gv = 0.f;
-    if (c == sel) {
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((sel >> 2) == c4) {
       const int t = __ldg(gt_mask + pix);
       if (t >= 0) {
+        float gv;
         const float inv_n = 1.0f / (float)max(*count, 1);
-        l = sigmoid_ce(__ldg(masks + pix * ld_m + c), t, &gv) * inv_n;
-        gv *= inv_n;
+        l = sigmoid_ce(__ldg(masks + pix * ld_m + sel), t, &gv) * inv_n;
+        gv = tc::round_tf32(gv * inv_n);
+        const int k = sel & 3;
+        out.x = k == 0 ? gv : 0.f;
+        out.y = k == 1 ? gv : 0.f;
+        out.z = k == 2 ? gv : 0.f;
+        out.w = k == 3 ? gv : 0.f;
       }
     }
-    g[e] = tc::round_tf32(gv);
+    g[e] = out;
   }
-  block_atomic_add(l, losses + 4);
+  // most blocks hold no selected element at all: skip their reduction
+  if (__syncthreads_or(l != 0.f)) block_atomic_add(l, losses + 4);
 }
 
 }  // namespace
@@ -240,7 +248,8 @@ extern "C" int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt
                              const int32_t* gt_mask, int R, int HW, int n_fg, float* g, int ld_g,
                              float* losses, void* stream) {
   CMR_REQUIRE(masks && gt_label && gt_mask && g && losses && R > 0 && HW > 0 && n_fg > 0);
-  CMR_REQUIRE(ld_masks >= n_fg && ld_g >= n_fg);
+  CMR_REQUIRE(ld_masks >= n_fg && ld_g >= n_fg && ld_g % 4 == 0);
+  CMR_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0);
   cudaStream_t st = as_stream(stream);
   int* count = reinterpret_cast<int*>(losses + 7);
   CMR_CUDA_TRY(cudaMemsetAsync(losses + 4, 0, sizeof(float), st));
@@ -249,9 +258,10 @@ extern "C" int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt
   count_ge0_kernel<<<(unsigned)min((long long)sm_count() * 8, ceil_div_ll(npix, 256)), 256, 0,
                      st>>>(gt_mask, npix, count);
   CMR_LAUNCH_CHECK();
-  const size_t total = npix * ld_g;
-  mask_loss_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
-      masks, ld_masks, gt_label, gt_mask, total, HW, n_fg, g, ld_g, losses, count);
+  const size_t total4 = npix * (ld_g / 4);
+  mask_loss_kernel<<<(unsigned)ceil_div_ll(total4, 256), 256, 0, st>>>(
+      masks, ld_masks, gt_label, gt_mask, total4, HW, n_fg, reinterpret_cast<float4*>(g),
+      ld_g / 4, losses, count);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -268,7 +268,8 @@ int cmr_roi_loss(const float* cls_loc, int ld_cls_loc, const float* score,
                  int n_class, float sigma, float* g, int ld_g, float* losses,
                  void* stream);
 /* masks (R,HW,ld_masks) logits in channels [0,n_fg), gt_mask (R,HW) in {-1,0,1};
- * g (R,HW,ld_g): channel label-1 of each RoI gets the gradient, the rest zeros. */
+ * g (R,HW,ld_g), ld_g % 4 == 0, 16-byte aligned: channel label-1 of each RoI gets the
+ * gradient, the rest zeros. */
 int cmr_mask_loss(const float* masks, int ld_masks, const int32_t* gt_label,
                   const int32_t* gt_mask, int R, int HW, int n_fg, float* g,
                   int ld_g, float* losses, void* stream);
