@@ -90,21 +90,6 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorM
       : "memory");
 }
 
-// Multicast form: the box lands at the same shared-memory offset of every CTA of the
-// cluster named in cta_mask, and each of those CTAs' mbarrier (same offset) receives the
-// complete_tx.
-__device__ __forceinline__ void tma_load_im2col_4d_mcast(uint32_t dst, const CUtensorMap* m,
-                                                         uint64_t* bar, int c, int w, int h,
-                                                         int n, int off_w, int off_h,
-                                                         uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      ".multicast::cluster [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
-      "h"((unsigned short)off_w), "h"((unsigned short)off_h), "h"(cta_mask)
-      : "memory");
-}
-
 // CTA-pair forms (.cta_group::2): the box lands in the executing CTA's shared memory, the
 // complete_tx goes to `bar_cluster_addr`, a shared::cluster address that may name the
 // mbarrier of the pair's leader CTA (see mapa_cluster).
@@ -215,14 +200,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           smem_u32(bar))
-      : "memory");
-}
-// Same, arriving on the barrier at this shared-memory offset in every CTA of cta_mask.
-__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
-      " [%0], %1;" ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
       : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread.

@@ -91,7 +91,6 @@ class MaskRCNN(object):
         self.nms_thresh = 0.5
         self.score_thresh = 0.05
         self._detections_per_im = detections_per_im
-        self._pinned_masks = {}
 
     @property
     def n_class(self):
@@ -253,24 +252,16 @@ class MaskRCNN(object):
             b = torch.from_numpy(np.ascontiguousarray(bbox, np.float32)).to(dev)
             l = torch.from_numpy(np.ascontiguousarray(label, np.int32)).to(dev)
             outs.append(_paste(b, l, roi_mask, size[0], size[1], True))
-        # one pinned staging buffer per image (a pageable download of ~100 MB of masks plus
-        # an astype copy would cost more than the whole network pass); 0/1 bytes are
-        # viewed as bool, and copied out because the staging buffer is reused
+        # the 0/1 bytes are downloaded straight into the arrays that are returned (a bool
+        # view of them, no astype copy): ~100 MB per image at the reference's output format
         res = []
-        for i, o in enumerate(outs):
-            if not isinstance(o, torch.Tensor):
-                res.append(o)
-                continue
-            buf = self._pinned_masks.get(i)
-            if buf is None or buf.numel() < o.numel():
-                buf = torch.empty((o.numel(),), dtype=torch.uint8).pin_memory()
-                self._pinned_masks[i] = buf
-            host = buf[:o.numel()].view(o.shape)
-            host.copy_(o, non_blocking=True)
-            res.append(host)
-        torch.cuda.synchronize()
-        return [r.numpy().view(np.bool_).copy() if isinstance(r, torch.Tensor) else r
-                for r in res]
+        for o in outs:
+            if isinstance(o, torch.Tensor):
+                host = torch.empty(o.shape, dtype=torch.uint8)
+                host.copy_(o)
+                o = host.numpy().view(np.bool_)
+            res.append(o)
+        return res
 
     def predict(self, imgs):
         """imgs: list of (3, H, W) float32 RGB arrays in [0, 255].
