@@ -125,21 +125,40 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
     }
     __syncthreads();
     if (t == 0) {
-      unsigned long long d[64];
-#pragma unroll
-      for (int j = 0; j < 64; ++j) d[j] = diag[j];
+      // walk only the boxes that are still alive: find-first-set over the complement of
+      // the removed mask (a chunk that earlier boxes suppressed entirely costs one test)
       unsigned long long r = remv[cb], rn = 0ull;
       int cnt = count_s, nk = 0;
       const int lim = min(64, n - cb * 64);
+      const unsigned long long valid = lim == 64 ? ~0ull : ((1ull << lim) - 1ull);
       bool done = false;
+      unsigned long long alive = ~r & valid;
+      if (__popcll(alive) > 20) {
+        // many survivors: the whole diagonal block in registers, fixed 64-step walk (the
+        // loads are issued up front instead of one dependent shared-memory read per box)
+        unsigned long long d[64];
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        if (j < lim && !done && !((r >> j) & 1ull)) {
+        for (int j = 0; j < 64; ++j) d[j] = diag[j];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          if (j < lim && !done && !((r >> j) & 1ull)) {
+            keep[cnt++] = cb * 64 + j;
+            kept_list[cur][nk++] = j;
+            r |= d[j];
+            rn |= nextw[j];
+            if (limit > 0 && cnt >= limit) done = true;
+          }
+        }
+      } else {
+        while (alive && !done) {
+          const int j = __ffsll((long long)alive) - 1;
           keep[cnt++] = cb * 64 + j;
           kept_list[cur][nk++] = j;
-          r |= d[j];
+          r |= diag[j];
           rn |= nextw[j];
           if (limit > 0 && cnt >= limit) done = true;
+          // boxes after j that are still not removed
+          alive = ~r & valid & (j == 63 ? 0ull : (~0ull << (j + 1)));
         }
       }
       if (rn && cb + 1 < nb) atomicOr(&remv[cb + 1], rn);
