@@ -424,3 +424,37 @@ def test_prefetch_step_matches_direct_call():
     np.testing.assert_allclose(hists[1], hists[0], rtol=5e-2)
     with pytest.raises(RuntimeError):
         up.step(); up.step()
+
+
+def test_ragged_image_size_train_and_predict():
+    """Image sizes that are not multiples of the feature stride (cover_all pooling, ragged
+    tiles in every GEMM, im2col TMA boxes crossing image borders): a train step runs, its
+    loss is finite and decreases, and predict() returns masks of the original sizes."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(21)
+    H, W = 150, 205
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE, min_size=150, max_size=400)
+    chain = models.MaskRCNNTrainChain(model, seed=3)
+    opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+    imgs = (rs.uniform(0, 255, (3, 3, H, W)) - 115.).astype(np.float32)
+    bboxes, labels, masks = [], [], []
+    for _ in range(3):
+        b = synth.random_boxes(rs, 4, H, W, 30., 120.)
+        b = b[(b[:, 2] - b[:, 0] > 8) & (b[:, 3] - b[:, 1] > 8)]
+        m = np.zeros((4, H, W), np.uint8)
+        for i, (y1, x1, y2, x2) in enumerate(b.astype(int)):
+            m[i, y1:y2, x1:x2] = 1
+        bboxes.append(b); labels.append(rs.randint(0, N_FG, len(b)).astype(np.int32))
+        masks.append(m)
+    masks_t = torch.from_numpy(np.stack(masks)).cuda()
+    hist = [opt.update(chain, imgs, bboxes, labels, masks_t, np.ones(3, np.float32)).item()
+            for _ in range(5)]
+    assert all(np.isfinite(hist)) and hist[-1] < hist[0], hist
+    model.score_thresh = 1e-3
+    raw = [rs.uniform(0, 255, (3, 97, 131)).astype(np.float32),
+           rs.uniform(0, 255, (3, 150, 101)).astype(np.float32)]
+    bb, mm, ll, ss = model.predict(raw)
+    for i, im in enumerate(raw):
+        assert mm[i].shape == (len(bb[i]),) + im.shape[1:]
+        assert np.isfinite(bb[i]).all() and np.isfinite(ss[i]).all()
