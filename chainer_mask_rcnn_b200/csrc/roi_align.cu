@@ -266,10 +266,15 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
                : "memory");
 }
 
-// One CTA per (RoI, produced output row); lanes over channels as float4.
+// One CTA per (RoI, produced output row); lanes over channels as float4, two channel
+// quads per thread (c and c + blockDim.x) so that the sample geometry -- table lookups,
+// the four bilinear weights and offsets -- is computed once per 8 channels.  The division
+// by the sample count is a multiplication by its reciprocal (exact when the count is a
+// power of two, else within 1 ulp of the reference's division; the NCHW drop-in kernels
+// keep the exact division).
 // forward: src = x (N,H,W,C), dst = y;   backward: src = gy, dst = gx.
 template <bool kBackward>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                       float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
                       int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
@@ -281,15 +286,23 @@ roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ 
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
   const TapSource taps = make_taps(tt, g, outh, outw, H, W, W * C4, C4);
   const size_t img_off = (size_t)g.batch * H * W * C4;
-  const float d = g.inv_count_den;
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const size_t bin0 = ((size_t)r * oh_s + row) * ow_s;
+  const int T = blockDim.x;
 
-  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+  for (int c = threadIdx.x; c < C4; c += 2 * T) {
+    const bool two = c + T < C4;
     for (int q = 0; q < ow_s; ++q) {
       const int pw = q * bin_stride;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 gv = acc;
-      if (kBackward) gv = __ldg(src + (bin0 + q) * C4 + c);
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;   // fwd: sums; bwd: scaled gy
+      if (kBackward) {
+        a0 = __ldg(src + (bin0 + q) * C4 + c);
+        a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
+        if (two) {
+          a1 = __ldg(src + (bin0 + q) * C4 + c + T);
+          a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
+        }
+      }
       for (int iy = 0; iy < g.grid_h; ++iy) {
         const float4 ty = taps.y(ph, iy);
         const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
@@ -304,28 +317,42 @@ roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ 
             const float4* img = src + img_off + c;
             const float4 v1 = __ldg(img + o[0]), v2 = __ldg(img + o[1]);
             const float4 v3 = __ldg(img + o[2]), v4 = __ldg(img + o[3]);
-            acc.x += w[0] * v1.x + w[1] * v2.x + w[2] * v3.x + w[3] * v4.x;
-            acc.y += w[0] * v1.y + w[1] * v2.y + w[2] * v3.y + w[3] * v4.y;
-            acc.z += w[0] * v1.z + w[1] * v2.z + w[2] * v3.z + w[3] * v4.z;
-            acc.w += w[0] * v1.w + w[1] * v2.w + w[2] * v3.w + w[3] * v4.w;
+            a0.x += w[0] * v1.x + w[1] * v2.x + w[2] * v3.x + w[3] * v4.x;
+            a0.y += w[0] * v1.y + w[1] * v2.y + w[2] * v3.y + w[3] * v4.y;
+            a0.z += w[0] * v1.z + w[1] * v2.z + w[2] * v3.z + w[3] * v4.z;
+            a0.w += w[0] * v1.w + w[1] * v2.w + w[2] * v3.w + w[3] * v4.w;
+            if (two) {
+              const float4 u1 = __ldg(img + o[0] + T), u2 = __ldg(img + o[1] + T);
+              const float4 u3 = __ldg(img + o[2] + T), u4 = __ldg(img + o[3] + T);
+              a1.x += w[0] * u1.x + w[1] * u2.x + w[2] * u3.x + w[3] * u4.x;
+              a1.y += w[0] * u1.y + w[1] * u2.y + w[2] * u3.y + w[3] * u4.y;
+              a1.z += w[0] * u1.z + w[1] * u2.z + w[2] * u3.z + w[3] * u4.z;
+              a1.w += w[0] * u1.w + w[1] * u2.w + w[2] * u3.w + w[3] * u4.w;
+            }
           } else {
             float4* img = dst + img_off + c;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
               red_add_f4(img + o[k],
-                         make_float4(__fdiv_rn(gv.x * w[k], d), __fdiv_rn(gv.y * w[k], d),
-                                     __fdiv_rn(gv.z * w[k], d), __fdiv_rn(gv.w * w[k], d)));
+                         make_float4(a0.x * w[k], a0.y * w[k], a0.z * w[k], a0.w * w[k]));
+              if (two)
+                red_add_f4(img + o[k] + T,
+                           make_float4(a1.x * w[k], a1.y * w[k], a1.z * w[k], a1.w * w[k]));
+            }
           }
         }
       }
       if (!kBackward) {
-        float4 o = make_float4(__fdiv_rn(acc.x, d), __fdiv_rn(acc.y, d), __fdiv_rn(acc.z, d),
-                               __fdiv_rn(acc.w, d));
+        float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+        float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
         if (round_out) {
-          o.x = round_tf32_rn(o.x); o.y = round_tf32_rn(o.y);
-          o.z = round_tf32_rn(o.z); o.w = round_tf32_rn(o.w);
+          o0.x = round_tf32_rn(o0.x); o0.y = round_tf32_rn(o0.y);
+          o0.z = round_tf32_rn(o0.z); o0.w = round_tf32_rn(o0.w);
+          o1.x = round_tf32_rn(o1.x); o1.y = round_tf32_rn(o1.y);
+          o1.z = round_tf32_rn(o1.z); o1.w = round_tf32_rn(o1.w);
         }
-        dst[(bin0 + q) * C4 + c] = o;
+        dst[(bin0 + q) * C4 + c] = o0;
+        if (two) dst[(bin0 + q) * C4 + c + T] = o1;
       }
     }
   }
@@ -338,7 +365,8 @@ int pick_threads(int positions) {
   return t;
 }
 
-int nhwc_threads(int C4) { return C4 >= 256 ? 256 : (C4 >= 128 ? 128 : (C4 >= 64 ? 64 : 32)); }
+// two channel quads per thread
+int nhwc_threads(int C4) { return C4 >= 256 ? 128 : (C4 >= 128 ? 64 : 32); }
 
 }  // namespace
 }  // namespace cmr
