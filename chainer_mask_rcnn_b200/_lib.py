@@ -60,7 +60,7 @@ _SIGNATURES = {
                                       c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     'cmr_prep_dgrad_weight_batch': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'cmr_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float,
-                                 c_float, c_float, c_void_p]),
+                                 c_float, c_float, c_void_p, c_void_p]),
     'cmr_rpn_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_longlong,
                              c_int, c_float, c_void_p, c_int, c_void_p, c_void_p]),
     'cmr_roi_loss': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -216,7 +216,8 @@ prep_dgrad_weight_batch_kernel(const cmr_prep_desc* __restrict__ descs, int n_de
 // v = momentum*v - lr*g';  p += v.
 __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ v,
-                    size_t n4, float lr, float momentum, float wd, float grad_scale) {
+                    float4* __restrict__ rounded, size_t n4, float lr, float momentum, float wd,
+                    float grad_scale) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = p[i], vv = v[i];
@@ -228,6 +229,9 @@ sgd_momentum_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4
     pp.x += vv.x; pp.y += vv.y; pp.z += vv.z; pp.w += vv.w;
     p[i] = pp;
     v[i] = vv;
+    if (rounded)   // the tf32 copy the next forward pass reads (saves a pass over the weights)
+      rounded[i] = make_float4(tc::round_tf32(pp.x), tc::round_tf32(pp.y), tc::round_tf32(pp.z),
+                               tc::round_tf32(pp.w));
   }
 }
 
@@ -331,16 +335,18 @@ extern "C" int cmr_prep_dgrad_weight_batch(const cmr_prep_desc* descs_dev, int n
 
 extern "C" int cmr_sgd_momentum(float* param, const float* grad, float* velocity, size_t n,
                                 float lr, float momentum, float weight_decay, float grad_scale,
-                                void* stream) {
+                                float* param_tf32, void* stream) {
   if (n == 0) return CMR_OK;
   CMR_REQUIRE(param && grad && velocity && n % 4 == 0);
   CMR_REQUIRE(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
-                reinterpret_cast<uintptr_t>(velocity)) & 15) == 0);
+                reinterpret_cast<uintptr_t>(velocity) | reinterpret_cast<uintptr_t>(param_tf32)) &
+               15) == 0);
   const size_t n4 = n / 4;
   const int blocks = (int)min((size_t)sm_count() * 8, (n4 + 255) / 256);
   sgd_momentum_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
-      reinterpret_cast<float4*>(velocity), n4, lr, momentum, weight_decay, grad_scale);
+      reinterpret_cast<float4*>(velocity), reinterpret_cast<float4*>(param_tf32), n4, lr, momentum,
+      weight_decay, grad_scale);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

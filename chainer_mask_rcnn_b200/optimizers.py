@@ -67,8 +67,9 @@ class MomentumSGD(object):
         scale = 1.0 / self.comm.size if self.comm is not None else 1.0
         _lib.call('cmr_sgd_momentum', E._p(self.ctx.train.data), E._p(self.ctx.grads),
                   E._p(self.velocity), n, float(self.lr), float(self.momentum),
-                  float(self.weight_decay), float(scale), E.stream())
+                  float(self.weight_decay), float(scale), E._p(self.ctx.rounded), E.stream())
         self.ctx.mark_dirty(frozen=False)
+        self.ctx._train_dirty = False        # the kernel refreshed the tf32 forward copy
 
 
 class Communicator(object):

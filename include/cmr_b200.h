@@ -243,10 +243,12 @@ typedef struct cmr_prep_desc {
 int cmr_prep_dgrad_weight_batch(const cmr_prep_desc* descs_dev, int n_desc,
                                 int total_tiles, void* stream);
 /* MomentumSGD + WeightDecay (examples/train_common.py:176-180) on a flat buffer:
- * g' = grad_scale*g + wd*p;  v = momentum*v - lr*g';  p += v.  n % 4 == 0. */
+ * g' = grad_scale*g + wd*p;  v = momentum*v - lr*g';  p += v.  n % 4 == 0.
+ * param_tf32 (may be NULL): receives round-to-nearest-tf32(p), the copy the next
+ * forward pass's GEMMs read. */
 int cmr_sgd_momentum(float* param, const float* grad, float* velocity, size_t n,
                      float lr, float momentum, float weight_decay,
-                     float grad_scale, void* stream);
+                     float grad_scale, float* param_tf32, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Losses of MaskRCNNTrainChain.__call__ and their gradients

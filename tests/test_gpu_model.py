@@ -274,6 +274,8 @@ def test_sgd_update_matches_numpy(setup):
         opt.update()
     assert float((ctx.train.data - p0).abs().max()) <= 1e-6
     assert torch.equal(ctx.frozen.data, frozen0)
+    # the update kernel also refreshed the tf32 copy the forward GEMMs read
+    assert torch.equal(ctx.rounded, E.round_tf32(ctx.train.data.clone()))
     model.load_state_dict(params)     # restore for other tests
 
 
