@@ -96,7 +96,7 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         'batch', 'in_h', 'in_w', 'in_c', 'in_ld', 'out_h', 'out_w', 'kh', 'kw', 'stride',
         'pad', 'n', 'd_h', 'd_w', 'd_ld', 'd_stride', 'd_oy', 'd_ox', 'relu', 'round_tf32',
-        'tile_n')]
+        'tile_n', 'tap_cols')]
 
 
 class PrepDesc(ctypes.Structure):

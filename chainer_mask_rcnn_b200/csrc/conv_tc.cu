@@ -53,6 +53,7 @@ struct ConvGemmParams {
   int M, N, K;
   float* d;
   int d_h, d_w, d_ld, d_stride, d_oy, d_ox;
+  int tap_cols;   // > 0: column block t = n / tap_cols goes to pixel offset (t >> 1, t & 1)
   const float* scale;
   const float* bias;
   const float* addend;
@@ -93,9 +94,13 @@ struct SmemLayout {
 // the leader CTA issues the MMAs for both, each CTA's TMEM receives its 128 rows and each
 // CTA runs its own epilogue.  TMA loads of both CTAs complete on the leader's barriers;
 // tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both.
-// BCAST: the epilogue has the extra row-group broadcast term of cmr_conv_gemm_tc_ex (its own
-// instantiation, so that the common epilogue keeps its register budget).
-template <int BN, int STAGES, bool PAIR, bool BCAST>
+// EPI: 0 = the common epilogue; 1 = with the row-group broadcast term of
+// cmr_conv_gemm_tc_ex; 2 = pixel-shuffle store of a fused 2x2 deconvolution (tap_cols).
+// The rare forms are their own instantiations so that the common epilogue keeps its
+// register budget (128 registers, no spills).
+constexpr int kEpiPlain = 0, kEpiBcast = 1, kEpiTaps = 2;
+
+template <int BN, int STAGES, bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
@@ -344,8 +349,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       for (int chunk = grp; chunk < kChunks; chunk += n_groups) {
         const int cbase = chunk * 32;                     // column of the tile
         if (n0 + cbase >= p.N) break;
-        const int n = n0 + cbase + c4;                    // this lane's first global column
-        const bool full4 = vec_ok && (n + 3 < p.N);
+        const int ng = n0 + cbase + c4;                   // this lane's first GEMM column
+        // pixel-shuffle store of a fused 2x2 stride-2 deconvolution: column block t =
+        // ng / tap_cols holds tap (t >> 1, t & 1); n / toff address the output tensor
+        const int tap = EPI == kEpiTaps ? (n0 + cbase) / p.tap_cols : 0;
+        const int toff = ((tap >> 1) * p.d_w + (tap & 1)) * p.d_ld;
+        const int n = ng - tap * p.tap_cols;              // channel in the output tensor
+        const bool full4 = vec_ok && (ng + 3 < p.N);
         // operands of the epilogue are requested before the accumulator is waited for
         // (coalesced: 8 lanes cover one 128 B row)
         float4 ad[8], mk[8];
@@ -354,13 +364,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           if (addend_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(addend_p + doff[i] + n))
+              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(addend_p + doff[i] + toff + n))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           if (mask_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(mask_p + doff[i] + n))
+              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(mask_p + doff[i] + toff + n))
                                    : make_float4(1.f, 1.f, 1.f, 1.f);
           }
           if (scale_p) sc = __ldg(reinterpret_cast<const float4*>(scale_p + n));
@@ -392,7 +402,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
             if (scale_p) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
             if (bias_p) { o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w; }
             if (addend_p) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-            if (BCAST) {
+            if (EPI == kEpiBcast) {
               const int grp_row = (m0 + q * 32 + r) / p.bcast_group;
               const float4 bv =
                   __ldg(reinterpret_cast<const float4*>(p.bcast + (size_t)grp_row * p.N + n));
@@ -411,7 +421,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
               o.x = round_tf32(o.x); o.y = round_tf32(o.y);
               o.z = round_tf32(o.z); o.w = round_tf32(o.w);
             }
-            *reinterpret_cast<float4*>(d_p + doff[i] + n) = o;
+            *reinterpret_cast<float4*>(d_p + doff[i] + toff + n) = o;
           }
         } else {
           // ragged / unaligned tail columns: scalar path
@@ -420,18 +430,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           for (int i = 0; i < 8; ++i) {
             if (doff[i] < 0) continue;
             const int r = 4 * i + sub;
-            for (int e = 0; e < 4 && n + e < p.N; ++e) {
+            for (int e = 0; e < 4 && ng + e < p.N; ++e) {
               float x = xs[r * 32 + ((((lane & 7) ^ (r & 7))) << 2) + e];
               if (scale_p) x *= __ldg(scale_p + n + e);
               if (bias_p) x += __ldg(bias_p + n + e);
-              if (addend_p) x += __ldg(addend_p + doff[i] + n + e);
-              if (BCAST)
+              if (addend_p) x += __ldg(addend_p + doff[i] + toff + n + e);
+              if (EPI == kEpiBcast)
                 x += __ldg(p.bcast + (size_t)((m0 + q * 32 + r) / p.bcast_group) * p.N + n + e) *
                      p.bcast_scale;
               if (relu) x = fmaxf(x, 0.f);
-              if (mask_p) x = __ldg(mask_p + doff[i] + n + e) > 0.f ? x : 0.f;
+              if (mask_p) x = __ldg(mask_p + doff[i] + toff + n + e) > 0.f ? x : 0.f;
               if (round_out) x = round_tf32(x);
-              d_p[doff[i] + n + e] = x;
+              d_p[doff[i] + toff + n + e] = x;
             }
           }
         }
@@ -572,13 +582,13 @@ int make_tmap_tiled_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
 
 namespace {
 
-template <int BN, int STAGES, bool PAIR, bool BCAST>
+template <int BN, int STAGES, bool PAIR, int EPI>
 int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
              cudaStream_t st) {
   using L = SmemLayout<BN, STAGES, PAIR>;
   static bool configured = false;
   if (!configured) {
-    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR, BCAST>,
+    CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       L::dynamic_bytes(3) <= 232448 ? L::dynamic_bytes(3)
                                                                     : L::dynamic_bytes(2)));
@@ -605,7 +615,7 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
   cfg.numAttrs = 1;
   prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
   cudaError_t e =
-      cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, BCAST>, tmap, tmap_a, q);
+      cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI>, tmap, tmap_a, q);
   prof_end(st);
   CMR_CUDA_TRY(e);
   CMR_LAUNCH_CHECK();
@@ -615,8 +625,9 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
 template <int BN, int STAGES, bool PAIR>
 int launch(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmParams& p,
            cudaStream_t st) {
-  return p.bcast ? launch_b<BN, STAGES, PAIR, true>(tmap, tmap_a, p, st)
-                 : launch_b<BN, STAGES, PAIR, false>(tmap, tmap_a, p, st);
+  if (p.bcast) return launch_b<BN, STAGES, PAIR, kEpiBcast>(tmap, tmap_a, p, st);
+  if (p.tap_cols > 0) return launch_b<BN, STAGES, PAIR, kEpiTaps>(tmap, tmap_a, p, st);
+  return launch_b<BN, STAGES, PAIR, kEpiPlain>(tmap, tmap_a, p, st);
 }
 
 }  // namespace
@@ -662,12 +673,20 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
   p.d = d;
   p.d_h = c->d_h; p.d_w = c->d_w; p.d_ld = c->d_ld; p.d_stride = c->d_stride;
   p.d_oy = c->d_oy; p.d_ox = c->d_ox;
+  p.tap_cols = c->tap_cols;
   p.scale = scale; p.bias = bias; p.addend = addend; p.mask = mask;
   p.bcast = bcast; p.bcast_group = bcast_group; p.bcast_scale = bcast_scale;
   p.relu = c->relu; p.round_out = c->round_tf32;
-  CMR_REQUIRE(p.d_ld >= p.N && p.d_stride >= 1);
-  CMR_REQUIRE((c->out_h - 1) * c->d_stride + c->d_oy < c->d_h);
-  CMR_REQUIRE((c->out_w - 1) * c->d_stride + c->d_ox < c->d_w);
+  CMR_REQUIRE(p.d_stride >= 1 && p.tap_cols >= 0);
+  if (p.tap_cols > 0) {   // fused 2x2 stride-2 deconvolution: four column blocks of tap_cols
+    CMR_REQUIRE(p.tap_cols % 32 == 0 && p.N == 4 * p.tap_cols && p.d_ld >= p.tap_cols);
+    CMR_REQUIRE(p.d_stride == 2 && !bcast);
+    CMR_REQUIRE((c->out_h - 1) * 2 + c->d_oy + 1 < c->d_h && (c->out_w - 1) * 2 + c->d_ox + 1 < c->d_w);
+  } else {
+    CMR_REQUIRE(p.d_ld >= p.N);
+    CMR_REQUIRE((c->out_h - 1) * c->d_stride + c->d_oy < c->d_h);
+    CMR_REQUIRE((c->out_w - 1) * c->d_stride + c->d_ox < c->d_w);
+  }
 
   // Tile width: minimise (waves over the SMs) x (per-tile cost); narrower tiles move
   // more operand bytes per FLOP through L2 (relative tile rates 1 : 0.75 : 0.5).

@@ -30,7 +30,7 @@ def conv_out(size, k, s, p):
 def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=None,
               addend=None, mask=None, relu=False, round_out=True, in_c=None, in_ld=None,
               out_hw=None, d_stride=1, d_off=(0, 0), tile_n=0, bcast=None, bcast_group=1,
-              bcast_scale=0.):
+              bcast_scale=0., tap_cols=0):
     """out[b, oy*d_stride+d_off[0], ox*d_stride+d_off[1], :n] =
     epilogue(sum_{fr,fs,c} x[b, oy*stride-pad+fr, ox*stride-pad+fs, c] * w[n, fr, fs, c]).
     x (B,H,W,C) contiguous NHWC; w (n, kh, kw, in_c) contiguous; see cmr_conv_gemm_tc."""
@@ -42,7 +42,8 @@ def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=N
         out = torch.empty((B, oh, ow, n), dtype=f32, device=x.device)
     _, dh, dw, dld = out.shape
     desc = _lib.ConvDesc(B, H, W, in_c, in_ld, oh, ow, kh, kw, stride, pad, n, dh, dw, dld,
-                         d_stride, d_off[0], d_off[1], int(relu), int(round_out), tile_n)
+                         d_stride, d_off[0], d_off[1], int(relu), int(round_out), tile_n,
+                         tap_cols)
     if bcast is None:
         _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _p(x), _p(w), _p(out), _p(scale),
                   _p(bias), _p(addend), _p(mask), stream())

@@ -17,8 +17,9 @@ from .resnet_extractor import ResNetExtractorBase
 
 
 class _Deconv2x2(object):
-    """Deconvolution2D(cin, cout, 2, stride=2) + bias + ReLU: four 1x1 GEMMs whose
-    outputs are interleaved by a pixel-shuffle store (models/mask_rcnn_resnet.py:138-139)."""
+    """Deconvolution2D(cin, cout, 2, stride=2) + bias + ReLU: ONE GEMM with N = 4 * cout
+    (the four filter taps side by side; the input is read once) whose column blocks are
+    interleaved by a pixel-shuffle store (models/mask_rcnn_resnet.py:138-139)."""
 
     def __init__(self, ctx, name, cin, cout):
         self.ctx, self.cin, self.cout = ctx, cin, cout
@@ -43,11 +44,9 @@ class _Deconv2x2(object):
     def forward(self, x):
         R, h, w, _ = x.shape
         out = torch.empty((R, 2 * h, 2 * w, self.cout), dtype=torch.float32, device=x.device)
-        wt = self.ctx.fwd(self.W)
-        bias = self.ctx.param(self.b)
-        for t in range(4):
-            E.conv_gemm(x, wt[t], self.cout, out=out, bias=bias, relu=True, d_stride=2,
-                        d_off=(t // 2, t % 2))
+        wt = self.ctx.fwd(self.W)                       # (4, cout, cin): tap-major rows
+        E.conv_gemm(x, wt, 4 * self.cout, out=out, bias=self.ctx.param(self.b), relu=True,
+                    d_stride=2, tap_cols=self.cout)
         return out
 
     def backward(self, g, x, bcast=None, mask=None):

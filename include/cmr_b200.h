@@ -142,6 +142,11 @@ typedef struct cmr_conv_desc {
   int d_h, d_w, d_ld, d_stride, d_oy, d_ox;
   int relu, round_tf32;
   int tile_n;
+  int tap_cols;   /* > 0: fused Deconvolution2D(2, stride 2): n == 4*tap_cols, d_stride == 2;
+                     GEMM column block t = column / tap_cols is filter tap (t >> 1, t & 1) and
+                     is written to pixel (2*oy + d_oy + (t >> 1), 2*ox + d_ox + (t & 1)),
+                     channels [0, tap_cols); scale / bias are indexed by the channel.
+                     0 = plain layout. */
 } cmr_conv_desc;
 
 /* The activation operand of cmr_conv_gemm_tc / cmr_conv_wgrad_tc is fetched by im2col-mode

@@ -173,3 +173,21 @@ def test_row_group_broadcast_epilogue():
     _lib.call('cmr_conv_gemm_tc_ex', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w), _lib.ptr(d),
               None, None, None, _lib.ptr(mask), _lib.ptr(bc), 49, 1.0 / 49, _lib.stream_ptr())
     assert rel(d, want) <= 1e-4
+
+
+def test_fused_deconvolution_tap_columns():
+    """Deconvolution2D(2, stride 2) + bias + ReLU as ONE GEMM with N = 4 * cout whose column
+    blocks are pixel-shuffled by the epilogue (cmr_conv_desc.tap_cols)."""
+    g = torch.Generator(device='cuda').manual_seed(9)
+    B, H, W, C, N = 3, 7, 7, 64, 64
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    wt = round_tf32(torch.randn((C, N, 2, 2), device='cuda', generator=g) / 8)   # (in, out, kh, kw)
+    bias = torch.randn((N,), device='cuda', generator=g)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), bias.double(), stride=2)
+    want = torch.relu(want).permute(0, 2, 3, 1).float()
+    w_taps = wt.permute(2, 3, 1, 0).contiguous().view(4 * N, 1, 1, C)      # (tap, out, in)
+    out = torch.zeros((B, 2 * H, 2 * W, N), device='cuda')
+    desc = _lib.ConvDesc(B, H, W, C, C, H, W, 1, 1, 1, 0, 4 * N, 2 * H, 2 * W, N, 2, 0, 0, 1, 0, 0, N)
+    _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w_taps), _lib.ptr(out),
+              None, _lib.ptr(bias), None, None, _lib.stream_ptr())
+    assert rel(out, want) <= 1e-4
