@@ -44,7 +44,12 @@ def _digest():
 
 
 def is_current():
+    """The library exists, its stamp holds the digest of the present sources, and the stamp
+    was written together with the library (a restored or copied stamp next to a library
+    built from other sources must not count)."""
     if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
+        return False
+    if abs(os.path.getmtime(STAMP_PATH) - os.path.getmtime(LIB_PATH)) > 120:
         return False
     with open(STAMP_PATH) as f:
         return f.read().strip() == _digest()
