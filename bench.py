@@ -332,9 +332,9 @@ def main():
                 'achieved': achieved, 'peak': tf32_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / tf32_peak if tf32_peak else None,
                 # dram__bytes_read + write of ONE representative launch (res5 3x3 forward,
-                # 236.8 GFLOP) from the ncu --set full capture profiles/r1_ncu_conv_v9_raw.csv;
-                # `achieved` sums all 108 launches of the step
-                'traffic': 177.1e6,
+                # 236.8 GFLOP, CTA-pair kernel) from the ncu --set full capture
+                # profiles/r1_ncu_conv_v12_raw.csv; `achieved` sums all launches of the step
+                'traffic': 184.4e6,
                 'peak_source': '%s bf16_tflops_sustained / 2: kind::tf32 issues at half the '
                                'bf16 rate (cuBLAS TF32 8192^3 on this pool: 763 burst / 622 '
                                'sustained TFLOP/s)' % pk['source'],

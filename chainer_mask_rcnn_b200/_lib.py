@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libcmr_b200.so')
 
 c_int = ctypes.c_int
 c_float = ctypes.c_float
+c_double = ctypes.c_double
 c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
 c_longlong = ctypes.c_longlong
@@ -84,6 +85,9 @@ _SIGNATURES = {
     'cmr_paste_masks': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_longlong,
                                 c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                 c_void_p]),
+    'cmr_prepare_size': (c_int, [c_int, c_int, c_double, c_double, c_void_p, c_void_p]),
+    'cmr_prepare_image': (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_float, c_float,
+                                  c_float, c_void_p, c_int, c_int, c_void_p]),
     'cmr_mask_targets': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'cmr_mask_loss': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

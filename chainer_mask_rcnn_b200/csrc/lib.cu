@@ -91,7 +91,7 @@ extern "C" const char* cmr_status_string(int status) {
   }
 }
 
-extern "C" int cmr_version(void) { return 4; }
+extern "C" int cmr_version(void) { return 5; }
 
 extern "C" long long cmr_launch_count(void) { return cmr::g_launches.load(); }
 

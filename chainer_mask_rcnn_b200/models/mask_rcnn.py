@@ -12,6 +12,7 @@ detections_per_im cut (a few hundred rows, with the reference's positional argso
 rule) runs in NumPy.
 """
 import ctypes
+import weakref
 
 import cv2
 import numpy as np
@@ -59,6 +60,57 @@ def segm_results(bbox, label, roi_mask, im_h, im_w):
     l = torch.from_numpy(np.ascontiguousarray(label, np.int32)).to(dev)
     m = torch.from_numpy(np.ascontiguousarray(roi_mask, np.float32)).to(dev)
     return _paste(b, l, m, im_h, im_w, False).cpu().numpy().astype(bool)
+
+
+def prepare_scale(H, W, min_size, max_size):
+    """The resize factor of ``prepare`` (mask_rcnn.py:158-165), Python-float arithmetic."""
+    scale = 1.
+    if min_size:
+        scale = min_size / min(H, W)
+    if max_size and scale * max(H, W) > max_size:
+        scale = max_size / max(H, W)
+    return scale
+
+
+def prepared_size(H, W, scale):
+    """(h, w) of cv2.resize(img, None, fx=scale, fy=scale): cvRound of the products."""
+    h, w = ctypes.c_int(), ctypes.c_int()
+    _lib.call('cmr_prepare_size', int(H), int(W), float(scale), float(scale),
+              ctypes.addressof(h), ctypes.addressof(w))
+    return h.value, w.value
+
+
+class _PinnedDownloads(object):
+    """Page-locked destination buffers for the (n, H, W) mask stacks predict returns.
+
+    ~100 MB per image leave the device in the reference's output format; into pageable
+    memory that copy runs at a fraction of the link rate.  The arrays handed to the caller
+    are views of page-locked tensors from torch's caching host allocator (a buffer goes
+    back to the cache when the caller drops the array, so a predict loop reuses the same
+    few buffers).  At most `budget` bytes are outstanding at a time; beyond that (a caller
+    who keeps every result) downloads go to ordinary pageable memory.
+    """
+
+    def __init__(self, budget=1 << 30):
+        self.budget = budget
+        self.outstanding = 0
+
+    def _release(self, nbytes):
+        self.outstanding -= nbytes
+
+    def download(self, dev_tensor):
+        nbytes = dev_tensor.numel() * dev_tensor.element_size()
+        pin = self.outstanding + nbytes <= self.budget
+        host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=pin)
+        host.copy_(dev_tensor)
+        arr = host.numpy()       # shares (and keeps alive) the tensor's storage
+        if pin:
+            self.outstanding += nbytes
+            weakref.finalize(arr, self._release, nbytes)   # views hold `arr` as their base
+        return arr
+
+
+_downloads = _PinnedDownloads()
 
 
 def as_device_f32(x):
@@ -117,17 +169,37 @@ class MaskRCNN(object):
         prepared, sizes, scales = [], [], []
         for img in imgs:
             _, H, W = img.shape
-            scale = 1.
-            if self.min_size:
-                scale = self.min_size / min(H, W)
-            if self.max_size and scale * max(H, W) > self.max_size:
-                scale = self.max_size / max(H, W)
+            scale = prepare_scale(H, W, self.min_size, self.max_size)
             out = cv2.resize(img.transpose(1, 2, 0), None, fx=scale, fy=scale)
             out = (out.transpose(2, 0, 1) - self.mean).astype(np.float32, copy=False)
             prepared.append(out)
             sizes.append((H, W))
             scales.append(scale)
         return prepared, sizes, scales
+
+    def _prepare_device(self, imgs):
+        """prepare + concat_examples(padding=0) of predict (mask_rcnn.py:308-311) on the
+        device: the raw float32 images are uploaded as they are and cmr_prepare_image
+        writes the resized, mean-subtracted, zero-padded (B, 3, Hm, Wm) batch.
+        -> x (device), sizes, scales."""
+        sizes, scales, shapes = [], [], []
+        for img in imgs:
+            _, H, W = img.shape
+            scale = prepare_scale(H, W, self.min_size, self.max_size)
+            sizes.append((H, W))
+            scales.append(scale)
+            shapes.append(prepared_size(H, W, scale))
+        Hm, Wm = max(s[0] for s in shapes), max(s[1] for s in shapes)
+        mean = np.asarray(self.mean, np.float32).reshape(-1)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        x = torch.empty((len(imgs), 3, Hm, Wm), dtype=torch.float32, device=dev)
+        for i, img in enumerate(imgs):
+            raw = as_device_f32(img)
+            _lib.call('cmr_prepare_image', E._p(raw), sizes[i][0], sizes[i][1], float(scales[i]),
+                      float(scales[i]), float(mean[0]), float(mean[1]), float(mean[2]),
+                      E._p(x[i]), Hm, Wm, E.stream())
+            raw.record_stream(torch.cuda.current_stream())
+        return x, sizes, scales
 
     # ---- inference (mask_rcnn.py:178-337) ----
     def _forward_padded(self, x, scales, pred_mask):
@@ -254,24 +326,13 @@ class MaskRCNN(object):
             outs.append(_paste(b, l, roi_mask, size[0], size[1], True))
         # the 0/1 bytes are downloaded straight into the arrays that are returned (a bool
         # view of them, no astype copy): ~100 MB per image at the reference's output format
-        res = []
-        for o in outs:
-            if isinstance(o, torch.Tensor):
-                host = torch.empty(o.shape, dtype=torch.uint8)
-                host.copy_(o)
-                o = host.numpy().view(np.bool_)
-            res.append(o)
-        return res
+        return [_downloads.download(o).view(np.bool_) if isinstance(o, torch.Tensor) else o
+                for o in outs]
 
     def predict(self, imgs):
         """imgs: list of (3, H, W) float32 RGB arrays in [0, 255].
         -> bboxes, masks, labels, scores (lists per image; mask_rcnn.py:307-337)."""
-        imgs, sizes, scales = self.prepare(imgs)
-        B = len(imgs)
-        Hm, Wm = max(i.shape[1] for i in imgs), max(i.shape[2] for i in imgs)
-        x = np.zeros((B, 3, Hm, Wm), np.float32)          # concat_examples(padding=0)
-        for i, im in enumerate(imgs):
-            x[i, :, :im.shape[1], :im.shape[2]] = im
+        x, sizes, scales = self._prepare_device(imgs)
         scales = np.asarray(scales, np.float32)
         with config.using_config('train', False), torch.no_grad():
             feat, rois, cnt, cls_locs, scores, _ = self._forward_padded(x, scales, False)

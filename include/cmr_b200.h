@@ -371,6 +371,18 @@ int cmr_paste_masks(const float* bbox, const int32_t* label, const float* mask_p
                     long long stride_x, int n, int mask_size, int H, int W,
                     int apply_sigmoid, uint8_t* out, void* stream);
 
+/* MaskRCNN.prepare (chainer_mask_rcnn/models/mask_rcnn.py:152-176) on the device.
+ * cmr_prepare_size: the size cv2.resize(img, None, fx=fx, fy=fy) produces,
+ * (cvRound(H*fy), cvRound(W*fx)); host-only, no CUDA call.
+ * cmr_prepare_image: img (3, H, W) fp32 planes on the device -> out (3, out_h, out_w) fp32
+ * planes: cv2.resize (INTER_LINEAR, fp32; exact 2x decimation = 2x2 block mean as in
+ * OpenCV) minus the per-channel mean inside (h, w), zeros outside (the padding
+ * chainer.dataset.concat_examples(padding=0) adds, mask_rcnn.py:310-311). */
+int cmr_prepare_size(int H, int W, double fx, double fy, int* h, int* w);
+int cmr_prepare_image(const float* img, int H, int W, double fx, double fy, float mean0,
+                      float mean1, float mean2, float* out, int out_h, int out_w,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

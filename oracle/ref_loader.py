@@ -163,6 +163,16 @@ def ref_to_bboxes(roi_cls_locs, roi_scores, rois, roi_indices, sizes, scales, n_
     return m._to_bboxes(roi_cls_locs, roi_scores, rois.copy(), roi_indices, sizes, scales)
 
 
+def ref_prepare(imgs, min_size, max_size, mean):
+    """MaskRCNN.prepare (mask_rcnn.py:152-176) run verbatim (cv2.resize as installed)."""
+    import numpy
+    mod = load_mask_rcnn_module()
+    m = mod.MaskRCNN.__new__(mod.MaskRCNN)
+    m.min_size, m.max_size = min_size, max_size
+    m.mean = numpy.asarray(mean, numpy.float32)[:, None, None]
+    return m.prepare(imgs)
+
+
 def ref_roi_align_forward(x, rois_xy, outh, outw, spatial_scale, sampling_ratio):
     """Reference ROIAlign2D.forward_cpu (roi_align_2d.py:61-160), run verbatim."""
     mod = load_roi_align_module()

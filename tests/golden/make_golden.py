@@ -157,6 +157,31 @@ def detect_fixture():
     return out
 
 
+PREPARE_CASES = [  # (H, W, min_size, max_size)
+    (60, 100, 100, 400),    # 5/3 up
+    (50, 200, 100, 250),    # capped by max_size: 1.25
+    (80, 103, 40, 400),     # exactly 0.5: OpenCV's 2x2 block mean; 103 * 0.5 rounds up to 52,
+                            # so the last column is a block cut by the edge
+    (48, 64, 48, 400),      # identity
+    (100, 60, 15, 400),     # 0.25: plain bilinear taps, no block mean
+]
+
+
+def prepare_fixture():
+    """MaskRCNN.prepare (models/mask_rcnn.py:152-176) verbatim, cv2 as installed (IPP on)."""
+    rs = np.random.RandomState(5)
+    mean = (123.152, 115.903, 103.063)
+    out = dict(mean=np.asarray(mean, np.float32), cases=np.asarray(PREPARE_CASES))
+    for k, (H, W, lo, hi) in enumerate(PREPARE_CASES):
+        img = rs.uniform(0, 255, (3, H, W)).astype(np.float32)
+        prepared, sizes, scales = ref_loader.ref_prepare([img], lo, hi, mean)
+        assert sizes[0] == (H, W)
+        out['img_%d' % k] = img
+        out['out_%d' % k] = prepared[0]
+        out['scale_%d' % k] = np.float64(scales[0])
+    return out
+
+
 def main():
     assert ref_loader.reference_available(), 'needs /root/reference'
     np.savez_compressed(os.path.join(HERE, 'roi_align_unit.npz'), **unit_fixture())
@@ -165,6 +190,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'affine_channel.npz'), **affine_fixture())
     np.savez_compressed(os.path.join(HERE, 'proposal_targets.npz'), **proposal_target_fixture())
     np.savez_compressed(os.path.join(HERE, 'detect.npz'), **detect_fixture())
+    np.savez_compressed(os.path.join(HERE, 'prepare.npz'), **prepare_fixture())
     print('golden vectors written to', HERE)
 
 

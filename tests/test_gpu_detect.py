@@ -89,3 +89,71 @@ def test_predict_runs_end_to_end():
         assert labels[i].shape == (n,) and scores[i].shape == (n,)
         assert (bboxes[i][:, 2] <= im.shape[1]).all() and (bboxes[i][:, 3] <= im.shape[2]).all()
         assert ((labels[i] >= 0) & (labels[i] < 5)).all()
+
+
+class _Prep(mr.MaskRCNN):
+    def __init__(self, min_size, max_size):
+        self.min_size, self.max_size = min_size, max_size
+        self.mean = np.array([123.152, 115.903, 103.063], np.float32)[:, None, None]
+
+
+@pytest.mark.parametrize('shapes,min_size,max_size', [
+    ([(120, 200), (100, 150)], 200, 400),       # up-scaling, two sizes in one padded batch
+    ([(100, 400)], 200, 500),                   # capped by max_size
+    ([(160, 203), (161, 322)], 80, 400),        # exact 2x decimation (block mean, cut edge) + plain taps
+    ([(96, 128)], 96, 400),                     # identity
+    ([(200, 120)], 30, 400),                    # 4x decimation
+])
+def test_prepare_device_bit_exact(shapes, min_size, max_size):
+    """cmr_prepare_image against oracle/prepare.py (itself bit-exact against cv2.resize,
+    tests/test_oracle_prepare.py): resize + mean subtraction + zero padding."""
+    from oracle import prepare as op
+    rs = np.random.RandomState(len(shapes) * 100 + min_size)
+    imgs = [rs.uniform(0, 255, (3, h, w)).astype(np.float32) for h, w in shapes]
+    m = _Prep(min_size, max_size)
+    want, sizes_w, scales_w = op.prepare(imgs, min_size, max_size, m.mean.reshape(-1))
+    x, sizes, scales = m._prepare_device(imgs)
+    assert sizes == sizes_w and scales == scales_w
+    x = x.cpu().numpy()
+    Hm, Wm = max(w.shape[1] for w in want), max(w.shape[2] for w in want)
+    assert x.shape == (len(imgs), 3, Hm, Wm)
+    for i, w in enumerate(want):
+        np.testing.assert_array_equal(x[i, :, :w.shape[1], :w.shape[2]], w)
+        assert not x[i, :, w.shape[1]:].any() and not x[i, :, :, w.shape[2]:].any()
+    # the host-side prepare of the reference API (cv2 as installed: the IPP code path
+    # rounds differently) agrees to 4e-5 of the pixel range
+    host, _, _ = m.prepare(imgs)
+    for i, h in enumerate(host):
+        np.testing.assert_allclose(x[i, :, :h.shape[1], :h.shape[2]], h, rtol=0, atol=1e-2)
+
+
+def test_prepare_golden():
+    """Golden vectors of the reference's own MaskRCNN.prepare (tests/golden/prepare.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prepare.npz'))
+    for k, (H, W, lo, hi) in enumerate(g['cases']):
+        x, sizes, scales = _Prep(int(lo), int(hi))._prepare_device([g['img_%d' % k]])
+        assert scales[0] == float(g['scale_%d' % k])
+        assert tuple(x.shape[2:]) == g['out_%d' % k].shape[1:]
+        np.testing.assert_allclose(x[0].cpu().numpy(), g['out_%d' % k], rtol=0, atol=255e-5)
+
+
+def test_mask_download_buffers():
+    """predict's mask stacks come back as views of page-locked buffers while the budget
+    lasts, pageable memory beyond it; either way the bytes are the device's."""
+    pool = mr._PinnedDownloads(budget=3000)
+    t = torch.arange(2000, dtype=torch.uint8, device='cuda').remainder(2).view(2, 10, 100)
+    a = pool.download(t)
+    assert pool.outstanding == 2000
+    b = pool.download(t)                      # over budget: pageable
+    assert pool.outstanding == 2000
+    np.testing.assert_array_equal(a, t.cpu().numpy())
+    np.testing.assert_array_equal(b, t.cpu().numpy())
+    v = a.view(np.bool_)
+    del a
+    import gc
+    gc.collect()
+    assert pool.outstanding == 2000 and v[0, 0, 1]     # the view keeps the buffer alive
+    del v
+    gc.collect()
+    assert pool.outstanding == 0

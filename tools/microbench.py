@@ -6,6 +6,7 @@ import ctypes
 import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -209,15 +210,38 @@ def bench_infer(out):
     model.score_thresh = 1. / 81. * 1.02
     for bs in (1, 2):
         imgs = [rs.uniform(0, 255, (3, 800, 1333)).astype(np.float32) for _ in range(bs)]
-        model.predict(imgs)
+        for _ in range(3):       # warm-up: also fills the page-locked download buffers
+            bboxes, masks, labels, scores = model.predict(imgs)
         torch.cuda.synchronize()
-        import time
         t0 = time.perf_counter()
-        iters = 5
+        iters = 10
         for _ in range(iters):
             bboxes, masks, labels, scores = model.predict(imgs)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3 / iters
+        # where the end-to-end time goes: each stage of predict bracketed by a device
+        # synchronise (so the sum is a little above the pipelined e2e time)
+        stages = {}
+
+        def timed(obj, name):
+            fn = getattr(obj, name)
+
+            def wrapper(*a, **k):
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize()
+                stages[name] = stages.get(name, 0.) + (time.perf_counter() - t) * 1e3 / 3
+                return r
+            setattr(obj, name, wrapper)
+        names = ('_prepare_device', '_forward_padded', '_detect', '_cut', '_to_roi_masks',
+                 '_to_masks')
+        for n in names:
+            timed(model, n)
+        for _ in range(3):
+            model.predict(imgs)
+        for n in names:
+            delattr(model, n)
         # device part only (network + detections), without the host mask download
         from chainer_mask_rcnn_b200.utils import config
         x = torch.from_numpy(np.stack(model.prepare(imgs)[0])).cuda()
@@ -231,7 +255,8 @@ def bench_infer(out):
         med, best = time_ms(dev_only, iters=10, warmup=2, flush=False)
         rec = dict(kernel='predict_r50_c4', batch=bs, n_det=[len(b) for b in bboxes],
                    ms_per_batch_e2e=ms, images_per_s_e2e=bs / ms * 1e3,
-                   ms_per_batch_box_pass=med, images_per_s_box_pass=bs / med * 1e3)
+                   ms_per_batch_box_pass=med, images_per_s_box_pass=bs / med * 1e3,
+                   stages_ms={k: round(v, 3) for k, v in stages.items()})
         print(json.dumps(rec)); out.append(rec)
 
 
