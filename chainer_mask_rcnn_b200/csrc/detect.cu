@@ -5,10 +5,10 @@
 //                    mask_rcnn.py:178-243): softmax, per-class box decoding (loc2bbox),
 //                    clipping, score threshold and per-class NMS for a whole batch.  The
 //                    reference loops over 80 classes per image calling a NumPy NMS each
-//                    time; here every (RoI, class) pair above the threshold becomes one
-//                    candidate, all candidates of an image are sorted by score once and a
-//                    single class-aware NMS pass (a box only suppresses boxes of its own
-//                    class) resolves all classes together.
+//                    time; here every (image, class) pair is one row of a batch: its
+//                    candidates (RoIs whose class probability exceeds the threshold) are
+//                    sorted by score in shared memory, and ONE batched NMS launch (mask +
+//                    sweep, csrc/nms.cu) resolves all B * (n_class - 1) rows in parallel.
 //   cmr_paste_masks  segm_results (mask_rcnn.py:63-107): every detection's 14x14 mask
 //                    probability map is padded to 16x16, resized (cv2 INTER_LINEAR, fp32)
 //                    to its expanded integer box, thresholded at 0.5 and written into a
@@ -38,19 +38,20 @@ __device__ __forceinline__ float sortable_to_float(unsigned int s) {
   return __uint_as_float((s & 0x80000000u) ? (s & 0x7fffffffu) : ~s);
 }
 
-// One warp per RoI row: softmax over the class logits, keys for the classes above the
-// threshold.  key = sortable(prob) << 32 | (roi * n_class + class); 0 = no candidate.
+// One warp per RoI row: softmax over the class logits, one key per foreground class into
+// that class's candidate row.  keys (B, n_class-1, n_pad): sortable(prob) << 32 | roi for
+// a probability above the threshold, 0 = no candidate (also every roi >= n_roi[img]).
 __global__ void __launch_bounds__(256)
 det_score_kernel(const float* __restrict__ score, int ld_score, const int* __restrict__ n_roi,
                  int max_roi, int n_class, int n_pad, float score_thresh,
-                 unsigned long long* __restrict__ keys, int* __restrict__ n_valid) {
+                 unsigned long long* __restrict__ keys) {
   const int img = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= max_roi) return;
-  unsigned long long* krow = keys + (size_t)img * n_pad + (size_t)r * n_class;
-  if (r >= n_roi[img]) {
-    for (int c = lane; c < n_class; c += 32) krow[c] = 0ull;
+  if (r >= n_pad) return;
+  unsigned long long* kcol = keys + (size_t)img * (n_class - 1) * n_pad + r;
+  if (r >= max_roi || r >= n_roi[img]) {
+    for (int c = 1 + lane; c < n_class; c += 32) kcol[(size_t)(c - 1) * n_pad] = 0ull;
     return;
   }
   const float* x = score + ((size_t)img * max_roi + r) * ld_score;
@@ -60,42 +61,34 @@ det_score_kernel(const float* __restrict__ score, int ld_score, const int* __res
   float s = 0.f;
   for (int c = lane; c < n_class; c += 32) s += expf(__fsub_rn(__ldg(x + c), m));
   for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  int cnt = 0;
   for (int c = lane; c < n_class; c += 32) {
+    if (c == 0) continue;
     const float p = __fdiv_rn(expf(__fsub_rn(__ldg(x + c), m)), s);
-    unsigned long long key = 0ull;
-    if (c >= 1 && p > score_thresh) {
-      key = ((unsigned long long)float_to_sortable(p) << 32) | (unsigned int)(r * n_class + c);
-      ++cnt;
-    }
-    krow[c] = key;
+    kcol[(size_t)(c - 1) * n_pad] =
+        p > score_thresh ? ((unsigned long long)float_to_sortable(p) << 32) | (unsigned int)r : 0ull;
   }
-  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0 && cnt) atomicAdd(n_valid + img, cnt);
 }
 
-// keys beyond max_roi * n_class up to n_pad
-__global__ void det_pad_keys_kernel(unsigned long long* __restrict__ keys, int used, int n_pad) {
-  const int k = used + blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n_pad) keys[(size_t)blockIdx.y * n_pad + k] = 0ull;
-}
-
-// Rank k of the sorted candidates -> decoded, clipped box of (roi, class), label, score.
+// Rank k of class c's sorted candidates -> decoded, clipped box of (roi, c) and its score;
+// the thread standing on the last non-zero key also writes the row's candidate count.
 __global__ void __launch_bounds__(256)
 det_gather_kernel(const unsigned long long* __restrict__ keys, int n_pad,
-                  const int* __restrict__ n_valid, int max_cand, const float* __restrict__ cls_loc,
-                  int ld_loc, const float4* __restrict__ rois, int max_roi, int n_class,
-                  const float* __restrict__ img_info, double4 mean, double4 stdv,
-                  float4* __restrict__ box, int* __restrict__ label, float* __restrict__ prob,
-                  int* __restrict__ n_cand) {
-  const int img = blockIdx.y;
+                  const float* __restrict__ cls_loc, int ld_loc, const float4* __restrict__ rois,
+                  int max_roi, int n_class, const float* __restrict__ img_info, double4 mean,
+                  double4 stdv, float4* __restrict__ box, float* __restrict__ prob,
+                  int* __restrict__ n_valid) {
+  const int img = blockIdx.z, l = blockIdx.y + 1;
+  const int row = img * (n_class - 1) + blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(n_valid[img], max_cand);
-  if (k == 0) n_cand[img] = n;
-  if (k >= n) return;
-  const unsigned long long key = keys[(size_t)img * n_pad + k];
-  const int idx = (int)(key & 0xffffffffull);
-  const int r = idx / n_class, l = idx - r * n_class;
+  if (k >= max_roi) return;
+  const unsigned long long* krow = keys + (size_t)row * n_pad;
+  const unsigned long long key = krow[k];
+  if (key == 0ull) {
+    if (k == 0) n_valid[row] = 0;
+    return;
+  }
+  if (k + 1 >= max_roi || krow[k + 1] == 0ull) n_valid[row] = k + 1;
+  const int r = (int)(key & 0xffffffffull);
   const float scale = __ldg(img_info + 3 * img), H = __ldg(img_info + 3 * img + 1),
               W = __ldg(img_info + 3 * img + 2);
   const float4 rr = __ldg(rois + (size_t)img * max_roi + r);
@@ -118,30 +111,49 @@ det_gather_kernel(const unsigned long long* __restrict__ keys, int n_pad,
   by2 = fminf(fmaxf(by2, 0.f), H);
   bx1 = fminf(fmaxf(bx1, 0.f), W);
   bx2 = fminf(fmaxf(bx2, 0.f), W);
-  const size_t o = (size_t)img * max_cand + k;
+  const size_t o = (size_t)row * max_roi + k;
   box[o] = make_float4(by1, bx1, by2, bx2);
-  label[o] = l;
   prob[o] = sortable_to_float((unsigned int)(key >> 32));
 }
 
-__global__ void __launch_bounds__(256)
-det_emit_kernel(const float4* __restrict__ box, const int* __restrict__ label,
-                const float* __restrict__ prob, const int32_t* __restrict__ keep,
-                const int32_t* __restrict__ n_keep, int max_cand, float4* __restrict__ det_bbox,
+// One CTA per image: the classes' survivor lists are concatenated in class order (the
+// order of the reference's per-class loop, mask_rcnn.py:186-201).
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads)
+det_emit_kernel(const float4* __restrict__ box, const float* __restrict__ prob,
+                const int32_t* __restrict__ keep, const int32_t* __restrict__ n_keep, int max_roi,
+                int n_class, int max_cand, float4* __restrict__ det_bbox,
                 int32_t* __restrict__ det_label, float* __restrict__ det_score,
                 int32_t* __restrict__ n_det) {
-  const int img = blockIdx.y;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = n_keep[img];
-  if (q == 0) n_det[img] = n;
-  if (q >= max_cand) return;
-  const size_t o = (size_t)img * max_cand + q;
-  if (q < n) {
-    const size_t s = (size_t)img * max_cand + keep[o];
-    det_bbox[o] = box[s];
-    det_label[o] = label[s] - 1;      // foreground class ids start at 0 (mask_rcnn.py:196-197)
-    det_score[o] = prob[s];
-  } else {
+  extern __shared__ int offs[];            // n_class entries: exclusive prefix of n_keep
+  const int img = blockIdx.x, t = threadIdx.x;
+  const int n_fg = n_class - 1;
+  if (t == 0) {
+    int acc = 0;
+    for (int c = 0; c < n_fg; ++c) {
+      offs[c] = acc;
+      acc += n_keep[img * n_fg + c];
+    }
+    offs[n_fg] = acc;
+    n_det[img] = min(acc, max_cand);
+  }
+  __syncthreads();
+  const int total = min(offs[n_fg], max_cand);
+  for (int c = 0; c < n_fg; ++c) {
+    const int row = img * n_fg + c;
+    const int n = offs[c + 1] - offs[c];
+    for (int q = t; q < n; q += kEmitThreads) {
+      const int dst = offs[c] + q;
+      if (dst >= max_cand) break;
+      const size_t s = (size_t)row * max_roi + keep[(size_t)row * max_roi + q];
+      const size_t o = (size_t)img * max_cand + dst;
+      det_bbox[o] = box[s];
+      det_label[o] = c;                  // foreground class ids start at 0 (:196-197)
+      det_score[o] = prob[s];
+    }
+  }
+  for (int q = total + t; q < max_cand; q += kEmitThreads) {
+    const size_t o = (size_t)img * max_cand + q;
     det_bbox[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     det_label[o] = -1;
     det_score[o] = 0.f;
@@ -230,28 +242,28 @@ int next_pow2(int v) {
 }
 
 struct DetWs {
-  size_t keys, n_valid, box, label, prob, n_cand, keep, n_keep, mask, total;
-  int n_pad;
+  size_t keys, n_valid, box, prob, keep, n_keep, mask, total;
+  int n_pad, rows;
 };
-DetWs det_ws(int B, int max_roi, int n_class, int max_cand) {
+DetWs det_ws(int B, int max_roi, int n_class) {
   DetWs w;
-  w.n_pad = next_pow2(max_roi * n_class);
+  w.n_pad = next_pow2(max_roi);
+  w.rows = B * (n_class - 1);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off = align_up(off + bytes, 256);
     return o;
   };
-  const size_t nb = (max_cand + 63) / 64;
-  w.keys = take(sizeof(unsigned long long) * (size_t)B * w.n_pad);
-  w.n_valid = take(sizeof(int) * B);
-  w.box = take(sizeof(float4) * (size_t)B * max_cand);
-  w.label = take(sizeof(int) * (size_t)B * max_cand);
-  w.prob = take(sizeof(float) * (size_t)B * max_cand);
-  w.n_cand = take(sizeof(int) * B);
-  w.keep = take(sizeof(int32_t) * (size_t)B * max_cand);
-  w.n_keep = take(sizeof(int32_t) * B);
-  w.mask = take(sizeof(unsigned long long) * (size_t)B * max_cand * nb);
+  const size_t nb = (max_roi + 63) / 64;
+  const size_t rows = w.rows;
+  w.keys = take(sizeof(unsigned long long) * rows * w.n_pad);
+  w.n_valid = take(sizeof(int) * rows);
+  w.box = take(sizeof(float4) * rows * max_roi);
+  w.prob = take(sizeof(float) * rows * max_roi);
+  w.keep = take(sizeof(int32_t) * rows * max_roi);
+  w.n_keep = take(sizeof(int32_t) * rows);
+  w.mask = take(sizeof(unsigned long long) * rows * max_roi * nb);
   w.total = off;
   return w;
 }
@@ -262,8 +274,9 @@ DetWs det_ws(int B, int max_roi, int n_class, int max_cand) {
 using namespace cmr;
 
 extern "C" size_t cmr_detections_workspace_bytes(int B, int max_roi, int n_class, int max_cand) {
-  if (B <= 0 || max_roi <= 0 || n_class <= 1 || max_cand <= 0) return 256;
-  return det_ws(B, max_roi, n_class, max_cand).total;
+  (void)max_cand;
+  if (B <= 0 || max_roi <= 0 || n_class <= 1) return 256;
+  return det_ws(B, max_roi, n_class).total;
 }
 
 extern "C" int cmr_detections(const float* cls_loc, int ld_loc, const float* score, int ld_score,
@@ -275,48 +288,42 @@ extern "C" int cmr_detections(const float* cls_loc, int ld_loc, const float* sco
                               size_t workspace_bytes, void* stream) {
   CMR_REQUIRE(cls_loc && score && rois && n_roi && img_info && loc_mean && loc_std);
   CMR_REQUIRE(det_bbox && det_label && det_score && n_det && workspace);
-  CMR_REQUIRE(B > 0 && B < 65536 && max_roi > 0 && n_class > 1 && max_cand > 0);
+  CMR_REQUIRE(B > 0 && max_roi > 0 && n_class > 1 && max_cand > 0);
+  CMR_REQUIRE((long long)B * (n_class - 1) < 65536 && n_class <= 4096);
   CMR_REQUIRE(ld_loc >= 4 * n_class && ld_score >= n_class);
-  CMR_REQUIRE((long long)max_roi * n_class < (1ll << 24) && max_cand <= 64 * 2048);
+  CMR_REQUIRE(max_roi <= 64 * 2048);
   CMR_REQUIRE(((reinterpret_cast<uintptr_t>(rois) | reinterpret_cast<uintptr_t>(det_bbox)) & 15) == 0);
-  const DetWs w = det_ws(B, max_roi, n_class, max_cand);
+  const DetWs w = det_ws(B, max_roi, n_class);
   if (workspace_bytes < w.total) return CMR_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   char* ws = reinterpret_cast<char*>(workspace);
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
   int* n_valid = reinterpret_cast<int*>(ws + w.n_valid);
   float4* box = reinterpret_cast<float4*>(ws + w.box);
-  int* label = reinterpret_cast<int*>(ws + w.label);
   float* prob = reinterpret_cast<float*>(ws + w.prob);
-  int* n_cand = reinterpret_cast<int*>(ws + w.n_cand);
   int32_t* keep = reinterpret_cast<int32_t*>(ws + w.keep);
   int32_t* n_keep = reinterpret_cast<int32_t*>(ws + w.n_keep);
   unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws + w.mask);
 
-  CMR_CUDA_TRY(cudaMemsetAsync(n_valid, 0, sizeof(int) * B, st));
-  det_score_kernel<<<dim3(ceil_div(max_roi, 8), B), 256, 0, st>>>(
-      score, ld_score, n_roi, max_roi, n_class, w.n_pad, score_thresh, keys, n_valid);
+  det_score_kernel<<<dim3(ceil_div(w.n_pad, 8), B), 256, 0, st>>>(
+      score, ld_score, n_roi, max_roi, n_class, w.n_pad, score_thresh, keys);
   CMR_LAUNCH_CHECK();
-  const int used = max_roi * n_class;
-  if (used < w.n_pad) {
-    det_pad_keys_kernel<<<dim3(ceil_div(w.n_pad - used, 256), B), 256, 0, st>>>(keys, used,
-                                                                              w.n_pad);
-    CMR_LAUNCH_CHECK();
-  }
-  int rc = launch_sort_desc_u64(keys, w.n_pad, B, st);
+  // every (image, class) row is sorted on its own: one shared-memory pass for <= 4096 RoIs
+  int rc = launch_sort_desc_u64(keys, w.n_pad, w.rows, st);
   if (rc != CMR_OK) return rc;
   const double4 mean = make_double4(loc_mean[0], loc_mean[1], loc_mean[2], loc_mean[3]);
   const double4 stdv = make_double4(loc_std[0], loc_std[1], loc_std[2], loc_std[3]);
-  det_gather_kernel<<<dim3(ceil_div(max_cand, 256), B), 256, 0, st>>>(
-      keys, w.n_pad, n_valid, max_cand, cls_loc, ld_loc, reinterpret_cast<const float4*>(rois),
-      max_roi, n_class, img_info, mean, stdv, box, label, prob, n_cand);
+  det_gather_kernel<<<dim3(ceil_div(max_roi, 256), n_class - 1, B), 256, 0, st>>>(
+      keys, w.n_pad, cls_loc, ld_loc, reinterpret_cast<const float4*>(rois), max_roi, n_class,
+      img_info, mean, stdv, box, prob, n_valid);
   CMR_LAUNCH_CHECK();
-  rc = launch_nms_batch(reinterpret_cast<const float*>(box), label, n_cand, max_cand, B,
+  // the (image, class) rows are independent NMS problems: one batched launch
+  rc = launch_nms_batch(reinterpret_cast<const float*>(box), nullptr, n_valid, max_roi, w.rows,
                         nms_thresh, keep, n_keep, mask, st);
   if (rc != CMR_OK) return rc;
-  det_emit_kernel<<<dim3(ceil_div(max_cand, 256), B), 256, 0, st>>>(
-      box, label, prob, keep, n_keep, max_cand, reinterpret_cast<float4*>(det_bbox), det_label,
-      det_score, n_det);
+  det_emit_kernel<<<B, kEmitThreads, sizeof(int) * (n_class + 1), st>>>(
+      box, prob, keep, n_keep, max_roi, n_class, max_cand, reinterpret_cast<float4*>(det_bbox),
+      det_label, det_score, n_det);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -249,8 +249,7 @@ class MaskRCNN(object):
             bbox = det_bbox[i, :n].cpu().numpy()
             label = det_label[i, :n].cpu().numpy()
             score = det_score[i, :n].cpu().numpy()
-            order = np.argsort(label, kind='stable')      # class-major, score order kept
-            out.append((bbox[order], label[order], score[order]))
+            out.append((bbox, label, score))
         return out
 
     def _to_bboxes(self, roi_cls_locs, roi_scores, rois, roi_indices, sizes, scales):

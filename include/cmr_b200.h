@@ -341,16 +341,17 @@ int cmr_mask_targets(const void* masks, int mask_elem_bytes, int B, int max_bbox
 /* MaskRCNN._to_bboxes + _suppress (chainer_mask_rcnn/models/mask_rcnn.py:178-243) for a
  * batch: softmax of the class logits, boxes of every (RoI, class >= 1) pair whose
  * probability exceeds score_thresh decoded against roi / scale (loc * std + mean,
- * loc2bbox) and clipped to the image, then per-class NMS -- done as ONE score-sorted,
- * class-aware NMS pass per image.
+ * loc2bbox) and clipped to the image, then per-class NMS -- every (image, class) pair is
+ * one row of a single batched NMS launch.
  * cls_loc (B*max_roi, ld_loc) holds 4*n_class offsets per RoI, score (B*max_roi,
  * ld_score) n_class logits; rois (B, max_roi, 4) with n_roi (B) valid rows (device);
  * img_info (B, 3) device floats = (scale, height, width) of each original image;
  * loc_mean / loc_std: HOST double[4].
- * Outputs per image, survivors in descending score order (rows >= n_det[b] are padding
- * with label -1): det_bbox (B, max_cand, 4), det_label (B, max_cand) foreground class ids
- * (class - 1), det_score (B, max_cand), n_det (B).  At most max_cand highest-scoring
- * candidates per image enter the NMS. */
+ * Outputs per image in the reference's order -- class by class, descending score inside
+ * a class (rows >= n_det[b] are padding with label -1): det_bbox (B, max_cand, 4),
+ * det_label (B, max_cand) foreground class ids (class - 1), det_score (B, max_cand),
+ * n_det (B).  max_cand is the row capacity of the outputs: max_roi * (n_class - 1) always
+ * suffices (19 * max_roi when score_thresh >= 0.05); survivors beyond it are dropped. */
 size_t cmr_detections_workspace_bytes(int B, int max_roi, int n_class, int max_cand);
 int cmr_detections(const float* cls_loc, int ld_loc, const float* score, int ld_score,
                    const float* rois, const int32_t* n_roi, int B, int max_roi,
