@@ -285,7 +285,8 @@ def main():
     lib.cmr_prof_enable(0)
     import ctypes
     prof = {}
-    for kind, name in ((0, 'conv_gemm_tc'), (1, 'conv_wgrad_tc')):
+    for kind, name in ((0, 'conv_gemm_tc'), (1, 'conv_wgrad_tc'), (2, 'roi_align'),
+                       (3, 'roi_align_bwd')):
         ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         lib.cmr_prof_collect(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt))
         prof[name] = (ms.value, work.value, cnt.value)
@@ -322,6 +323,13 @@ def main():
         tf32_peak = pk['bf16_tflops_sustained'] / 2.0
         achieved = work_k / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
         ms_w, work_w, cnt_w = prof['conv_wgrad_tc']
+        roi = {}
+        for name in ('roi_align', 'roi_align_bwd'):
+            ms_r, work_r, cnt_r = prof[name]
+            gbs = work_r / (ms_r * 1e-3) / 1e9 if ms_r > 0 else 0.0
+            roi[name] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': gbs / pk['hbm_gbs'], 'launches_per_step': cnt_r / args.steps,
+                         'us_per_launch': 1e3 * ms_r / cnt_r if cnt_r else None}
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_per_step,
@@ -346,6 +354,11 @@ def main():
                 'wgrad': {'achieved': work_w / (ms_w * 1e-3) / 1e12 if ms_w > 0 else 0.0,
                           'launches_per_step': cnt_w / args.steps,
                           'share_of_step': ms_w / ms_total if ms_total else None},
+                # the HBM-bound kernel north_star names: ROIAlign launches of the same pass,
+                # algorithmic bytes 4*(R*C*oh*ow + N*C*H*W + 5R) per launch (oh*ow = the 7x7
+                # bins res5's stride-2 convolutions read).  The backward launch runs while
+                # weight-gradient kernels occupy the side stream, so its time is an upper bound.
+                'roi_align': roi['roi_align'], 'roi_align_bwd': roi['roi_align_bwd'],
             },
             'step_tflops': FLOPS_PER_IMAGE[args.layers] * BS * world / (ms_per_step * 1e-3) / 1e12,
             'gpu_launches': int(launches.item()),

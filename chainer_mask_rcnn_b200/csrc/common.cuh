@@ -31,8 +31,8 @@ void count_launch();
 
 // Optional per-launch timing of the tensor-core kernels (cmr_prof_enable): a pair of
 // CUDA events on the launching stream around the launch, plus the launch's algorithmic
-// work (FLOPs), summed by cmr_prof_collect.  Skipped while a stream is being captured.
-enum ProfKind { kProfConvGemm = 0, kProfWgrad = 1, kProfKinds = 2 };
+// work (FLOPs; algorithmic bytes for ROIAlign), summed by cmr_prof_collect.  Skipped while a stream is being captured.
+enum ProfKind { kProfConvGemm = 0, kProfWgrad = 1, kProfRoiAlign = 2, kProfRoiAlignBwd = 3, kProfKinds = 4 };
 void prof_begin(int kind, double work, cudaStream_t st);
 void prof_end(cudaStream_t st);
 

@@ -373,6 +373,14 @@ int nhwc_threads(int C4) { return C4 >= 256 ? 128 : (C4 >= 128 ? 64 : 32); }
 
 using namespace cmr;
 
+namespace {
+// Algorithmic bytes of one ROIAlign pass: the pooled tensor once, the
+// feature map once, the RoI table.
+double roi_align_bytes(int R, int C, int oh, int ow, int N, int H, int W) {
+  return 4.0 * ((double)R * C * oh * ow + (double)N * C * H * W + 5.0 * R);
+}
+}  // namespace
+
 extern "C" int cmr_roi_align_fwd(const float* x, int N, int C, int H, int W, const float* rois,
                                  int R, int outh, int outw, float spatial_scale,
                                  int sampling_ratio, float* y, void* stream) {
@@ -417,9 +425,11 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
   CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  prof_begin(kProfRoiAlign, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
   roi_align_nhwc_kernel<false><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C / 4, outh,
       outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, round_tf32);
+  prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -436,9 +446,11 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
   CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  prof_begin(kProfRoiAlignBwd, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
   roi_align_nhwc_kernel<true><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
       outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, 0);
+  prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }

@@ -39,9 +39,10 @@ const char* cmr_last_cuda_error(void);
 long long cmr_launch_count(void);
 /* Measurement aid for bench.py: when enabled, every tensor-core launch is bracketed
  * by a pair of CUDA events on its stream.  cmr_prof_collect(kind) waits for the
- * recorded launches of `kind` (0 = cmr_conv_gemm_tc, 1 = cmr_conv_wgrad_tc), returns
- * their summed device time (ms), summed algorithmic FLOPs (2*M*N*K per launch, no
- * padding) and count, and forgets them. */
+ * recorded launches of `kind` (0 = cmr_conv_gemm_tc, 1 = cmr_conv_wgrad_tc, 2 =
+ * cmr_roi_align_nhwc_fwd, 3 = cmr_roi_align_nhwc_bwd), returns their summed device time (ms), summed algorithmic
+ * work (FLOPs, 2*M*N*K per launch without padding; for kinds 2 and 3 bytes, 4*(R*C*oh*ow +
+ * N*C*H*W + 5R) per launch) and count, and forgets them. */
 int cmr_prof_enable(int on);
 int cmr_prof_collect(int kind, double* total_ms, double* total_work,
                      long long* launches);
