@@ -236,11 +236,16 @@ proposal_decode_kernel(const float4* __restrict__ loc, const float* __restrict__
 }
 
 // Descending bitonic sort of `rows` independent arrays of n_pad (power of two) 64-bit
-// keys, spread over many CTAs: chunks of kSortChunk keys are sorted / merged in shared
-// memory (one CTA per chunk), and the stages whose partner distance reaches across
-// chunks run as grid-wide passes over the (L2-resident) array, two stages per pass.
-constexpr int kSortThreads = 1024;
-constexpr int kSortChunk = 4096;  // 32 KB of 64-bit keys per CTA
+// keys, spread over many CTAs: chunks of 512 * KPT keys are sorted / merged by one CTA
+// each, and the stages whose partner distance reaches across chunks run as grid-wide
+// passes over the (L2-resident) array, two stages per pass.
+//
+// Inside a chunk thread t keeps the KPT consecutive keys KPT*t .. KPT*t + KPT-1 in
+// registers: stages with partner distance j < KPT are compare-exchanges between a
+// thread's own registers, KPT <= j <= 16*KPT exchange keys with lane (t ^ j/KPT) by warp
+// shuffles, and only j >= 32*KPT goes through shared memory with a CTA barrier per stage
+// (10 of the 78 stages of a 4096-key sort).
+constexpr int kSortThreads = 512;
 
 __device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned long long& b,
                                               bool desc) {
@@ -251,35 +256,72 @@ __device__ __forceinline__ void cmp_swap_desc(unsigned long long& a, unsigned lo
   }
 }
 
-// Stages j = j_hi .. 1 of merge level k on one chunk, in shared memory.
-__device__ __forceinline__ void bitonic_smem_stages(unsigned long long* sk, int chunk, int base,
-                                                    int k, int j_hi) {
-  for (int j = j_hi; j > 0; j >>= 1) {
-    for (int i = threadIdx.x; i < chunk / 2; i += kSortThreads) {
-      const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-      const int hi = lo | j;
-      cmp_swap_desc(sk[lo], sk[hi], ((base + lo) & k) == 0);
-    }
+// Stages j = j_hi .. 1 of merge level k on the chunk held in r (position KPT*t + e of the
+// chunk, global position base + that).
+template <int KPT>
+__device__ __forceinline__ void bitonic_level(unsigned long long (&r)[KPT],
+                                              unsigned long long* sk, int base, int k,
+                                              int j_hi) {
+  constexpr int kChunk = kSortThreads * KPT;
+  const int t = threadIdx.x;
+  int j = j_hi;
+  if (j >= 32 * KPT) {
+#pragma unroll
+    for (int e = 0; e < KPT; ++e) sk[KPT * t + e] = r[e];
     __syncthreads();
+    for (; j >= 32 * KPT; j >>= 1) {
+      for (int i = t; i < kChunk / 2; i += kSortThreads) {
+        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+        cmp_swap_desc(sk[lo], sk[lo | j], ((base + lo) & k) == 0);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < KPT; ++e) r[e] = sk[KPT * t + e];
+  }
+  for (; j >= KPT; j >>= 1) {
+    // k > j >= KPT: all keys of the thread share the direction and the side of the pair
+    const bool take_max = (((KPT * t) & j) == 0) == (((base + KPT * t) & k) == 0);
+#pragma unroll
+    for (int e = 0; e < KPT; ++e) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, r[e], j / KPT);
+      r[e] = ((other > r[e]) == take_max) ? other : r[e];
+    }
+  }
+#pragma unroll
+  for (int jj = KPT / 2; jj >= 1; jj >>= 1) {
+    if (jj > j) continue;              // stages above j_hi belong to earlier calls
+#pragma unroll
+    for (int e = 0; e < KPT; ++e)
+      if ((e & jj) == 0)
+        cmp_swap_desc(r[e], r[e | jj], ((base + KPT * t + e) & k) == 0);
   }
 }
 
 // k_first == 2: full sort of every chunk (levels 2 .. chunk); otherwise the tail
-// (j < chunk) of merge level k_first.  grid = (n_pad / chunk, rows).
+// (j < chunk) of merge level k_first.  grid = (max(1, n_pad / chunk), rows); a row shorter
+// than one chunk is padded with zero keys (they sort to the end).
+template <int KPT>
 __global__ void __launch_bounds__(kSortThreads)
-bitonic_chunk_kernel(unsigned long long* __restrict__ keys_all, int n_pad, int chunk,
-                     int k_first) {
-  extern __shared__ unsigned long long sk[];
-  const int base = blockIdx.x * chunk;
+bitonic_chunk_kernel(unsigned long long* __restrict__ keys_all, int n_pad, int k_first) {
+  constexpr int kChunk = kSortThreads * KPT;
+  __shared__ unsigned long long sk[kChunk];
+  const int base = blockIdx.x * kChunk;
+  const int t = threadIdx.x;
   unsigned long long* keys = keys_all + (size_t)blockIdx.y * n_pad + base;
-  for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = keys[i];
-  __syncthreads();
+  const int n = min(kChunk, n_pad - base);
+  unsigned long long r[KPT];
+#pragma unroll
+  for (int e = 0; e < KPT; ++e) r[e] = KPT * t + e < n ? keys[KPT * t + e] : 0ull;
   if (k_first == 2) {
-    for (int k = 2; k <= chunk; k <<= 1) bitonic_smem_stages(sk, chunk, base, k, k >> 1);
+#pragma unroll 1
+    for (int k = 2; k <= kChunk; k <<= 1) bitonic_level<KPT>(r, sk, base, k, k >> 1);
   } else {
-    bitonic_smem_stages(sk, chunk, base, k_first, chunk >> 1);
+    bitonic_level<KPT>(r, sk, base, k_first, kChunk >> 1);
   }
-  for (int i = threadIdx.x; i < chunk; i += kSortThreads) keys[i] = sk[i];
+#pragma unroll
+  for (int e = 0; e < KPT; ++e)
+    if (KPT * t + e < n) keys[KPT * t + e] = r[e];
 }
 
 // Grid-wide pass: stages j and j/2 of merge level k (j/2 skipped when two == 0).  Each
@@ -383,11 +425,11 @@ int launch_nms_batch(const float* boxes, const int* labels, const int* n_arr, in
 }
 
 // Shared with targets.cu: sorts `rows` independent key arrays of n_pad (power of two).
-int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {
-  const int chunk = n_pad < kSortChunk ? n_pad : kSortChunk;
-  const size_t smem = sizeof(unsigned long long) * chunk;
-  const dim3 cgrid(n_pad / chunk, rows);
-  bitonic_chunk_kernel<<<cgrid, kSortThreads, smem, st>>>(keys, n_pad, chunk, 2);
+template <int KPT>
+int launch_sort_kpt(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {
+  constexpr int chunk = kSortThreads * KPT;
+  const dim3 cgrid(n_pad > chunk ? n_pad / chunk : 1, rows);
+  bitonic_chunk_kernel<KPT><<<cgrid, kSortThreads, 0, st>>>(keys, n_pad, 2);
   CMR_LAUNCH_CHECK();
   for (int k = chunk << 1; k <= n_pad; k <<= 1) {
     int j = k >> 1;
@@ -399,10 +441,18 @@ int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStre
       CMR_LAUNCH_CHECK();
       j >>= two ? 2 : 1;
     }
-    bitonic_chunk_kernel<<<cgrid, kSortThreads, smem, st>>>(keys, n_pad, chunk, k);
+    bitonic_chunk_kernel<KPT><<<cgrid, kSortThreads, 0, st>>>(keys, n_pad, k);
     CMR_LAUNCH_CHECK();
   }
   return CMR_OK;
+}
+
+int launch_sort_desc_u64(unsigned long long* keys, int n_pad, int rows, cudaStream_t st) {
+  if (n_pad <= 0 || (n_pad & (n_pad - 1)) != 0 || rows <= 0 || rows > 65535)
+    return CMR_ERR_INVALID_ARG;
+  if (n_pad >= kSortThreads * 8) return launch_sort_kpt<8>(keys, n_pad, rows, st);
+  if (n_pad >= kSortThreads * 4) return launch_sort_kpt<4>(keys, n_pad, rows, st);
+  return launch_sort_kpt<2>(keys, n_pad, rows, st);
 }
 }  // namespace cmr
 
