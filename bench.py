@@ -125,14 +125,31 @@ class ClockSampler(object):
         return out
 
 
+class all_host_threads(object):
+    """Gives NumPy's BLAS every host core for the CPU legs (torchrun exports
+    OMP_NUM_THREADS=1 to its workers); `.threads` is what the BLAS pool then reports."""
+
+    def __enter__(self):
+        from threadpoolctl import threadpool_info, threadpool_limits
+        self._limits = threadpool_limits(limits=os.cpu_count(), user_api='blas')
+        blas = [d['num_threads'] for d in threadpool_info() if d.get('user_api') == 'blas']
+        self.threads = max(blas) if blas else 1
+        return self
+
+    def __exit__(self, *exc):
+        self._limits.restore_original_limits()
+        return False
+
+
 def cpu_baseline(budget_s=12.0, n_layers=50):
     """The oracle port of the reference CPU path on a bounded sample (oracle/cpu_step.py)."""
     from oracle import cpu_step
-    f = cpu_step.calibrate_fraction(budget_s)
-    s = cpu_step.CpuStepSample(f, n_layers=n_layers)
-    s.step()                                   # warm the BLAS threads / page in buffers
-    t = s.step()
-    return {'value': s.images_per_second(t), 'unit': 'images/s', 'cores': os.cpu_count(),
+    with all_host_threads() as pool:
+        f = cpu_step.calibrate_fraction(budget_s)
+        s = cpu_step.CpuStepSample(f, n_layers=n_layers)
+        s.step()                                   # warm the BLAS threads / page in buffers
+        t = s.step()
+    return {'value': s.images_per_second(t), 'unit': 'images/s', 'cores': pool.threads,
             'kind': 'port',
             'sample': '%.4f of one image: %dx%d crop through backbone+RPN and %d RoIs through '
                       'the res5 head, forward+backward, %.1f s; NumPy im2col + BLAS sgemm '
@@ -148,11 +165,12 @@ def run_reference(args, rank, world):
     from oracle import cpu_step
     total = max(args.steps + args.warmup, 1)
     budget = min(15.0, 150.0 / total)
-    f = cpu_step.calibrate_fraction(budget)
-    s = cpu_step.CpuStepSample(f, n_layers=args.layers)
-    for _ in range(args.warmup):
-        s.step()
-    ts = [s.step() for _ in range(args.steps)]
+    with all_host_threads() as pool:
+        f = cpu_step.calibrate_fraction(budget)
+        s = cpu_step.CpuStepSample(f, n_layers=args.layers)
+        for _ in range(args.warmup):
+            s.step()
+        ts = [s.step() for _ in range(args.steps)]
     sec = float(np.mean(ts))
     v = s.images_per_second(sec)
     sample = ('%.4f of one image per step (%dx%d crop, %d RoIs), forward+backward, linearly '
@@ -163,7 +181,7 @@ def run_reference(args, rank, world):
         'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args.gpus, args.layers),
-        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': os.cpu_count(), 'kind': 'port',
+        'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': pool.threads, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
