@@ -297,14 +297,19 @@ def main():
         loss = opt.update(chain, imgs_dev, bboxes, labels, masks_dev, scales)
         losses.append(loss.array)
 
+    # (weight gradients on the main stream for this pass: a kernel's own rate is what the
+    # roofline is about, not the rate it gets while sharing the SMs with another stream)
+    os.environ['CMR_GRAD_SIDE'] = '0'
     step_eager()
     lib.cmr_prof_enable(1)
     ms_eager, _ = timed(step_eager, args.steps)
     lib.cmr_prof_enable(0)
+    os.environ.pop('CMR_GRAD_SIDE')
     import ctypes
     prof = {}
-    for kind, name in ((0, 'conv_gemm_tc'), (1, 'conv_wgrad_tc'), (2, 'roi_align'),
-                       (3, 'roi_align_bwd')):
+    # the two secondary views of the conv_gemm launches are collected before kind 0
+    for kind, name in ((4, 'conv_tensor_bound'), (5, 'conv_hbm_bound'), (0, 'conv_gemm_tc'),
+                       (1, 'conv_wgrad_tc'), (2, 'roi_align'), (3, 'roi_align_bwd')):
         ms, work, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         lib.cmr_prof_collect(kind, ctypes.byref(ms), ctypes.byref(work), ctypes.byref(cnt))
         prof[name] = (ms.value, work.value, cnt.value)
@@ -348,6 +353,23 @@ def main():
             roi[name] = {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                          'frac': gbs / pk['hbm_gbs'], 'launches_per_step': cnt_r / args.steps,
                          'us_per_launch': 1e3 * ms_r / cnt_r if cnt_r else None}
+        # conv_gemm launches split by what bounds them (arithmetic intensity against the
+        # machine balance, csrc/conv_tc.cu): long reductions against the tensor peak, short
+        # reductions with residual / mask operands against the HBM peak
+        ms_t, work_t, cnt_t = prof['conv_tensor_bound']
+        ms_h, work_h, cnt_h = prof['conv_hbm_bound']
+        tf_t = work_t / (ms_t * 1e-3) / 1e12 if ms_t > 0 else 0.0
+        gb_h = work_h / (ms_h * 1e-3) / 1e9 if ms_h > 0 else 0.0
+        split = {
+            'tensor_bound_launches': {'achieved': tf_t, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                                      'frac': tf_t / tf32_peak if tf32_peak else None,
+                                      'launches_per_step': cnt_t / args.steps,
+                                      'ms_per_step': ms_t / args.steps},
+            'hbm_bound_launches': {'achieved': gb_h, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                   'frac': gb_h / pk['hbm_gbs'],
+                                   'launches_per_step': cnt_h / args.steps,
+                                   'ms_per_step': ms_h / args.steps},
+        }
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': warmup, 'ms_per_step': ms_per_step,
@@ -367,16 +389,17 @@ def main():
                 'launches_per_step': cnt_k / args.steps,
                 'share_of_step': ms_k / ms_total if ms_total else None,
                 'measured_in': 'second pass of the same %d steps launched eagerly with '
-                               'per-launch CUDA events (%.2f ms/step; the timed region replays '
-                               'a CUDA graph)' % (args.steps, ms_eager / args.steps),
+                               'per-launch CUDA events on one stream (%.2f ms/step; the timed '
+                               'region replays a CUDA graph with the weight gradients on a '
+                               'side stream)' % (args.steps, ms_eager / args.steps),
                 'wgrad': {'achieved': work_w / (ms_w * 1e-3) / 1e12 if ms_w > 0 else 0.0,
                           'launches_per_step': cnt_w / args.steps,
                           'share_of_step': ms_w / ms_total if ms_total else None},
                 # the HBM-bound kernel north_star names: ROIAlign launches of the same pass,
                 # algorithmic bytes 4*(R*C*oh*ow + N*C*H*W + 5R) per launch (oh*ow = the 7x7
-                # bins res5's stride-2 convolutions read).  The backward launch runs while
-                # weight-gradient kernels occupy the side stream, so its time is an upper bound.
+                # bins res5's stride-2 convolutions read)
                 'roi_align': roi['roi_align'], 'roi_align_bwd': roi['roi_align_bwd'],
+                'split': split,
             },
             'step_tflops': FLOPS_PER_IMAGE[args.layers] * BS * world / (ms_per_step * 1e-3) / 1e12,
             'gpu_launches': int(launches.item()),

@@ -32,8 +32,15 @@ void count_launch();
 // Optional per-launch timing of the tensor-core kernels (cmr_prof_enable): a pair of
 // CUDA events on the launching stream around the launch, plus the launch's algorithmic
 // work (FLOPs; algorithmic bytes for ROIAlign), summed by cmr_prof_collect.  Skipped while a stream is being captured.
-enum ProfKind { kProfConvGemm = 0, kProfWgrad = 1, kProfRoiAlign = 2, kProfRoiAlignBwd = 3, kProfKinds = 4 };
+enum ProfKind {
+  kProfConvGemm = 0, kProfWgrad = 1, kProfRoiAlign = 2, kProfRoiAlignBwd = 3,
+  // secondary views of the kProfConvGemm launches, split by what bounds them (prof_tag)
+  kProfConvTensorBound = 4,   // work = FLOPs
+  kProfConvHbmBound = 5,      // work = algorithmic bytes
+  kProfKinds = 6
+};
 void prof_begin(int kind, double work, cudaStream_t st);
+void prof_tag(int kind2, double work2);   // between prof_begin and prof_end
 void prof_end(cudaStream_t st);
 
 #define CMR_REQUIRE(cond)                 \

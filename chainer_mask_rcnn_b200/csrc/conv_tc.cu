@@ -66,6 +66,7 @@ struct ConvGemmParams {
   int tma_a;   // A tiles by TMA: 1 = im2col-mode map, 2 = tiled-mode map (plain matrix);
                // 0 = cp.async gathers
   int epi_groups;   // epilogue warps per TMEM lane quarter: 3 with TMA A tiles, else 2
+  double alg_bytes; // host only: algorithmic HBM bytes of the launch (profiling)
 };
 
 constexpr int kBM = 128;
@@ -613,7 +614,12 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  prof_begin(kProfConvGemm, 2.0 * p.M * (double)p.N * p.K, st);
+  const double flops = 2.0 * p.M * (double)p.N * p.K;
+  prof_begin(kProfConvGemm, flops, st);
+  // the launch is tensor-bound when its arithmetic intensity exceeds the machine balance
+  // (TF32 ~706 TFLOP/s over ~6.45 TB/s measured on this pool: 110 FLOP per byte)
+  if (flops >= 110.0 * p.alg_bytes) prof_tag(kProfConvTensorBound, flops);
+  else prof_tag(kProfConvHbmBound, p.alg_bytes);
   cudaError_t e =
       cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI>, tmap, tmap_a, q);
   prof_end(st);
@@ -675,6 +681,14 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
   p.d_oy = c->d_oy; p.d_ox = c->d_ox;
   p.tap_cols = c->tap_cols;
   p.scale = scale; p.bias = bias; p.addend = addend; p.mask = mask;
+  {
+    // activations once (the pixels the filter touches), filter once, output once, plus the
+    // epilogue operands
+    const double in_px = (double)c->batch * c->in_h * c->in_w * c->in_c;
+    const double mk = (double)p.M * p.K, mn = (double)p.M * p.N;
+    p.alg_bytes = 4.0 * ((in_px < mk ? in_px : mk) + (double)p.N * p.K +
+                         mn * (1 + (addend != nullptr) + (mask != nullptr)));
+  }
   p.bcast = bcast; p.bcast_group = bcast_group; p.bcast_scale = bcast_scale;
   p.relu = c->relu; p.round_out = c->round_tf32;
   CMR_REQUIRE(p.d_stride >= 1 && p.tap_cols >= 0);

@@ -16,6 +16,8 @@ struct ProfRec {
   cudaEvent_t a, b;
   int kind;
   double work;
+  int kind2;      // optional second classification of the same launch (prof_tag), -1 = none
+  double work2;
 };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -47,9 +49,19 @@ void prof_begin(int kind, double work, cudaStream_t st) {
   g_cur.b = take_event();
   g_cur.kind = kind;
   g_cur.work = work;
+  g_cur.kind2 = -1;
+  g_cur.work2 = 0.0;
   if (!g_cur.a || !g_cur.b) return;
   cudaEventRecord(g_cur.a, st);
   g_open = true;
+}
+
+void prof_tag(int kind2, double work2) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_open) return;
+  g_cur.kind2 = kind2;
+  g_cur.work2 = work2;
 }
 
 void prof_end(cudaStream_t st) {
@@ -108,8 +120,8 @@ extern "C" int cmr_prof_collect(int kind, double* total_ms, double* total_work,
   double ms = 0.0, work = 0.0;
   long long n = 0;
   std::vector<cmr::ProfRec> keep;
-  for (const cmr::ProfRec& r : cmr::g_recs) {
-    if (r.kind != kind) {
+  for (cmr::ProfRec r : cmr::g_recs) {
+    if (r.kind != kind && r.kind2 != kind) {
       keep.push_back(r);
       continue;
     }
@@ -117,8 +129,14 @@ extern "C" int cmr_prof_collect(int kind, double* total_ms, double* total_work,
     float t = 0.f;
     CMR_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
-    work += r.work;
     ++n;
+    if (r.kind2 == kind) {     // secondary view: the record stays for its primary kind
+      work += r.work2;
+      r.kind2 = -1;
+      keep.push_back(r);
+      continue;
+    }
+    work += r.work;
     cmr::g_free.push_back(r.a);
     cmr::g_free.push_back(r.b);
   }

@@ -37,12 +37,18 @@ int cmr_version(void);
 const char* cmr_last_cuda_error(void);
 /* Number of CUDA kernels this library has launched in this process so far. */
 long long cmr_launch_count(void);
-/* Measurement aid for bench.py: when enabled, every tensor-core launch is bracketed
- * by a pair of CUDA events on its stream.  cmr_prof_collect(kind) waits for the
- * recorded launches of `kind` (0 = cmr_conv_gemm_tc, 1 = cmr_conv_wgrad_tc, 2 =
- * cmr_roi_align_nhwc_fwd, 3 = cmr_roi_align_nhwc_bwd), returns their summed device time (ms), summed algorithmic
- * work (FLOPs, 2*M*N*K per launch without padding; for kinds 2 and 3 bytes, 4*(R*C*oh*ow +
- * N*C*H*W + 5R) per launch) and count, and forgets them. */
+/* Measurement aid for bench.py: when enabled, every tensor-core and ROIAlign launch is
+ * bracketed by a pair of CUDA events on its stream (not while the stream is captured).
+ * cmr_prof_collect(kind) waits for the recorded launches of `kind`, returns their summed
+ * device time (ms), summed algorithmic work and count, and forgets them.  Kinds:
+ *   0 cmr_conv_gemm_tc[_ex]   work = FLOPs, 2*M*N*K per launch without padding
+ *   1 cmr_conv_wgrad_tc       work = FLOPs
+ *   2 cmr_roi_align_nhwc_fwd  work = bytes, 4*(R*C*oh*ow + N*C*H*W + 5R)
+ *   3 cmr_roi_align_nhwc_bwd  work = bytes, same formula
+ *   4 / 5 the kind-0 launches again, split by what bounds them: 4 = tensor-bound (FLOPs
+ *     >= 110 x algorithmic bytes; work = FLOPs), 5 = HBM-bound (work = algorithmic bytes:
+ *     activations, filter, output, residual and mask operands once each).  Collect 4 and
+ *     5 before 0. */
 int cmr_prof_enable(int on);
 int cmr_prof_collect(int kind, double* total_ms, double* total_work,
                      long long* launches);
