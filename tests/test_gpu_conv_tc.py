@@ -84,6 +84,7 @@ CASES = [
     (8, 48, 50, 1024, 256, 1, 1, 0, 256),   # CTA-pair path (cta_group::2): 75 x 1 tiles of 256 rows
     (4, 70, 70, 128, 512, 3, 1, 1, 256),    # CTA-pair path, 3x3, ragged last tile, 2 column tiles
     (2, 51, 84, 128, 256, 3, 1, 1, 128),    # res4 3x3 geometry, 128-wide tiles
+    (8, 48, 50, 256, 512, 1, 1, 0, 256),    # short reduction (K = 256), 150 x 2 tiles: 3 epilogue groups, 2 tiles per CTA
 ]
 
 
@@ -120,6 +121,25 @@ def test_fused_epilogue():
     got = conv_tc(x, w, 1, 1, round_out=True)
     assert torch.equal(got, round_tf32(got))
     assert rel(got, base) <= 1e-3
+
+
+def test_short_reduction_epilogue_many_tiles():
+    """res5 conv3 geometry (1x1, K = 512, wide N) with several tiles per persistent CTA
+    (both TMEM accumulator buffers in flight, three epilogue groups): affine + residual +
+    ReLU, and the masked data gradient."""
+    g = torch.Generator(device='cuda').manual_seed(9)
+    B, H, W, C, N = 400, 7, 7, 512, 1024          # 77 pair tiles x 4 column tiles
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    w = round_tf32(torch.randn((N, 1, 1, C), device='cuda', generator=g) / 22)
+    scale = torch.rand((N,), device='cuda', generator=g) + 0.5
+    bias = torch.randn((N,), device='cuda', generator=g)
+    addend = torch.randn((B, H, W, N), device='cuda', generator=g)
+    mask = torch.randn((B, H, W, N), device='cuda', generator=g)
+    base = ref_conv(x, w, 1, 0)
+    got = conv_tc(x, w, 1, 0, scale=scale, bias=bias, addend=addend, relu=True, tile_n=256)
+    assert rel(got, torch.relu(base * scale + bias + addend)) <= 1e-4
+    got = conv_tc(x, w, 1, 0, addend=addend, mask=mask, tile_n=256)
+    assert rel(got, (base + addend) * (mask > 0)) <= 1e-4
 
 
 def test_strided_scatter_output():
