@@ -110,8 +110,10 @@ struct TapSource {
   }
 };
 
+// only_ph >= 0: the CTA reads the vertical taps of that output row only.
 __device__ __forceinline__ TapSource make_taps(TapTables& tt, const RoiGeom& g, int outh,
-                                               int outw, int H, int W, int y_mul, int x_mul) {
+                                               int outw, int H, int W, int y_mul, int x_mul,
+                                               int only_ph = -1) {
   TapSource ts;
   ts.tt = &tt;
   ts.g = g;
@@ -121,7 +123,9 @@ __device__ __forceinline__ TapSource make_taps(TapTables& tt, const RoiGeom& g, 
   ts.x_mul = x_mul;
   ts.tabled = (long long)outh * g.grid_h <= kMaxTaps && (long long)outw * g.grid_w <= kMaxTaps;
   if (ts.tabled) {
-    for (int e = threadIdx.x; e < outh * g.grid_h; e += blockDim.x) {
+    const int y_first = only_ph >= 0 ? only_ph * g.grid_h : 0;
+    const int y_end = only_ph >= 0 ? y_first + g.grid_h : outh * g.grid_h;
+    for (int e = y_first + threadIdx.x; e < y_end; e += blockDim.x) {
       const int ph = e / g.grid_h;
       tt.y[e] = packed_tap(g.start_h, g.bin_h, ph, e - ph * g.grid_h, g.grid_h, H, y_mul);
     }
@@ -267,95 +271,286 @@ __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
 }
 
 // One CTA per (RoI, produced output row); lanes over channels as float4, two channel
-// quads per thread (c and c + blockDim.x) so that the sample geometry -- table lookups,
-// the four bilinear weights and offsets -- is computed once per 8 channels.  The division
-// by the sample count is a multiplication by its reciprocal (exact when the count is a
-// power of two, else within 1 ulp of the reference's division; the NCHW drop-in kernels
-// keep the exact division).
-// forward: src = x (N,H,W,C), dst = y;   backward: src = gy, dst = gx.
-template <bool kBackward>
+// quads per thread (c and c + blockDim.x) so that the sample geometry is looked up once
+// per 8 channels.
+//
+// The bilinear sum is evaluated separably.  Every sample of an output row uses the same
+// vertical taps, so a feature column enters the row only through its vertical blend
+//     g[x] = sum over iy of  hy(iy) * f[y_low(iy)][x] + ly(iy) * f[y_high(iy)][x],
+// and bin (ph, pw) = 1/count * sum over ix of  hx(ix) * g[x_low(ix)] + lx(ix) * g[x_high(ix)].
+// The samples of a row run left to right, so the thread keeps just the two blended columns
+// under the current sample in registers and fetches a feature column (2 * grid_h loads)
+// only when the window moves: 2 * grid_h * (columns the RoI spans) loads per row instead of
+// 4 * grid_h * grid_w * pooled_w -- neighbouring bins of all but the largest RoIs share
+// their columns, and those re-reads were what bound the kernel (L1 bandwidth).  Same
+// products as the reference, summed in a different order (<= a few ulp apart; the NCHW
+// drop-in kernels keep the reference's order).  The division by the sample count is a
+// multiplication by its reciprocal.
+// acc += w * v on a channel quad as two packed FFMA2 (sm_100: two fp32 FMAs per issue
+// slot; the kernels below are issue-bound).  Same single rounding as the scalar FMA.
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  asm("{\n"
+      ".reg .b64 a, b, ww, p, q;\n"
+      "mov.b64 ww, {%8, %8};\n"
+      "mov.b64 a, {%0, %1};\n"
+      "mov.b64 b, {%2, %3};\n"
+      "mov.b64 p, {%4, %5};\n"
+      "mov.b64 q, {%6, %7};\n"
+      "fma.rn.f32x2 a, ww, p, a;\n"
+      "fma.rn.f32x2 b, ww, q, b;\n"
+      "mov.b64 {%0, %1}, a;\n"
+      "mov.b64 {%2, %3}, b;\n"
+      "}"
+      : "+f"(acc.x), "+f"(acc.y), "+f"(acc.z), "+f"(acc.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w));
+}
+
+// Taps of one output row / of all output columns as the row kernels walk them: from the
+// CTA's shared-memory tables (kTabled, the case for every RoI that fits the image) or
+// recomputed on the fly (RoIs more than kMaxTaps / pooled samples tall or wide).
+template <bool kTabled>
+struct RowTaps {
+  const float4* ytab;       // grid_h entries of row ph
+  const float4* xtab;       // pooled_w * grid_w entries
+  RoiGeom g;
+  int ph, H, W, y_mul, x_mul;
+  __device__ __forceinline__ float4 y(int iy) const {
+    if (kTabled) return ytab[iy];
+    return packed_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, y_mul);
+  }
+  __device__ __forceinline__ float4 x(int pw, int ix) const {
+    if (kTabled) return xtab[pw * g.grid_w + ix];
+    return packed_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, x_mul);
+  }
+};
+
+template <bool kTabled>
+__device__ __forceinline__ RowTaps<kTabled> row_taps(const TapTables& tt, const RoiGeom& g,
+                                                     int ph, int H, int W, int y_mul,
+                                                     int x_mul) {
+  RowTaps<kTabled> t;
+  t.ytab = tt.y + ph * g.grid_h;
+  t.xtab = tt.x;
+  t.g = g;
+  t.ph = ph; t.H = H; t.W = W; t.y_mul = y_mul; t.x_mul = x_mul;
+  return t;
+}
+
+// g = vertical blend of the feature column at `col` (its pixel in image row 0; col1 = the
+// thread's second channel quad) for the CTA's output row.
+// (The row kernels keep tap offsets in BYTES, so that an address is one 64-bit add.)
+__device__ __forceinline__ const float4* at(const char* base, int byte_off) {
+  return reinterpret_cast<const float4*>(base + byte_off);
+}
+__device__ __forceinline__ float4* at(char* base, int byte_off) {
+  return reinterpret_cast<float4*>(base + byte_off);
+}
+
+template <bool kTabled>
+__device__ __forceinline__ void blend_column(const RowTaps<kTabled>& taps, int grid_h,
+                                             const char* __restrict__ col,
+                                             const char* __restrict__ col1, bool two,
+                                             float4& g0, float4& g1) {
+  g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  g1 = g0;
+  for (int iy = 0; iy < grid_h; ++iy) {
+    const float4 ty = taps.y(iy);
+    const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
+    if (yl < 0) continue;
+    const float4 v = __ldg(at(col, yl)), u = __ldg(at(col, yh));
+    if (two) {
+      const float4 v1 = __ldg(at(col1, yl)), u1 = __ldg(at(col1, yh));
+      fma4(g1, ty.w, v1);
+      fma4(g1, ty.z, u1);
+    }
+    fma4(g0, ty.w, v);
+    fma4(g0, ty.z, u);
+  }
+}
+
+template <bool kTabled>
+__device__ __forceinline__ void roi_align_fwd_row(const RowTaps<kTabled>& taps,
+                                                  const float4* __restrict__ img,
+                                                  float4* __restrict__ out, int C4, int T,
+                                                  int ow_s, int bin_stride, float inv,
+                                                  int round_out) {
+  const int grid_h = taps.g.grid_h, grid_w = taps.g.grid_w;
+  for (int c = threadIdx.x; c < C4; c += 2 * T) {
+    const bool two = c + T < C4;
+    const char* img0 = reinterpret_cast<const char*>(img + c);
+    const char* img1 = reinterpret_cast<const char*>(img + c + T);
+    float4* o = out + c;
+    int lo = -1, hi = -1;                       // x offsets of the two cached blended columns
+    float4 g0lo, g1lo, g0hi, g1hi;
+    g0lo = g1lo = g0hi = g1hi = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < ow_s; ++q, o += C4) {
+      const int pw = q * bin_stride;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      for (int ix = 0; ix < grid_w; ++ix) {
+        const float4 tx = taps.x(pw, ix);
+        const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+        if (xl < 0) continue;
+        if (xl != lo) {
+          if (xl == hi) {
+            g0lo = g0hi; g1lo = g1hi;
+          } else {
+            blend_column<kTabled>(taps, grid_h, img0 + xl, img1 + xl, two, g0lo, g1lo);
+          }
+          lo = xl;
+          hi = -1;
+        }
+        if (xh != hi) {
+          if (xh == lo) {                       // right border: both taps on the last column
+            g0hi = g0lo; g1hi = g1lo;
+          } else {
+            blend_column<kTabled>(taps, grid_h, img0 + xh, img1 + xh, two, g0hi, g1hi);
+          }
+          hi = xh;
+        }
+        fma4(a0, tx.w, g0lo);
+        fma4(a0, tx.z, g0hi);
+        fma4(a1, tx.w, g1lo);
+        fma4(a1, tx.z, g1hi);
+      }
+      float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+      float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
+      if (round_out) {
+        o0.x = round_tf32_rn(o0.x); o0.y = round_tf32_rn(o0.y);
+        o0.z = round_tf32_rn(o0.z); o0.w = round_tf32_rn(o0.w);
+        o1.x = round_tf32_rn(o1.x); o1.y = round_tf32_rn(o1.y);
+        o1.z = round_tf32_rn(o1.z); o1.w = round_tf32_rn(o1.w);
+      }
+      o[0] = o0;
+      if (two) o[T] = o1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
-roi_align_nhwc_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
-                      float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
-                      int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
-                      int round_out) {
+roi_align_nhwc_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
+                          float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
+                          int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
+                          int round_out) {
   __shared__ TapTables tt;
   const int r = blockIdx.x / oh_s;
   const int row = blockIdx.x - r * oh_s;
   const int ph = row * bin_stride;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
-  const TapSource taps = make_taps(tt, g, outh, outw, H, W, W * C4, C4);
-  const size_t img_off = (size_t)g.batch * H * W * C4;
+  const TapSource ts = make_taps(tt, g, outh, outw, H, W, W * C4 * 16, C4 * 16, ph);
+  const float4* img = src + (size_t)g.batch * H * W * C4;
+  float4* out = dst + ((size_t)r * oh_s + row) * ow_s * C4;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
-  const size_t bin0 = ((size_t)r * oh_s + row) * ow_s;
-  const int T = blockDim.x;
+  if (ts.tabled)
+    roi_align_fwd_row<true>(row_taps<true>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), img, out, C4,
+                            blockDim.x, ow_s, bin_stride, inv, round_out);
+  else
+    roi_align_fwd_row<false>(row_taps<false>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), img, out, C4,
+                             blockDim.x, ow_s, bin_stride, inv, round_out);
+}
 
-  for (int c = threadIdx.x; c < C4; c += 2 * T) {
-    const bool two = c + T < C4;
-    for (int q = 0; q < ow_s; ++q) {
-      const int pw = q * bin_stride;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;   // fwd: sums; bwd: scaled gy
-      if (kBackward) {
-        a0 = __ldg(src + (bin0 + q) * C4 + c);
-        a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
-        if (two) {
-          a1 = __ldg(src + (bin0 + q) * C4 + c + T);
-          a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
-        }
-      }
-      for (int iy = 0; iy < g.grid_h; ++iy) {
-        const float4 ty = taps.y(ph, iy);
-        const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
-        if (yl < 0) continue;
-        for (int ix = 0; ix < g.grid_w; ++ix) {
-          const float4 tx = taps.x(pw, ix);
-          const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
-          if (xl < 0) continue;
-          const float w[4] = {ty.w * tx.w, ty.w * tx.z, ty.z * tx.w, ty.z * tx.z};
-          const int o[4] = {yl + xl, yl + xh, yh + xl, yh + xh};
-          if (!kBackward) {
-            const float4* img = src + img_off + c;
-            const float4 v1 = __ldg(img + o[0]), v2 = __ldg(img + o[1]);
-            const float4 v3 = __ldg(img + o[2]), v4 = __ldg(img + o[3]);
-            a0.x += w[0] * v1.x + w[1] * v2.x + w[2] * v3.x + w[3] * v4.x;
-            a0.y += w[0] * v1.y + w[1] * v2.y + w[2] * v3.y + w[3] * v4.y;
-            a0.z += w[0] * v1.z + w[1] * v2.z + w[2] * v3.z + w[3] * v4.z;
-            a0.w += w[0] * v1.w + w[1] * v2.w + w[2] * v3.w + w[3] * v4.w;
-            if (two) {
-              const float4 u1 = __ldg(img + o[0] + T), u2 = __ldg(img + o[1] + T);
-              const float4 u3 = __ldg(img + o[2] + T), u4 = __ldg(img + o[3] + T);
-              a1.x += w[0] * u1.x + w[1] * u2.x + w[2] * u3.x + w[3] * u4.x;
-              a1.y += w[0] * u1.y + w[1] * u2.y + w[2] * u3.y + w[3] * u4.y;
-              a1.z += w[0] * u1.z + w[1] * u2.z + w[2] * u3.z + w[3] * u4.z;
-              a1.w += w[0] * u1.w + w[1] * u2.w + w[2] * u3.w + w[3] * u4.w;
-            }
-          } else {
-            float4* img = dst + img_off + c;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              red_add_f4(img + o[k],
-                         make_float4(a0.x * w[k], a0.y * w[k], a0.z * w[k], a0.w * w[k]));
-              if (two)
-                red_add_f4(img + o[k] + T,
-                           make_float4(a1.x * w[k], a1.y * w[k], a1.z * w[k], a1.w * w[k]));
-            }
-          }
-        }
-      }
-      if (!kBackward) {
-        float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
-        float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
-        if (round_out) {
-          o0.x = round_tf32_rn(o0.x); o0.y = round_tf32_rn(o0.y);
-          o0.z = round_tf32_rn(o0.z); o0.w = round_tf32_rn(o0.w);
-          o1.x = round_tf32_rn(o1.x); o1.y = round_tf32_rn(o1.y);
-          o1.z = round_tf32_rn(o1.z); o1.w = round_tf32_rn(o1.w);
-        }
-        dst[(bin0 + q) * C4 + c] = o0;
-        if (two) dst[(bin0 + q) * C4 + c + T] = o1;
-      }
+// Backward, the transpose of the above: the gradients of a row's bins are first gathered
+// per feature column (h[x] = sum of hx * gy over the samples whose low tap is x, lx * gy
+// over those whose high tap is x), and a column is scattered through the vertical taps
+// when the window leaves it: 2 * grid_h vector reductions per column of the RoI.
+template <bool kTabled>
+__device__ __forceinline__ void scatter_column(const RowTaps<kTabled>& taps, int grid_h,
+                                               char* __restrict__ col,
+                                               char* __restrict__ col1, bool two,
+                                               const float4& h0, const float4& h1) {
+  for (int iy = 0; iy < grid_h; ++iy) {
+    const float4 ty = taps.y(iy);
+    const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
+    if (yl < 0) continue;
+    red_add_f4(at(col, yl), make_float4(h0.x * ty.w, h0.y * ty.w, h0.z * ty.w, h0.w * ty.w));
+    red_add_f4(at(col, yh), make_float4(h0.x * ty.z, h0.y * ty.z, h0.z * ty.z, h0.w * ty.z));
+    if (two) {
+      red_add_f4(at(col1, yl), make_float4(h1.x * ty.w, h1.y * ty.w, h1.z * ty.w, h1.w * ty.w));
+      red_add_f4(at(col1, yh), make_float4(h1.x * ty.z, h1.y * ty.z, h1.z * ty.z, h1.w * ty.z));
     }
   }
+}
+
+template <bool kTabled>
+__device__ __forceinline__ void roi_align_bwd_row(const RowTaps<kTabled>& taps,
+                                                  const float4* __restrict__ gyrow,
+                                                  float4* __restrict__ img, int C4, int T,
+                                                  int ow_s, int bin_stride, float inv) {
+  const int grid_h = taps.g.grid_h, grid_w = taps.g.grid_w;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = threadIdx.x; c < C4; c += 2 * T) {
+    const bool two = c + T < C4;
+    char* img0 = reinterpret_cast<char*>(img + c);
+    char* img1 = reinterpret_cast<char*>(img + c + T);
+    const float4* gp = gyrow + c;
+    int lo = -1, hi = -1;
+    float4 h0lo = zero, h1lo = zero, h0hi = zero, h1hi = zero;
+    for (int q = 0; q < ow_s; ++q, gp += C4) {
+      const int pw = q * bin_stride;
+      float4 a0 = __ldg(gp), a1 = zero;
+      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
+      if (two) {
+        a1 = __ldg(gp + T);
+        a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
+      }
+      for (int ix = 0; ix < grid_w; ++ix) {
+        const float4 tx = taps.x(pw, ix);
+        const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+        if (xl < 0) continue;
+        if (xl != lo) {
+          if (lo >= 0)
+            scatter_column<kTabled>(taps, grid_h, img0 + lo, img1 + lo, two, h0lo, h1lo);
+          if (xl == hi) {
+            h0lo = h0hi; h1lo = h1hi;
+          } else {
+            if (hi >= 0)
+              scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
+            h0lo = zero; h1lo = zero;
+          }
+          lo = xl;
+          hi = -1;
+          h0hi = zero; h1hi = zero;
+        }
+        fma4(h0lo, tx.w, a0);
+        fma4(h1lo, tx.w, a1);
+        if (xh == lo) {                         // right border: the high tap is the same pixel
+          fma4(h0lo, tx.z, a0);
+          fma4(h1lo, tx.z, a1);
+        } else {
+          if (xh != hi) {
+            if (hi >= 0)
+              scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
+            hi = xh;
+            h0hi = zero; h1hi = zero;
+          }
+          fma4(h0hi, tx.z, a0);
+          fma4(h1hi, tx.z, a1);
+        }
+      }
+    }
+    if (lo >= 0) scatter_column<kTabled>(taps, grid_h, img0 + lo, img1 + lo, two, h0lo, h1lo);
+    if (hi >= 0) scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict__ rois,
+                          float4* __restrict__ gx, int H, int W, int C4, int outh, int outw,
+                          int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio) {
+  __shared__ TapTables tt;
+  const int r = blockIdx.x / oh_s;
+  const int row = blockIdx.x - r * oh_s;
+  const int ph = row * bin_stride;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
+  const TapSource ts = make_taps(tt, g, outh, outw, H, W, W * C4 * 16, C4 * 16, ph);
+  float4* img = gx + (size_t)g.batch * H * W * C4;
+  const float4* gyrow = gy + ((size_t)r * oh_s + row) * ow_s * C4;
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
+  if (ts.tabled)
+    roi_align_bwd_row<true>(row_taps<true>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), gyrow, img, C4,
+                            blockDim.x, ow_s, bin_stride, inv);
+  else
+    roi_align_bwd_row<false>(row_taps<false>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), gyrow, img, C4,
+                             blockDim.x, ow_s, bin_stride, inv);
 }
 
 int pick_threads(int positions) {
@@ -425,8 +620,9 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
   CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  CMR_REQUIRE((long long)H * W * C * 4 < (1ll << 31));   // byte offsets inside an image are ints
   prof_begin(kProfRoiAlign, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
-  roi_align_nhwc_kernel<false><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+  roi_align_nhwc_fwd_kernel<<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C / 4, outh,
       outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, round_tf32);
   prof_end(as_stream(stream));
@@ -446,10 +642,11 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
   CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
+  CMR_REQUIRE((long long)H * W * C * 4 < (1ll << 31));   // byte offsets inside an image are ints
   prof_begin(kProfRoiAlignBwd, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
-  roi_align_nhwc_kernel<true><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+  roi_align_nhwc_bwd_kernel<<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, 0);
+      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;

@@ -135,6 +135,41 @@ def test_nhwc_variant_and_bin_stride(stride, ratio):
     assert _rel(got_gx, want_gx) <= REL
 
 
+@pytest.mark.parametrize('C,stride,ratio', [(40, 1, 0), (256, 2, 0), (128, 1, 2), (1024, 2, 3)])
+def test_nhwc_many_rois_borders_and_skips(C, stride, ratio):
+    """The separable NHWC kernels on RoIs of every size: whole-image and sub-pixel boxes,
+    boxes hanging over every border (clamped taps; samples beyond the 1-pixel margin are
+    skipped but still counted), zero-size boxes (forced to 1x1), one and two channel quads
+    per thread."""
+    rs = np.random.RandomState(C + stride)
+    N, H, W = 2, 21, 30
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = synth.rois_xy(rs, 70, N, H * 16, W * 16, lo=2., hi=500.)
+    extra = np.array([
+        [0, 0, 0, W * 16, H * 16],                  # the whole image
+        [1, -40, -30, 90, 70],                      # over the top-left corner, beyond the margin
+        [0, W * 16 - 50, H * 16 - 60, W * 16 + 45, H * 16 + 70],   # over the bottom-right corner
+        [1, W * 16 - 8, 10, W * 16 + 30, 200],      # narrow strip on the right border
+        [0, 100, 100, 100, 100],                    # zero size
+        [1, 200, 150, 190, 140],                    # inverted
+        [0, 33.3, 47.1, 35.9, 48.2],                # far below one feature pixel
+        [1, -200, 50, -100, 90],                    # entirely outside: every sample skipped
+    ], np.float32)
+    rois = np.concatenate([rois, extra])
+    full = ora.roi_align_forward(x, rois, 14, 14, 1. / 16, ratio)
+    want = full[:, :, ::stride, ::stride]
+    gy = rs.standard_normal(want.shape).astype(np.float32)
+    gy_full = np.zeros_like(full)
+    gy_full[:, :, ::stride, ::stride] = gy
+    want_gx = ora.roi_align_backward(x.shape, rois, gy_full, 14, 14, 1. / 16, ratio)
+    got, got_gx = _nhwc(x, rois, 14, 14, stride, ratio, gy)
+    assert _rel(got, want) <= REL
+    assert _rel(got_gx, want_gx) <= REL
+    # per-RoI check, so that a small RoI's error is not hidden by the global maximum
+    for k in range(len(rois)):
+        assert np.abs(got[k] - want[k]).max() <= 1e-5 * max(np.abs(want[k]).max(), 1e-3), k
+
+
 def test_full_size_against_torchvision_cpu():
     """BASELINE config 5 shape (1024 x 50 x 68 map, 14 x 14 bins), 300 RoIs, against
     torchvision's CPU roi_align(aligned=False), which agrees with the reference code

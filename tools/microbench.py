@@ -198,6 +198,22 @@ def bench_peaks(out):
     print(json.dumps(rec)); out.append(rec)
 
 
+def bench_hbm(out):
+    """HBM stream rates on this box, to put the write-dominated kernels (ROIAlign forward,
+    the residual epilogues) in context: write-only (fill), read-only (sum) and copy."""
+    n = 1 << 29                                   # 2 GiB of float32
+    a = torch.empty((n,), device='cuda')
+    b = torch.empty((n,), device='cuda')
+    a.normal_()
+    for name, fn, nbytes in (('hbm_write_only_fill', lambda: b.fill_(1.0), 4 * n),
+                             ('hbm_read_only_sum', lambda: a.sum(), 4 * n),
+                             ('hbm_copy', lambda: b.copy_(a), 8 * n)):
+        med, best = time_ms(fn, iters=10, warmup=3, flush=False)
+        rec = dict(kernel=name, ms=med, ms_min=best, gbs=nbytes / best / 1e6,
+                   gbs_median=nbytes / med / 1e6)
+        print(json.dumps(rec)); out.append(rec)
+
+
 def bench_infer(out):
     """BASELINE config 3: R50-C4 inference on a 1333x800 image, 6000 -> 1000 proposals ->
     100 detections with masks (MaskRCNN.predict: both head passes, per-class NMS, mask
@@ -274,6 +290,8 @@ if __name__ == '__main__':
         bench_conv(out)
     if args.what in ('peaks', 'all'):
         bench_peaks(out)
+    if args.what in ('hbm', 'all'):
+        bench_hbm(out)
     if args.what in ('infer', 'all'):
         bench_infer(out)
     if args.out:
