@@ -484,14 +484,18 @@ __device__ __forceinline__ void roi_align_bwd_row(const RowTaps<kTabled>& taps,
     const float4* gp = gyrow + c;
     int lo = -1, hi = -1;
     float4 h0lo = zero, h1lo = zero, h0hi = zero, h1hi = zero;
-    for (int q = 0; q < ow_s; ++q, gp += C4) {
+    // the gradient of the next bin is requested while the current one is scattered
+    float4 n0 = __ldg(gp), n1 = two ? __ldg(gp + T) : zero;
+    for (int q = 0; q < ow_s; ++q) {
       const int pw = q * bin_stride;
-      float4 a0 = __ldg(gp), a1 = zero;
-      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
-      if (two) {
-        a1 = __ldg(gp + T);
-        a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
+      float4 a0 = n0, a1 = n1;
+      gp += C4;
+      if (q + 1 < ow_s) {
+        n0 = __ldg(gp);
+        if (two) n1 = __ldg(gp + T);
       }
+      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
+      a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
       for (int ix = 0; ix < grid_w; ++ix) {
         const float4 tx = taps.x(pw, ix);
         const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
