@@ -426,7 +426,7 @@ __device__ __forceinline__ void roi_align_fwd_row(const RowTaps<kTabled>& taps,
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128)   // (128, 8) = 64 registers was measured: slower
 roi_align_nhwc_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                           float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
                           int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
@@ -536,7 +536,7 @@ __device__ __forceinline__ void roi_align_bwd_row(const RowTaps<kTabled>& taps,
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)   // 80 registers: 6 CTAs per SM (+5 % over 95 / 5)
 roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict__ rois,
                           float4* __restrict__ gx, int H, int W, int C4, int outh, int outw,
                           int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio) {
