@@ -31,7 +31,7 @@ def test_binding_table_matches_header(lib):
 
 
 def test_version_and_status_strings(lib):
-    assert lib.cmr_version() >= 1
+    assert lib.cmr_version() == 5       # bumped with every ABI change
     assert lib.cmr_status_string(0) == b'ok'
     assert b'workspace' in lib.cmr_status_string(-3)
 
@@ -49,3 +49,30 @@ def test_conv_desc_layout_matches_header():
     fields = [f.strip() for decl in re.findall(r'int ([^;]+);', body) for f in decl.split(',')]
     assert fields == [name for name, _ in _lib.ConvDesc._fields_]
     assert ctypes.sizeof(_lib.ConvDesc) == 4 * len(fields)
+
+
+def test_prepare_size_is_cv_round(lib):
+    """cmr_prepare_size is host-only: the size cv2.resize(img, None, fx, fy) produces --
+    cvRound (ties to even) of the products -- against the oracle and cv2 itself."""
+    import cv2
+    import numpy as np
+    from oracle import prepare as op
+    h, w = ctypes.c_int(), ctypes.c_int()
+    rs = np.random.RandomState(0)
+    cases = [(80, 103, 0.5), (80, 101, 0.5), (500, 833, 1.6), (3, 5, 0.5), (480, 640, 800 / 480.)]
+    cases += [(int(rs.randint(8, 400)), int(rs.randint(8, 400)), float(rs.uniform(0.3, 3.)))
+              for _ in range(50)]
+    for H, W, f in cases:
+        assert lib.cmr_prepare_size(H, W, f, f, ctypes.addressof(h), ctypes.addressof(w)) == 0
+        assert (h.value, w.value) == op.out_size(H, W, f, f)
+        got = cv2.resize(np.zeros((H, W, 3), np.float32), None, fx=f, fy=f).shape[:2]
+        assert (h.value, w.value) == got, (H, W, f)
+    assert lib.cmr_prepare_size(0, 5, 1., 1., ctypes.addressof(h), ctypes.addressof(w)) == -1
+    assert lib.cmr_prepare_size(5, 5, 0.01, 0.01, ctypes.addressof(h), ctypes.addressof(w)) == -1
+
+
+def test_detections_workspace_scales_with_rows(lib):
+    """One NMS row per (image, class): the mask dominates, rows * max_roi * ceil(max_roi/64) words."""
+    b = lib.cmr_detections_workspace_bytes(2, 1000, 81, 19000)
+    assert b >= 2 * 80 * 1000 * 16 * 8
+    assert lib.cmr_detections_workspace_bytes(0, 1000, 81, 19000) == 256
