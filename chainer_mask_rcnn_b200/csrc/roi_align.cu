@@ -11,10 +11,12 @@
 //    output bin (ph,pw), computes the sample geometry once and reuses it for
 //    every channel of the chunk (4*kChanPerCta independent loads in flight per
 //    sample), then writes bins of one (roi,channel) plane contiguously.
-//  * NHWC  (what the model uses internally).  One CTA = one RoI x one output
-//    bin; lanes run over channels as float4, so every tap is a fully coalesced
-//    512 B warp load and the geometry is CTA-uniform.  `bin_stride` produces only
-//    every bin_stride-th bin (res5.a reads the 14x14 pool with stride 2).
+//  * NHWC  (what the model uses internally).  One CTA = one RoI x one produced
+//    output row; lanes run over channels as float4, so every tap is a fully
+//    coalesced 512 B warp load and the geometry is CTA-uniform.  The bilinear sum is
+//    evaluated separably over a two-column register window (see the kernels).
+//    `bin_stride` produces only every bin_stride-th bin (res5.a reads the 14x14 pool
+//    with stride 2).
 #include "common.cuh"
 
 namespace cmr {
