@@ -170,6 +170,32 @@ def test_nhwc_many_rois_borders_and_skips(C, stride, ratio):
         assert np.abs(got[k] - want[k]).max() <= 1e-5 * max(np.abs(want[k]).max(), 1e-3), k
 
 
+def test_operator_paths_agree():
+    """functions.roi_align_2d with the backward through the channels-last kernel (default
+    for C % 4 == 0) and through the reference-layout kernel (ROIAlign2D.exact_order): same
+    gradients, contiguous NCHW results either way."""
+    rs = np.random.RandomState(11)
+    x = rs.standard_normal((2, 64, 21, 30)).astype(np.float32)
+    rois = synth.rois_xy(rs, 40, 2, 21 * 16, 30 * 16, lo=4., hi=400.)
+    gy = rs.standard_normal((40, 64, 7, 7)).astype(np.float32)
+    want = ora.roi_align_forward(x, rois, 7, 7, 1. / 16, 0)
+    want_gx = ora.roi_align_backward(x.shape, rois, gy, 7, 7, 1. / 16, 0)
+    outs = []
+    for exact in (False, True):
+        functions.ROIAlign2D.exact_order = exact
+        try:
+            xt = torch.from_numpy(x).cuda().requires_grad_(True)
+            y = functions.roi_align_2d(xt, torch.from_numpy(rois).cuda(), 7, 7, 1. / 16)
+            y.backward(torch.from_numpy(gy).cuda())
+        finally:
+            functions.ROIAlign2D.exact_order = False
+        assert y.is_contiguous() and xt.grad.is_contiguous()
+        assert _rel(y.detach().cpu().numpy(), want) <= REL
+        assert _rel(xt.grad.cpu().numpy(), want_gx) <= REL
+        outs.append(y.detach())
+    assert float((outs[0] - outs[1]).abs().max()) <= 1e-5
+
+
 def test_full_size_against_torchvision_cpu():
     """BASELINE config 5 shape (1024 x 50 x 68 map, 14 x 14 bins), 300 RoIs, against
     torchvision's CPU roi_align(aligned=False), which agrees with the reference code

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import synth  # noqa: E402
-from chainer_mask_rcnn_b200 import _lib, utils  # noqa: E402
+from chainer_mask_rcnn_b200 import _lib, functions, utils  # noqa: E402
 
 PEAKS = {'hbm_gbs': 6543.7, 'bf16_tflops': 1606.6}
 try:
@@ -81,8 +81,23 @@ def bench_roi(out):
                 _lib.call('cmr_roi_align_nhwc_bwd', _lib.ptr(yn), _lib.ptr(rois), R, 1, 50, 68,
                           1024, oh, oh, 1, 1. / 16, ratio, _lib.ptr(gx), _lib.stream_ptr())
 
+            # the drop-in operator (functions.roi_align_2d, NCHW in and out) incl. its layout
+            # conversions; the backward is timed through autograd on a retained graph
+            xg = x.detach().clone().requires_grad_(True)
+            yg = functions.roi_align_2d(xg, rois, oh, oh, 1. / 16, ratio)
+            gyg = torch.ones_like(yg)
+
+            def fwd_api():
+                with torch.no_grad():
+                    functions.roi_align_2d(x, rois, oh, oh, 1. / 16, ratio)
+
+            def bwd_api():
+                xg.grad = None
+                yg.backward(gyg, retain_graph=True)
+
             for name, fn in (('roi_align_fwd_nchw', fwd), ('roi_align_bwd_nchw', bwd),
-                             ('roi_align_fwd_nhwc', fwd_nhwc), ('roi_align_bwd_nhwc', bwd_nhwc)):
+                             ('roi_align_fwd_nhwc', fwd_nhwc), ('roi_align_bwd_nhwc', bwd_nhwc),
+                             ('roi_align_2d_api_fwd', fwd_api), ('roi_align_2d_api_bwd', bwd_api)):
                 if R == 6000 and 'bwd' in name and oh == 14 and ratio == 2:
                     continue
                 med, best = time_ms(fn, iters=10, warmup=3)
