@@ -218,13 +218,14 @@ def main():
     import torch
     import torch.distributed as dist
     import __graft_entry__ as entry
-    if rank == 0:
-        entry.build()
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-        dist.barrier()
+    if rank == 0:
+        entry.build()            # a no-op when the in-tree library is current
+    if world > 1:
+        dist.barrier()           # nobody loads the library before rank 0 is done with it
     from chainer_mask_rcnn_b200 import _lib, models, optimizers
     lib = _lib.load()
     warmup = max(args.warmup, 3)
