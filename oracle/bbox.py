@@ -5,7 +5,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED: chainercv
 under the reference tree and cannot be installed offline, and no reference test
 holds golden vectors for these functions.  Each function restates the published
 chainercv 0.13 algorithm, anchored on the reference's own
-call sites:
+call sites (and cross-checked against torchvision's CPU box_iou / nms / BoxCoder, an
+independent implementation, in tests/test_oracle_bbox.py):
 
   generate_anchor_base      <- models/region_proposal_network.py:20-21,67-68
   enumerate_shifted_anchor  <- models/region_proposal_network.py:148-167 (in-tree)

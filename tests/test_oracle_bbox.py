@@ -135,3 +135,33 @@ def test_anchor_target_creator_contract():
     assert (label == 1).sum() >= 1
     outside = (anchor[:, 0] < 0) | (anchor[:, 1] < 0) | (anchor[:, 2] > 320) | (anchor[:, 3] > 400)
     assert (label[outside] == -1).all() and (loc[outside] == 0).all()
+
+
+def test_cross_check_against_torchvision_cpu():
+    """chainercv is absent (SURVEY.md 8c), so these restatements are 'parity unpinned';
+    torchvision's CPU ops are an implementation nobody here wrote: same IoU matrix, same
+    greedy keep list (torchvision suppresses on IoU > thresh, chainercv on >=: identical on
+    boxes without an exact tie), same box decoding as its BoxCoder with unit weights."""
+    import torch
+    import torchvision
+    from torchvision.models.detection._utils import BoxCoder
+    rs = np.random.RandomState(42)
+    boxes = synth.clustered_boxes(rs, 1500, 600, 800, n_centers=90)
+    boxes = boxes[(boxes[:, 2] - boxes[:, 0] > 1) & (boxes[:, 3] - boxes[:, 1] > 1)]
+    xyxy = torch.from_numpy(boxes[:, [1, 0, 3, 2]].copy())
+    iou_tv = torchvision.ops.box_iou(xyxy[:200], xyxy).numpy()
+    np.testing.assert_allclose(ob.bbox_iou(boxes[:200], boxes), iou_tv, rtol=1e-5, atol=1e-6)
+    score = synth.tie_free_scores(rs, len(boxes))
+    for thresh in (0.3, 0.5, 0.7):
+        keep_tv = torchvision.ops.nms(xyxy, torch.from_numpy(score), thresh).numpy()
+        keep = ob.non_maximum_suppression(boxes, thresh, score=score)
+        np.testing.assert_array_equal(keep, keep_tv)
+    # loc2bbox: (dy, dx, dh, dw) on yx boxes == BoxCoder((1,1,1,1)).decode of (dx, dy, dw, dh)
+    loc = (rs.standard_normal((len(boxes), 4)) * 0.3).astype(np.float32)
+    got = ob.loc2bbox(boxes, loc)
+    coder = BoxCoder((1., 1., 1., 1.), bbox_xform_clip=1e9)
+    want = coder.decode_single(torch.from_numpy(loc[:, [1, 0, 3, 2]].copy()), xyxy).numpy()
+    np.testing.assert_allclose(got[:, [1, 0, 3, 2]], want, rtol=1e-5, atol=1e-3)
+    # bbox2loc is its inverse under the same coder
+    enc = coder.encode_single(torch.from_numpy(want), xyxy).numpy()
+    np.testing.assert_allclose(ob.bbox2loc(boxes, got)[:, [1, 0, 3, 2]], enc, rtol=1e-3, atol=2e-4)
