@@ -1,7 +1,9 @@
 """NumPy restatement of the reference model graph (forward and backward), NCHW fp32.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py); PARITY UNPINNED for the Chainer /
-ChainerCV pieces (oracle/nn.py, oracle/bbox.py headers).  Follows:
+ChainerCV pieces (oracle/nn.py, oracle/bbox.py headers); the forward and the hand-written
+backward are cross-checked against torch float64 autograd of the same graph
+(tests/test_oracle_model.py).  Follows:
 
   ResNetExtractorBase.__call__   models/resnet_extractor.py:61-90  (conv1 has a bias;
                                  max_pooling_2d(3, stride=2, pad=1) with Chainer's
