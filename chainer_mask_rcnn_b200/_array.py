@@ -14,8 +14,9 @@ def device():
     return torch.device('cuda', torch.cuda.current_device())
 
 
-def to_device(a, dtype=None):
-    """-> (contiguous CUDA tensor, was_numpy)."""
+def to_device(a, dtype=None, keep_layout=False):
+    """-> (contiguous CUDA tensor, was_numpy).  keep_layout: a dense tensor is returned with
+    the strides it has (a channels-last feature map stays channels-last)."""
     if isinstance(a, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(a)).to(device(), non_blocking=False)
         was_numpy = True
@@ -26,6 +27,8 @@ def to_device(a, dtype=None):
         raise InvalidType('expected numpy.ndarray or torch.Tensor, got {}'.format(type(a)))
     if dtype is not None and t.dtype != dtype:
         raise InvalidType('expected dtype {}, got {}'.format(dtype, t.dtype))
+    if keep_layout and t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous():
+        return t, was_numpy
     return t.contiguous(), was_numpy
 
 

@@ -35,6 +35,27 @@ _SIGNATURES = {
     'cmr_roi_align_nhwc_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_float, c_int,
                                        c_void_p, c_void_p]),
+    'cmr_roi_align_cl_supported': (c_int, [c_int] * 7),
+    'cmr_roi_align_fwd_cl': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                     c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'cmr_roi_align_bwd_cl': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'cmr_roi_align_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'cmr_roi_align_fwd_ws': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                     c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+    'cmr_roi_align_bwd_ws': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
+    'cmr_transpose_batched': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'cmr_affine_channel_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_void_p, c_void_p]),
+    'cmr_affine_channel_bwd_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'cmr_affine_channel_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                       c_void_p]),
+    'cmr_bn_fold': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p,
+                            c_void_p, c_void_p]),
     'cmr_nms_workspace_bytes': (c_size_t, [c_int]),
     'cmr_nms': (c_int, [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p,
                         c_size_t, c_void_p]),

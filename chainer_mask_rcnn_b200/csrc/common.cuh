@@ -37,7 +37,9 @@ enum ProfKind {
   // secondary views of the kProfConvGemm launches, split by what bounds them (prof_tag)
   kProfConvTensorBound = 4,   // work = FLOPs
   kProfConvHbmBound = 5,      // work = algorithmic bytes
-  kProfKinds = 6
+  // the reference-layout ROIAlign operator (cmr_roi_align_fwd_cl / _bwd_cl), bytes
+  kProfRoiAlignApi = 6, kProfRoiAlignApiBwd = 7,
+  kProfKinds = 8
 };
 void prof_begin(int kind, double work, cudaStream_t st);
 void prof_tag(int kind2, double work2);   // between prof_begin and prof_end

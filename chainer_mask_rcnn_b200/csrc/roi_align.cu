@@ -31,11 +31,22 @@ struct RoiGeom {
 
 // roi_align_2d.py:184-211.  All fp32, IEEE ops without contraction so the
 // truncations / comparisons below see the same values as the reference.
+// A batch index outside [0, n_img) (or NaN) makes the RoI empty: no samples, zero output,
+// no gradient -- never an out-of-bounds access.
 __device__ __forceinline__ RoiGeom roi_geometry(const float* __restrict__ roi,
                                                 float scale, int outh, int outw,
-                                                int sampling_ratio) {
+                                                int sampling_ratio, int n_img) {
   RoiGeom g;
-  g.batch = (int)roi[0];
+  const float bf = roi[0];
+  if (!(bf >= 0.0f && bf < (float)n_img)) {
+    g.batch = 0;
+    g.start_w = g.start_h = 0.f;
+    g.bin_w = g.bin_h = 1.f;
+    g.grid_h = g.grid_w = 0;
+    g.inv_count_den = 1.f;
+    return g;
+  }
+  g.batch = (int)bf;
   g.start_w = __fmul_rn(roi[1], scale);
   g.start_h = __fmul_rn(roi[2], scale);
   float end_w = __fmul_rn(roi[3], scale);
@@ -147,11 +158,11 @@ template <int CB>
 __global__ void __launch_bounds__(256)
 roi_align_nchw_fwd_kernel(const float* __restrict__ x, const float* __restrict__ rois,
                           float* __restrict__ y, int C, int H, int W, int outh, int outw,
-                          float scale, int sampling_ratio, int chunks_per_roi) {
+                          float scale, int sampling_ratio, int chunks_per_roi, int n_img) {
   __shared__ TapTables tt;
   const int r = blockIdx.x / chunks_per_roi;
   const int c0 = (blockIdx.x - r * chunks_per_roi) * CB;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
   const TapSource taps = make_taps(tt, g, outh, outw, H, W, W, 1);
   const int P = outh * outw;
   const size_t HW = (size_t)H * W;
@@ -213,11 +224,11 @@ template <int CB>
 __global__ void __launch_bounds__(256)
 roi_align_nchw_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                           float* __restrict__ gx, int C, int H, int W, int outh, int outw,
-                          float scale, int sampling_ratio, int chunks_per_roi) {
+                          float scale, int sampling_ratio, int chunks_per_roi, int n_img) {
   __shared__ TapTables tt;
   const int r = blockIdx.x / chunks_per_roi;
   const int c0 = (blockIdx.x - r * chunks_per_roi) * CB;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
   const TapSource taps = make_taps(tt, g, outh, outw, H, W, W, 1);
   const int P = outh * outw;
   const size_t HW = (size_t)H * W;
@@ -307,256 +318,499 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
       : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(w));
 }
 
-// Taps of one output row / of all output columns as the row kernels walk them: from the
-// CTA's shared-memory tables (kTabled, the case for every RoI that fits the image) or
-// recomputed on the fly (RoIs more than kMaxTaps / pooled samples tall or wide).
-template <bool kTabled>
-struct RowTaps {
-  const float4* ytab;       // grid_h entries of row ph
-  const float4* xtab;       // pooled_w * grid_w entries
-  RoiGeom g;
-  int ph, H, W, y_mul, x_mul;
-  __device__ __forceinline__ float4 y(int iy) const {
-    if (kTabled) return ytab[iy];
-    return packed_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H, y_mul);
-  }
-  __device__ __forceinline__ float4 x(int pw, int ix) const {
-    if (kTabled) return xtab[pw * g.grid_w + ix];
-    return packed_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W, x_mul);
-  }
+// ---------------------------------------------------------------- merged rows --
+// The vertical taps of one output row, merged per feature row.  Consecutive samples of a bin
+// are at most one pixel apart (grid = ceil(bin size)), so the 2 * grid_h (row, weight) taps
+// of an output row fall on a short run of consecutive feature rows; summing the weights per
+// row first turns 2 * grid_h loads (forward) / vector reductions (backward) per feature
+// column into (rows spanned) of them: ~1.5x fewer for the usual RoIs.  Same products as the
+// reference up to the order of the weight sum (a few ulp).
+constexpr int kRowSlots = 8;      // feature rows one output row may span on this path
+constexpr int kColTaps = 256;     // pooled_w * grid_w x-taps kept in shared memory
+
+struct RowBlend {
+  int first;                // byte offset of the first feature row, -1: every sample skipped
+  int n;                    // rows spanned (0 when every sample is skipped)
+  float w[kRowSlots];
 };
 
-template <bool kTabled>
-__device__ __forceinline__ RowTaps<kTabled> row_taps(const TapTables& tt, const RoiGeom& g,
-                                                     int ph, int H, int W, int y_mul,
-                                                     int x_mul) {
-  RowTaps<kTabled> t;
-  t.ytab = tt.y + ph * g.grid_h;
-  t.xtab = tt.x;
-  t.g = g;
-  t.ph = ph; t.H = H; t.W = W; t.y_mul = y_mul; t.x_mul = x_mul;
-  return t;
-}
-
-// g = vertical blend of the feature column at `col` (its pixel in image row 0; col1 = the
-// thread's second channel quad) for the CTA's output row.
-// (The row kernels keep tap offsets in BYTES, so that an address is one 64-bit add.)
-__device__ __forceinline__ const float4* at(const char* base, int byte_off) {
-  return reinterpret_cast<const float4*>(base + byte_off);
-}
-__device__ __forceinline__ float4* at(char* base, int byte_off) {
-  return reinterpret_cast<float4*>(base + byte_off);
-}
-
-template <bool kTabled>
-__device__ __forceinline__ void blend_column(const RowTaps<kTabled>& taps, int grid_h,
-                                             const char* __restrict__ col,
-                                             const char* __restrict__ col1, bool two,
-                                             float4& g0, float4& g1) {
-  g0 = make_float4(0.f, 0.f, 0.f, 0.f);
-  g1 = g0;
-  for (int iy = 0; iy < grid_h; ++iy) {
-    const float4 ty = taps.y(iy);
-    const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
-    if (yl < 0) continue;
-    const float4 v = __ldg(at(col, yl)), u = __ldg(at(col, yh));
-    if (two) {
-      const float4 v1 = __ldg(at(col1, yl)), u1 = __ldg(at(col1, yh));
-      fma4(g1, ty.w, v1);
-      fma4(g1, ty.z, u1);
+// Threads e < nph * kRowSlots fill rb[0 .. nph) for output rows ph0, ph0 + ph_step, ...;
+// returns false (CTA-uniform, through *ok) when some row spans more than kRowSlots rows.
+__device__ __forceinline__ void build_row_blends(RowBlend* rb, int* ok, const RoiGeom& g,
+                                                 int ph0, int ph_step, int nph, int H,
+                                                 int row_bytes) {
+  for (int e = threadIdx.x; e < nph * kRowSlots; e += blockDim.x) {
+    const int i = e / kRowSlots, k = e - i * kRowSlots;
+    const int ph = ph0 + i * ph_step;
+    int lo = 1 << 30, hi = -1;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+      if (!t.valid) continue;
+      lo = min(lo, t.low);
+      hi = max(hi, t.high);
     }
-    fma4(g0, ty.w, v);
-    fma4(g0, ty.z, u);
+    const int row = lo + k;
+    float w = 0.f;
+    if (hi >= 0 && row <= hi) {
+      for (int iy = 0; iy < g.grid_h; ++iy) {
+        const AxisTap t = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+        if (!t.valid) continue;
+        if (t.low == row) w += t.h;
+        if (t.high == row) w += t.l;
+      }
+    }
+    rb[i].w[k] = w;
+    if (k == 0) {
+      rb[i].first = hi >= 0 ? lo * row_bytes : -1;
+      rb[i].n = hi >= 0 ? hi - lo + 1 : 0;
+      if (hi - lo + 1 > kRowSlots) atomicExch(ok, 0);
+    }
   }
 }
 
-template <bool kTabled>
-__device__ __forceinline__ void roi_align_fwd_row(const RowTaps<kTabled>& taps,
-                                                  const float4* __restrict__ img,
-                                                  float4* __restrict__ out, int C4, int T,
-                                                  int ow_s, int bin_stride, float inv,
-                                                  int round_out) {
-  const int grid_h = taps.g.grid_h, grid_w = taps.g.grid_w;
-  for (int c = threadIdx.x; c < C4; c += 2 * T) {
-    const bool two = c + T < C4;
-    const char* img0 = reinterpret_cast<const char*>(img + c);
-    const char* img1 = reinterpret_cast<const char*>(img + c + T);
-    float4* o = out + c;
-    int lo = -1, hi = -1;                       // x offsets of the two cached blended columns
-    float4 g0lo, g1lo, g0hi, g1hi;
-    g0lo = g1lo = g0hi = g1hi = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < ow_s; ++q, o += C4) {
-      const int pw = q * bin_stride;
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+__device__ __forceinline__ void build_col_taps(float4* xt, const RoiGeom& g, int outw, int W,
+                                               int px_bytes) {
+  for (int e = threadIdx.x; e < outw * g.grid_w; e += blockDim.x) {
+    const int pw = e / g.grid_w;
+    xt[e] = packed_tap(g.start_w, g.bin_w, pw, e - pw * g.grid_w, g.grid_w, W, px_bytes);
+  }
+}
+
+// g[j] = sum over the rows of rb of w * f[row][column at byte offset xoff], for the NQ
+// channel quads of the thread (quad j sits qs bytes after quad j - 1)
+template <int NQ>
+__device__ __forceinline__ void blend_rows(const RowBlend& rb, const char* __restrict__ img,
+                                           int xoff, int row_bytes, int qs, float4 (&g)[NQ]) {
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const char* p = img + rb.first + xoff;
+  int k = 0;
+  for (; k + 1 < rb.n; k += 2, p += 2 * row_bytes) {
+    float4 v0[NQ], v1[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      v0[j] = __ldg(reinterpret_cast<const float4*>(p + j * qs));
+      v1[j] = __ldg(reinterpret_cast<const float4*>(p + row_bytes + j * qs));
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      fma4(g[j], rb.w[k], v0[j]);
+      fma4(g[j], rb.w[k + 1], v1[j]);
+    }
+  }
+  if (k < rb.n) {
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+      fma4(g[j], rb.w[k], __ldg(reinterpret_cast<const float4*>(p + j * qs)));
+  }
+}
+
+template <int NQ>
+__device__ __forceinline__ void scatter_rows(const RowBlend& rb, char* __restrict__ img, int xoff,
+                                             int row_bytes, int qs, const float4 (&h)[NQ]) {
+  char* p = img + rb.first + xoff;
+  for (int k = 0; k < rb.n; ++k, p += row_bytes) {
+    const float w = rb.w[k];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+      red_add_f4(reinterpret_cast<float4*>(p + j * qs),
+                 make_float4(h[j].x * w, h[j].y * w, h[j].z * w, h[j].w * w));
+  }
+}
+
+// One output row of NQ channel quads, forward: bins left to right over a two-column window
+// of vertically blended feature columns (described above); emit(q, j, value) receives
+// finished bin q (bin index pw0 + q * pw_step) of quad j.
+template <int NQ, typename Emit>
+__device__ __forceinline__ void walk_row_fwd(const RowBlend& rb, const float4* __restrict__ xt,
+                                             int grid_w, int pw0, int pw_step, int npw,
+                                             const char* __restrict__ img, int row_bytes, int qs,
+                                             float inv, Emit emit) {
+  int lo = -1, hi = -1;
+  float4 glo[NQ], ghi[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) glo[j] = ghi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < npw; ++q) {
+    const int pw = pw0 + q * pw_step;
+    float4 a[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rb.n > 0) {
       for (int ix = 0; ix < grid_w; ++ix) {
-        const float4 tx = taps.x(pw, ix);
+        const float4 tx = xt[pw * grid_w + ix];
         const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
         if (xl < 0) continue;
         if (xl != lo) {
           if (xl == hi) {
-            g0lo = g0hi; g1lo = g1hi;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) glo[j] = ghi[j];
           } else {
-            blend_column<kTabled>(taps, grid_h, img0 + xl, img1 + xl, two, g0lo, g1lo);
+            blend_rows<NQ>(rb, img, xl, row_bytes, qs, glo);
           }
           lo = xl;
           hi = -1;
         }
         if (xh != hi) {
-          if (xh == lo) {                       // right border: both taps on the last column
-            g0hi = g0lo; g1hi = g1lo;
+          if (xh == lo) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) ghi[j] = glo[j];
           } else {
-            blend_column<kTabled>(taps, grid_h, img0 + xh, img1 + xh, two, g0hi, g1hi);
+            blend_rows<NQ>(rb, img, xh, row_bytes, qs, ghi);
           }
           hi = xh;
         }
-        fma4(a0, tx.w, g0lo);
-        fma4(a0, tx.z, g0hi);
-        fma4(a1, tx.w, g1lo);
-        fma4(a1, tx.z, g1hi);
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) {
+          fma4(a[j], tx.w, glo[j]);
+          fma4(a[j], tx.z, ghi[j]);
+        }
       }
-      float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
-      float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
-      if (round_out) {
-        o0.x = round_tf32_rn(o0.x); o0.y = round_tf32_rn(o0.y);
-        o0.z = round_tf32_rn(o0.z); o0.w = round_tf32_rn(o0.w);
-        o1.x = round_tf32_rn(o1.x); o1.y = round_tf32_rn(o1.y);
-        o1.z = round_tf32_rn(o1.z); o1.w = round_tf32_rn(o1.w);
+    }
+#pragma unroll
+    for (int j = 0; j < NQ; ++j)
+      emit(q, j, make_float4(a[j].x * inv, a[j].y * inv, a[j].z * inv, a[j].w * inv));
+  }
+}
+
+// Backward of the same walk: fetch(q, j) returns the gradient of bin q of quad j.
+template <int NQ, typename Fetch>
+__device__ __forceinline__ void walk_row_bwd(const RowBlend& rb, const float4* __restrict__ xt,
+                                             int grid_w, int pw0, int pw_step, int npw,
+                                             char* __restrict__ img, int row_bytes, int qs,
+                                             float inv, Fetch fetch) {
+  if (rb.n <= 0) return;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  int lo = -1, hi = -1;
+  float4 hlo[NQ], hhi[NQ], nxt[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    hlo[j] = hhi[j] = zero;
+    nxt[j] = fetch(0, j);
+  }
+  for (int q = 0; q < npw; ++q) {
+    const int pw = pw0 + q * pw_step;
+    float4 a[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      a[j] = make_float4(nxt[j].x * inv, nxt[j].y * inv, nxt[j].z * inv, nxt[j].w * inv);
+      if (q + 1 < npw) nxt[j] = fetch(q + 1, j);   // requested while bin q is scattered
+    }
+    for (int ix = 0; ix < grid_w; ++ix) {
+      const float4 tx = xt[pw * grid_w + ix];
+      const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
+      if (xl < 0) continue;
+      if (xl != lo) {
+        if (lo >= 0) scatter_rows<NQ>(rb, img, lo, row_bytes, qs, hlo);
+        if (xl == hi) {
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) hlo[j] = hhi[j];
+        } else {
+          if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) hlo[j] = zero;
+        }
+        lo = xl;
+        hi = -1;
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) hhi[j] = zero;
       }
-      o[0] = o0;
-      if (two) o[T] = o1;
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) fma4(hlo[j], tx.w, a[j]);
+      if (xh == lo) {                           // right border: the high tap is the same pixel
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) fma4(hlo[j], tx.z, a[j]);
+      } else {
+        if (xh != hi) {
+          if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+          hi = xh;
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) hhi[j] = zero;
+        }
+#pragma unroll
+        for (int j = 0; j < NQ; ++j) fma4(hhi[j], tx.z, a[j]);
+      }
+    }
+  }
+  if (lo >= 0) scatter_rows<NQ>(rb, img, lo, row_bytes, qs, hlo);
+  if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+}
+
+// Generic (any RoI size) single-bin evaluation on a channels-last map; the rare path for
+// RoIs whose rows span more than kRowSlots feature rows or whose x taps do not fit.
+__device__ __forceinline__ float4 bin_fwd_generic(const RoiGeom& g, int ph, int pw, int H, int W,
+                                                  const char* __restrict__ img, int row_bytes,
+                                                  int px_bytes, float inv) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int iy = 0; iy < g.grid_h; ++iy) {
+    const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+    if (!ty.valid) continue;
+    for (int ix = 0; ix < g.grid_w; ++ix) {
+      const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
+      if (!tx.valid) continue;
+      const char* r0 = img + (size_t)ty.low * row_bytes;
+      const char* r1 = img + (size_t)ty.high * row_bytes;
+      fma4(a, ty.h * tx.h, __ldg(reinterpret_cast<const float4*>(r0 + tx.low * px_bytes)));
+      fma4(a, ty.h * tx.l, __ldg(reinterpret_cast<const float4*>(r0 + tx.high * px_bytes)));
+      fma4(a, ty.l * tx.h, __ldg(reinterpret_cast<const float4*>(r1 + tx.low * px_bytes)));
+      fma4(a, ty.l * tx.l, __ldg(reinterpret_cast<const float4*>(r1 + tx.high * px_bytes)));
+    }
+  }
+  return make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+
+__device__ __forceinline__ void bin_bwd_generic(const RoiGeom& g, int ph, int pw, int H, int W,
+                                                char* __restrict__ img, int row_bytes,
+                                                int px_bytes, float inv, float4 gv) {
+  gv.x *= inv; gv.y *= inv; gv.z *= inv; gv.w *= inv;
+  for (int iy = 0; iy < g.grid_h; ++iy) {
+    const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
+    if (!ty.valid) continue;
+    for (int ix = 0; ix < g.grid_w; ++ix) {
+      const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
+      if (!tx.valid) continue;
+      char* r0 = img + (size_t)ty.low * row_bytes;
+      char* r1 = img + (size_t)ty.high * row_bytes;
+      const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
+      red_add_f4(reinterpret_cast<float4*>(r0 + tx.low * px_bytes),
+                 make_float4(gv.x * w1, gv.y * w1, gv.z * w1, gv.w * w1));
+      red_add_f4(reinterpret_cast<float4*>(r0 + tx.high * px_bytes),
+                 make_float4(gv.x * w2, gv.y * w2, gv.z * w2, gv.w * w2));
+      red_add_f4(reinterpret_cast<float4*>(r1 + tx.low * px_bytes),
+                 make_float4(gv.x * w3, gv.y * w3, gv.z * w3, gv.w * w3));
+      red_add_f4(reinterpret_cast<float4*>(r1 + tx.high * px_bytes),
+                 make_float4(gv.x * w4, gv.y * w4, gv.z * w4, gv.w * w4));
     }
   }
 }
+
+// ------------------------------------------------------- channels-last in and out --
+// What the model runs (ResNetRoIHead): one CTA per (RoI, produced output row), lanes over
+// channel quads, two quads per thread (c and c + blockDim.x) so that the taps are looked up
+// once per 8 channels and twice the loads are in flight.
+struct RowKernelSmem {
+  int ok;
+  RowBlend rb;
+  float4 xt[kColTaps];
+};
 
 __global__ void __launch_bounds__(128)   // (128, 8) = 64 registers was measured: slower
 roi_align_nhwc_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                           float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
                           int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
-                          int round_out) {
-  __shared__ TapTables tt;
+                          int round_out, int n_img) {
+  __shared__ RowKernelSmem sm;
   const int r = blockIdx.x / oh_s;
   const int row = blockIdx.x - r * oh_s;
   const int ph = row * bin_stride;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
-  const TapSource ts = make_taps(tt, g, outh, outw, H, W, W * C4 * 16, C4 * 16, ph);
-  const float4* img = src + (size_t)g.batch * H * W * C4;
+  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
+  const bool fits = outw * g.grid_w <= kColTaps;
+  if (threadIdx.x == 0) sm.ok = fits ? 1 : 0;
+  __syncthreads();
+  build_row_blends(&sm.rb, &sm.ok, g, ph, 1, 1, H, row_bytes);
+  if (fits) build_col_taps(sm.xt, g, outw, W, px_bytes);
+  __syncthreads();
+  const bool fast = sm.ok != 0;
+  const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4);
   float4* out = dst + ((size_t)r * oh_s + row) * ow_s * C4;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
-  if (ts.tabled)
-    roi_align_fwd_row<true>(row_taps<true>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), img, out, C4,
-                            blockDim.x, ow_s, bin_stride, inv, round_out);
-  else
-    roi_align_fwd_row<false>(row_taps<false>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), img, out, C4,
-                             blockDim.x, ow_s, bin_stride, inv, round_out);
-}
-
-// Backward, the transpose of the above: the gradients of a row's bins are first gathered
-// per feature column (h[x] = sum of hx * gy over the samples whose low tap is x, lx * gy
-// over those whose high tap is x), and a column is scattered through the vertical taps
-// when the window leaves it: 2 * grid_h vector reductions per column of the RoI.
-template <bool kTabled>
-__device__ __forceinline__ void scatter_column(const RowTaps<kTabled>& taps, int grid_h,
-                                               char* __restrict__ col,
-                                               char* __restrict__ col1, bool two,
-                                               const float4& h0, const float4& h1) {
-  for (int iy = 0; iy < grid_h; ++iy) {
-    const float4 ty = taps.y(iy);
-    const int yl = __float_as_int(ty.x), yh = __float_as_int(ty.y);
-    if (yl < 0) continue;
-    red_add_f4(at(col, yl), make_float4(h0.x * ty.w, h0.y * ty.w, h0.z * ty.w, h0.w * ty.w));
-    red_add_f4(at(col, yh), make_float4(h0.x * ty.z, h0.y * ty.z, h0.z * ty.z, h0.w * ty.z));
-    if (two) {
-      red_add_f4(at(col1, yl), make_float4(h1.x * ty.w, h1.y * ty.w, h1.z * ty.w, h1.w * ty.w));
-      red_add_f4(at(col1, yh), make_float4(h1.x * ty.z, h1.y * ty.z, h1.z * ty.z, h1.w * ty.z));
-    }
-  }
-}
-
-template <bool kTabled>
-__device__ __forceinline__ void roi_align_bwd_row(const RowTaps<kTabled>& taps,
-                                                  const float4* __restrict__ gyrow,
-                                                  float4* __restrict__ img, int C4, int T,
-                                                  int ow_s, int bin_stride, float inv) {
-  const int grid_h = taps.g.grid_h, grid_w = taps.g.grid_w;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int T = blockDim.x;
   for (int c = threadIdx.x; c < C4; c += 2 * T) {
-    const bool two = c + T < C4;
-    char* img0 = reinterpret_cast<char*>(img + c);
-    char* img1 = reinterpret_cast<char*>(img + c + T);
-    const float4* gp = gyrow + c;
-    int lo = -1, hi = -1;
-    float4 h0lo = zero, h1lo = zero, h0hi = zero, h1hi = zero;
-    // the gradient of the next bin is requested while the current one is scattered
-    float4 n0 = __ldg(gp), n1 = two ? __ldg(gp + T) : zero;
-    for (int q = 0; q < ow_s; ++q) {
-      const int pw = q * bin_stride;
-      float4 a0 = n0, a1 = n1;
-      gp += C4;
-      if (q + 1 < ow_s) {
-        n0 = __ldg(gp);
-        if (two) n1 = __ldg(gp + T);
+    float4* o = out + c;
+    auto emit = [&](int q, int j, float4 v) {
+      if (round_out) {
+        v.x = round_tf32_rn(v.x); v.y = round_tf32_rn(v.y);
+        v.z = round_tf32_rn(v.z); v.w = round_tf32_rn(v.w);
       }
-      a0.x *= inv; a0.y *= inv; a0.z *= inv; a0.w *= inv;
-      a1.x *= inv; a1.y *= inv; a1.z *= inv; a1.w *= inv;
-      for (int ix = 0; ix < grid_w; ++ix) {
-        const float4 tx = taps.x(pw, ix);
-        const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
-        if (xl < 0) continue;
-        if (xl != lo) {
-          if (lo >= 0)
-            scatter_column<kTabled>(taps, grid_h, img0 + lo, img1 + lo, two, h0lo, h1lo);
-          if (xl == hi) {
-            h0lo = h0hi; h1lo = h1hi;
-          } else {
-            if (hi >= 0)
-              scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
-            h0lo = zero; h1lo = zero;
-          }
-          lo = xl;
-          hi = -1;
-          h0hi = zero; h1hi = zero;
-        }
-        fma4(h0lo, tx.w, a0);
-        fma4(h1lo, tx.w, a1);
-        if (xh == lo) {                         // right border: the high tap is the same pixel
-          fma4(h0lo, tx.z, a0);
-          fma4(h1lo, tx.z, a1);
-        } else {
-          if (xh != hi) {
-            if (hi >= 0)
-              scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
-            hi = xh;
-            h0hi = zero; h1hi = zero;
-          }
-          fma4(h0hi, tx.z, a0);
-          fma4(h1hi, tx.z, a1);
-        }
-      }
+      o[(size_t)q * C4 + j * T] = v;
+    };
+    const char* base = img + (size_t)c * 16;
+    if (!fast) {
+      for (int j = 0; j < 2 && c + j * T < C4; ++j)
+        for (int q = 0; q < ow_s; ++q)
+          emit(q, j, bin_fwd_generic(g, ph, q * bin_stride, H, W, base + (size_t)j * T * 16,
+                                     row_bytes, px_bytes, inv));
+    } else if (c + T < C4) {
+      walk_row_fwd<2>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, T * 16, inv,
+                      emit);
+    } else {
+      walk_row_fwd<1>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, 0, inv, emit);
     }
-    if (lo >= 0) scatter_column<kTabled>(taps, grid_h, img0 + lo, img1 + lo, two, h0lo, h1lo);
-    if (hi >= 0) scatter_column<kTabled>(taps, grid_h, img0 + hi, img1 + hi, two, h0hi, h1hi);
   }
 }
 
-__global__ void __launch_bounds__(128, 6)   // 80 registers: 6 CTAs per SM (+5 % over 95 / 5)
+__global__ void __launch_bounds__(128, 6)
 roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict__ rois,
                           float4* __restrict__ gx, int H, int W, int C4, int outh, int outw,
-                          int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio) {
-  __shared__ TapTables tt;
+                          int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
+                          int n_img) {
+  __shared__ RowKernelSmem sm;
   const int r = blockIdx.x / oh_s;
   const int row = blockIdx.x - r * oh_s;
   const int ph = row * bin_stride;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio);
-  const TapSource ts = make_taps(tt, g, outh, outw, H, W, W * C4 * 16, C4 * 16, ph);
-  float4* img = gx + (size_t)g.batch * H * W * C4;
+  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
+  const bool fits = outw * g.grid_w <= kColTaps;
+  if (threadIdx.x == 0) sm.ok = fits ? 1 : 0;
+  __syncthreads();
+  build_row_blends(&sm.rb, &sm.ok, g, ph, 1, 1, H, row_bytes);
+  if (fits) build_col_taps(sm.xt, g, outw, W, px_bytes);
+  __syncthreads();
+  const bool fast = sm.ok != 0;
+  char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4);
   const float4* gyrow = gy + ((size_t)r * oh_s + row) * ow_s * C4;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
-  if (ts.tabled)
-    roi_align_bwd_row<true>(row_taps<true>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), gyrow, img, C4,
-                            blockDim.x, ow_s, bin_stride, inv);
-  else
-    roi_align_bwd_row<false>(row_taps<false>(tt, g, ph, H, W, W * C4 * 16, C4 * 16), gyrow, img, C4,
-                             blockDim.x, ow_s, bin_stride, inv);
+  const int T = blockDim.x;
+  for (int c = threadIdx.x; c < C4; c += 2 * T) {
+    const float4* gp = gyrow + c;
+    auto fetch = [&](int q, int j) { return __ldg(gp + (size_t)q * C4 + j * T); };
+    char* base = img + (size_t)c * 16;
+    if (!fast) {
+      for (int j = 0; j < 2 && c + j * T < C4; ++j)
+        for (int q = 0; q < ow_s; ++q)
+          bin_bwd_generic(g, ph, q * bin_stride, H, W, base + (size_t)j * T * 16, row_bytes,
+                          px_bytes, inv, fetch(q, j));
+    } else if (c + T < C4) {
+      walk_row_bwd<2>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, T * 16, inv,
+                      fetch);
+    } else {
+      walk_row_bwd<1>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, 0, inv, fetch);
+    }
+  }
+}
+
+// ------------------------------------------- reference layout over a channels-last map --
+// The drop-in operator's fast path: the feature map is read channels-last (the model's own
+// layout; a plain NCHW input is re-laid once -- it is 2 % of the pooled tensor), the pooled
+// tensor is written / read in the reference's (R, C, outh, outw) layout.
+//
+// One CTA = one RoI x CH channels.  Thread (ph, quad) walks output row ph of one channel
+// quad with the separable two-column window: every load is a float4 of 4 channels and a
+// warp's loads cover whole 128-byte lines of the map.  The CTA's (CH, outh*outw) output
+// block is contiguous in the NCHW pooled tensor: it is staged in shared memory (transposed
+// on the way in, plane stride outh*outw + 1 to spread the banks) and written out as full
+// 128-byte lines (forward) / read in as full lines and walked from shared memory (backward).
+struct RoiTileSmem {
+  int ok;
+  int pad_[3];
+  float4 xt[kColTaps];
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
+                        float* __restrict__ dst, int H, int W, int C, int outh, int outw,
+                        float scale, int sampling_ratio, int chunks, int n_img) {
+  extern __shared__ __align__(16) unsigned char roi_smem[];
+  RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
+  RowBlend* rb = reinterpret_cast<RowBlend*>(roi_smem + sizeof(RoiTileSmem));
+  float* tile = reinterpret_cast<float*>(rb + outh);
+  constexpr int Q = CH / 4;
+  const int r = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x - r * chunks) * CH;
+  const int nch = min(CH, C - c0);
+  const int P = outh * outw, PS = P + 1;
+  const int C4 = C >> 2;
+  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
+  if (threadIdx.x == 0) sm->ok = outw * g.grid_w <= kColTaps ? 1 : 0;
+  __syncthreads();
+  build_row_blends(rb, &sm->ok, g, 0, 1, outh, H, row_bytes);
+  if (outw * g.grid_w <= kColTaps) build_col_taps(sm->xt, g, outw, W, px_bytes);
+  __syncthreads();
+  const bool fast = sm->ok != 0;
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
+  const int quad = threadIdx.x % Q;
+  const int rows_per_pass = blockDim.x / Q;
+  if (4 * quad < nch) {
+    const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 +
+                                                    (c0 >> 2) + quad);
+    float* t0 = tile + (size_t)(4 * quad) * PS;
+    for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
+      float* trow = t0 + ph * outw;
+      auto emit = [&](int pw, int, const float4& v) {
+        trow[pw] = v.x; trow[PS + pw] = v.y; trow[2 * PS + pw] = v.z; trow[3 * PS + pw] = v.w;
+      };
+      if (fast) {
+        walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, emit);
+      } else {
+        for (int pw = 0; pw < outw; ++pw)
+          emit(pw, 0, bin_fwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv));
+      }
+    }
+  }
+  __syncthreads();
+  float* out = dst + ((size_t)r * C + c0) * P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < nch; c += nwarp) {
+    const float* tp = tile + (size_t)c * PS;
+    float* op = out + (size_t)c * P;
+    for (int p = lane; p < P; p += 32) op[p] = tp[p];
+  }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
+                        float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
+                        float scale, int sampling_ratio, int chunks, int n_img) {
+  extern __shared__ __align__(16) unsigned char roi_smem[];
+  RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
+  RowBlend* rb = reinterpret_cast<RowBlend*>(roi_smem + sizeof(RoiTileSmem));
+  float* tile = reinterpret_cast<float*>(rb + outh);
+  constexpr int Q = CH / 4;
+  const int r = blockIdx.x / chunks;
+  const int c0 = (blockIdx.x - r * chunks) * CH;
+  const int nch = min(CH, C - c0);
+  const int P = outh * outw, PS = P + 1;
+  const int C4 = C >> 2;
+  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
+  if (threadIdx.x == 0) sm->ok = outw * g.grid_w <= kColTaps ? 1 : 0;
+  // the CTA's block of the pooled gradient: (nch, P) contiguous floats
+  const float* in = gy + ((size_t)r * C + c0) * P;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int c = warp; c < nch; c += nwarp) {
+    float* tp = tile + (size_t)c * PS;
+    const float* ip = in + (size_t)c * P;
+    for (int p = lane; p < P; p += 32) tp[p] = __ldg(ip + p);
+  }
+  __syncthreads();
+  build_row_blends(rb, &sm->ok, g, 0, 1, outh, H, row_bytes);
+  if (outw * g.grid_w <= kColTaps) build_col_taps(sm->xt, g, outw, W, px_bytes);
+  __syncthreads();
+  const bool fast = sm->ok != 0;
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
+  const int quad = threadIdx.x % Q;
+  const int rows_per_pass = blockDim.x / Q;
+  if (4 * quad >= nch) return;
+  char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4 + (c0 >> 2) + quad);
+  const float* t0 = tile + (size_t)(4 * quad) * PS;
+  for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
+    const float* trow = t0 + ph * outw;
+    auto fetch = [&](int pw, int) {
+      return make_float4(trow[pw], trow[PS + pw], trow[2 * PS + pw], trow[3 * PS + pw]);
+    };
+    if (fast) {
+      walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, fetch);
+    } else {
+      for (int pw = 0; pw < outw; ++pw)
+        bin_bwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv, fetch(pw, 0));
+    }
+  }
+}
+
+constexpr int kClChannels = 64;   // channels per CTA of the two kernels above
+
+size_t cl_smem_bytes(int outh, int outw) {
+  return sizeof(RoiTileSmem) + sizeof(RowBlend) * (size_t)outh +
+         sizeof(float) * (size_t)kClChannels * (outh * outw + 1);
+}
+
+int cl_threads(int outh) {
+  int t = outh * (kClChannels / 4);
+  t = (t + 31) / 32 * 32;
+  return t > 256 ? 256 : (t < 64 ? 64 : t);
 }
 
 int pick_threads(int positions) {
@@ -593,7 +847,7 @@ extern "C" int cmr_roi_align_fwd(const float* x, int N, int C, int H, int W, con
   CMR_REQUIRE((long long)R * chunks < (1ll << 31));
   roi_align_nchw_fwd_kernel<kChanPerCta>
       <<<R * chunks, pick_threads(outh * outw), 0, as_stream(stream)>>>(
-          x, rois, y, C, H, W, outh, outw, spatial_scale, sampling_ratio, chunks);
+          x, rois, y, C, H, W, outh, outw, spatial_scale, sampling_ratio, chunks, N);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -610,7 +864,7 @@ extern "C" int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int 
   CMR_REQUIRE((long long)R * chunks < (1ll << 31));
   roi_align_nchw_bwd_kernel<kChanPerCta>
       <<<R * chunks, pick_threads(outh * outw), 0, as_stream(stream)>>>(
-          gy, rois, gx, C, H, W, outh, outw, spatial_scale, sampling_ratio, chunks);
+          gy, rois, gx, C, H, W, outh, outw, spatial_scale, sampling_ratio, chunks, N);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
@@ -630,7 +884,7 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   prof_begin(kProfRoiAlign, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
   roi_align_nhwc_fwd_kernel<<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), rois, reinterpret_cast<float4*>(y), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, round_tf32);
+      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, round_tf32, N);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -642,18 +896,137 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
                                       void* stream) {
   CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
   CMR_REQUIRE(sampling_ratio >= 0 && bin_stride >= 1 && C % 4 == 0 && gx);
-  CMR_CUDA_TRY(cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)N * C * H * W, as_stream(stream)));
-  if (R == 0) return CMR_OK;
-  CMR_REQUIRE(gy && rois);
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
   CMR_REQUIRE((long long)R * oh_s < (1ll << 31));
   CMR_REQUIRE((long long)N * H * W * (C / 4) < (1ll << 31));
   CMR_REQUIRE((long long)H * W * C * 4 < (1ll << 31));   // byte offsets inside an image are ints
+  CMR_REQUIRE(R == 0 || (gy && rois));
+  // the zero fill of gx is part of the operator: it is inside the timed bracket
   prof_begin(kProfRoiAlignBwd, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
+  cudaError_t me = cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)N * C * H * W, as_stream(stream));
+  if (me != cudaSuccess || R == 0) {
+    prof_end(as_stream(stream));
+    CMR_CUDA_TRY(me);
+    return CMR_OK;
+  }
   roi_align_nhwc_bwd_kernel<<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio);
+      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, N);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
+}
+
+// ---- reference-layout operator through the channels-last kernels -----------------------
+namespace {
+bool cl_supported(int N, int C, int H, int W, int R, int outh, int outw) {
+  return C % 4 == 0 && (long long)N * H * W * (C / 4) < (1ll << 31) &&
+         (long long)H * W * C * 4 < (1ll << 31) &&
+         (long long)R * ceil_div(C, kClChannels) < (1ll << 31) &&
+         cl_smem_bytes(outh, outw) <= 200 * 1024;
+}
+
+template <typename K>
+int cl_configure(K kernel, size_t bytes) {
+  // (a process-wide maximum: the attribute only ever grows)
+  static size_t configured = 0;
+  if (bytes > configured) {
+    CMR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)bytes));
+    configured = bytes;
+  }
+  return CMR_OK;
+}
+}  // namespace
+
+extern "C" int cmr_roi_align_cl_supported(int N, int C, int H, int W, int R, int outh, int outw) {
+  return cl_supported(N, C, H, W, R, outh, outw) ? 1 : 0;
+}
+
+extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, int C,
+                                    const float* rois, int R, int outh, int outw,
+                                    float spatial_scale, int sampling_ratio, float* y,
+                                    void* stream) {
+  CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
+  CMR_REQUIRE(sampling_ratio >= 0);
+  if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
+  if (R == 0) return CMR_OK;
+  CMR_REQUIRE(x_nhwc && rois && y);
+  const size_t smem = cl_smem_bytes(outh, outw);
+  int rc = cl_configure(roi_align_cl_fwd_kernel<kClChannels>, smem);
+  if (rc != CMR_OK) return rc;
+  const int chunks = ceil_div(C, kClChannels);
+  prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
+  roi_align_cl_fwd_kernel<kClChannels><<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
+      sampling_ratio, chunks, N);
+  prof_end(as_stream(stream));
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, int N, int H,
+                                    int W, int C, int outh, int outw, float spatial_scale,
+                                    int sampling_ratio, float* gx_nhwc, void* stream) {
+  CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
+  CMR_REQUIRE(sampling_ratio >= 0 && gx_nhwc);
+  if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
+  CMR_REQUIRE(R == 0 || (gy && rois));
+  const size_t smem = cl_smem_bytes(outh, outw);
+  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels>, smem);
+  if (rc != CMR_OK) return rc;
+  prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
+  cudaError_t me =
+      cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, as_stream(stream));
+  if (me != cudaSuccess || R == 0) {
+    prof_end(as_stream(stream));
+    CMR_CUDA_TRY(me);
+    return CMR_OK;
+  }
+  const int chunks = ceil_div(C, kClChannels);
+  roi_align_cl_bwd_kernel<kClChannels><<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+      gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
+      sampling_ratio, chunks, N);
+  prof_end(as_stream(stream));
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+extern "C" size_t cmr_roi_align_workspace_bytes(int N, int C, int H, int W) {
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return sizeof(float) * (size_t)N * C * H * W;
+}
+
+extern "C" int cmr_roi_align_fwd_ws(const float* x, int N, int C, int H, int W, const float* rois,
+                                    int R, int outh, int outw, float spatial_scale,
+                                    int sampling_ratio, float* y, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
+  if (!workspace || workspace_bytes < cmr_roi_align_workspace_bytes(N, C, H, W) ||
+      !cl_supported(N, C, H, W, R, outh, outw))
+    return cmr_roi_align_fwd(x, N, C, H, W, rois, R, outh, outw, spatial_scale, sampling_ratio,
+                             y, stream);
+  if (R == 0) return CMR_OK;
+  CMR_REQUIRE(x && rois && y);
+  float* xt = static_cast<float*>(workspace);
+  int rc = cmr_transpose_batched(x, N, C, H * W, xt, stream);     // (N,C,HW) -> (N,HW,C)
+  if (rc != CMR_OK) return rc;
+  return cmr_roi_align_fwd_cl(xt, N, H, W, C, rois, R, outh, outw, spatial_scale, sampling_ratio,
+                              y, stream);
+}
+
+extern "C" int cmr_roi_align_bwd_ws(const float* gy, const float* rois, int R, int N, int C,
+                                    int H, int W, int outh, int outw, float spatial_scale,
+                                    int sampling_ratio, float* gx, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0 && gx);
+  if (!workspace || workspace_bytes < cmr_roi_align_workspace_bytes(N, C, H, W) ||
+      !cl_supported(N, C, H, W, R, outh, outw))
+    return cmr_roi_align_bwd(gy, rois, R, N, C, H, W, outh, outw, spatial_scale, sampling_ratio,
+                             gx, stream);
+  float* gt = static_cast<float*>(workspace);
+  int rc = cmr_roi_align_bwd_cl(gy, rois, R, N, H, W, C, outh, outw, spatial_scale,
+                                sampling_ratio, gt, stream);
+  if (rc != CMR_OK) return rc;
+  return cmr_transpose_batched(gt, N, H * W, C, gx, stream);       // (N,HW,C) -> (N,C,HW)
 }

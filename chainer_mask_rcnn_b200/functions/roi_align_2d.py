@@ -2,10 +2,11 @@
 
 Mirrors ``chainer_mask_rcnn/functions/roi_align_2d.py``: class ``ROIAlign2D``
 (:25-524; argument checks :29-47, type checks :49-59) and the wrapper
-``roi_align_2d`` (:527-560; ``axes`` handling :555-558).  The forward runs in
-``cmr_roi_align_fwd`` (reference layout and summation order), the backward in
-``cmr_roi_align_nhwc_bwd`` behind a layout conversion, or in ``cmr_roi_align_bwd`` (channel
-counts that are not a multiple of 4, or ``ROIAlign2D.exact_order``); csrc/roi_align.cu.
+``roi_align_2d`` (:527-560; ``axes`` handling :555-558).  Both passes run in
+``cmr_roi_align_fwd_cl / _bwd_cl`` (feature map channels-last, pooled tensor in the
+reference's layout), or in ``cmr_roi_align_fwd / _bwd`` (reference layout AND summation
+order: channel counts that are not a multiple of 4, or ``ROIAlign2D.exact_order``);
+csrc/roi_align.cu.
 """
 import torch
 
@@ -13,40 +14,64 @@ from .. import _lib
 from .._array import from_device, InvalidType, to_device
 
 
-# The backward pass of NCHW callers is routed through the channels-last kernel
-# (cmr_roi_align_nhwc_bwd: vector reductions, one scatter per feature column) whenever the
-# channel count allows float4 lanes: with both layout conversions it is 2.3x - 5.5x faster
-# than the reference-layout kernel's scalar atomics (profiles/README.md).  The forward pass
-# stays on the reference-layout kernel, which also keeps the reference's summation order
-# (the conversion of the large pooled tensor would cost more than the faster kernel saves).
-# ``ROIAlign2D.exact_order = True`` keeps the backward on the reference-layout kernel too.
-def _nhwc_ok(N, C, H, W, R, outh):
-    return (not ROIAlign2D.exact_order and C % 4 == 0 and R * outh < 2 ** 31 and
-            N * H * W * (C // 4) < 2 ** 31 and H * W * C * 4 < 2 ** 31)
+# Both passes run on the channels-last kernels (cmr_roi_align_fwd_cl / _bwd_cl): vector loads /
+# vector reductions of 4 channels on the feature map, the pooled tensor kept in the
+# reference's (R, C, outh, outw) layout and moved as full 128-byte lines through a
+# shared-memory tile.  A feature map that already is channels-last in memory (what this
+# package's extractor returns) is used as it is; a plain NCHW map is re-laid once into a
+# workspace (cmr_roi_align_fwd_ws / _bwd_ws; the map is ~2 % of the pooled tensor's bytes).
+# ``ROIAlign2D.exact_order = True`` selects the reference-layout kernels, which also keep the
+# reference's summation order (cmr_roi_align_fwd / _bwd); channel counts that are not a
+# multiple of 4 always take them.
+def _fast_ok(N, C, H, W, R, outh, outw):
+    return (not ROIAlign2D.exact_order and
+            _lib.load().cmr_roi_align_cl_supported(N, C, H, W, R, outh, outw) == 1)
+
+
+def _is_channels_last(x):
+    return x.dim() == 4 and x.shape[1] > 1 and x.permute(0, 2, 3, 1).is_contiguous()
 
 
 def _forward(x, rois, outh, outw, spatial_scale, sampling_ratio):
     N, C, H, W = x.shape
     R = rois.shape[0]
     rois = rois.contiguous()
-    x = x.contiguous()
     y = torch.empty((R, C, outh, outw), dtype=torch.float32, device=x.device)
+    if _fast_ok(N, C, H, W, R, outh, outw):
+        if _is_channels_last(x):
+            _lib.call('cmr_roi_align_fwd_cl', _lib.ptr(x.permute(0, 2, 3, 1)), N, H, W, C,
+                      _lib.ptr(rois), R, outh, outw, spatial_scale, sampling_ratio, _lib.ptr(y),
+                      _lib.stream_ptr())
+            return y
+        x = x.contiguous()
+        ws = torch.empty((N * C * H * W,), dtype=torch.float32, device=x.device)
+        _lib.call('cmr_roi_align_fwd_ws', _lib.ptr(x), N, C, H, W, _lib.ptr(rois), R, outh, outw,
+                  spatial_scale, sampling_ratio, _lib.ptr(y), _lib.ptr(ws), ws.numel() * 4,
+                  _lib.stream_ptr())
+        return y
+    x = x.contiguous()
     _lib.call('cmr_roi_align_fwd', _lib.ptr(x), N, C, H, W, _lib.ptr(rois), R, outh,
               outw, spatial_scale, sampling_ratio, _lib.ptr(y), _lib.stream_ptr())
     return y
 
 
-def _backward(gy, rois, shape, outh, outw, spatial_scale, sampling_ratio):
+def _backward(gy, rois, shape, outh, outw, spatial_scale, sampling_ratio, channels_last=False):
     N, C, H, W = shape
     R = rois.shape[0]
     rois = rois.contiguous()
-    if _nhwc_ok(N, C, H, W, R, outh):
-        gt = gy.permute(0, 2, 3, 1).contiguous()
-        gxt = torch.empty((N, H, W, C), dtype=torch.float32, device=gy.device)
-        _lib.call('cmr_roi_align_nhwc_bwd', _lib.ptr(gt), _lib.ptr(rois), R, N, H, W, C, outh,
-                  outw, 1, spatial_scale, sampling_ratio, _lib.ptr(gxt), _lib.stream_ptr())
-        return gxt.permute(0, 3, 1, 2).contiguous()
     gy = gy.contiguous()
+    if _fast_ok(N, C, H, W, R, outh, outw):
+        if channels_last:       # the gradient in the layout of the map it belongs to
+            gxt = torch.empty((N, H, W, C), dtype=torch.float32, device=gy.device)
+            _lib.call('cmr_roi_align_bwd_cl', _lib.ptr(gy), _lib.ptr(rois), R, N, H, W, C, outh,
+                      outw, spatial_scale, sampling_ratio, _lib.ptr(gxt), _lib.stream_ptr())
+            return gxt.permute(0, 3, 1, 2)
+        gx = torch.empty((N, C, H, W), dtype=torch.float32, device=gy.device)
+        ws = torch.empty((N * C * H * W,), dtype=torch.float32, device=gy.device)
+        _lib.call('cmr_roi_align_bwd_ws', _lib.ptr(gy), _lib.ptr(rois), R, N, C, H, W, outh,
+                  outw, spatial_scale, sampling_ratio, _lib.ptr(gx), _lib.ptr(ws),
+                  ws.numel() * 4, _lib.stream_ptr())
+        return gx
     gx = torch.empty((N, C, H, W), dtype=torch.float32, device=gy.device)
     _lib.call('cmr_roi_align_bwd', _lib.ptr(gy), _lib.ptr(rois), R, N, C, H, W, outh, outw,
               spatial_scale, sampling_ratio, _lib.ptr(gx), _lib.stream_ptr())
@@ -59,14 +84,15 @@ class _ROIAlignFn(torch.autograd.Function):
     def forward(ctx, x, rois, outh, outw, spatial_scale, sampling_ratio):
         y = _forward(x, rois, outh, outw, spatial_scale, sampling_ratio)
         ctx.save_for_backward(rois)      # only the rois are retained (:62-63)
-        ctx.meta = (tuple(x.shape), outh, outw, spatial_scale, sampling_ratio)
+        ctx.meta = (tuple(x.shape), outh, outw, spatial_scale, sampling_ratio,
+                    _is_channels_last(x))
         return y
 
     @staticmethod
     def backward(ctx, gy):
         rois, = ctx.saved_tensors
-        shape, outh, outw, spatial_scale, sampling_ratio = ctx.meta
-        gx = _backward(gy, rois, shape, outh, outw, spatial_scale, sampling_ratio)
+        shape, outh, outw, spatial_scale, sampling_ratio, cl = ctx.meta
+        gx = _backward(gy, rois, shape, outh, outw, spatial_scale, sampling_ratio, cl)
         return gx, None, None, None, None, None
 
 
@@ -100,7 +126,7 @@ class ROIAlign2D(object):
                 rois.dtype, tuple(rois.shape)))
 
     def __call__(self, x, rois):
-        x, x_np = to_device(x)
+        x, x_np = to_device(x, keep_layout=True)
         rois, _ = to_device(rois)
         self.check_type_forward(x, rois)
         y = _ROIAlignFn.apply(x, rois, self.outh, self.outw, self.spatial_scale,

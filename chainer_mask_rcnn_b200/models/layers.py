@@ -101,7 +101,10 @@ class Context(object):
 
     def set_from_reference(self, name, value):
         kind, ref_shape, trainable = self.kinds[name]
-        t = torch.as_tensor(np.asarray(value, dtype=np.float32)).to(self.device)
+        if isinstance(value, torch.Tensor):
+            t = value.detach().to(self.device, torch.float32)
+        else:
+            t = torch.as_tensor(np.asarray(value, dtype=np.float32)).to(self.device)
         if tuple(t.shape) != ref_shape:
             raise ValueError('{}: expected shape {}, got {}'.format(name, ref_shape,
                                                                     tuple(t.shape)))

@@ -241,6 +241,36 @@ class MaskRCNNResNet(MaskRCNN):
         if pretrained_model:
             self.load_npz(pretrained_model)
 
+    def load_imagenet_resnet(self, src, bgr_to_rgb=True):
+        """What the reference does when no ``pretrained_model`` is given
+        (``pretrained_model='auto'``): take Chainer's ImageNet ``ResNet{50,101}Layers``
+        snapshot (keys ``conv1/W``, ``bn1/{gamma,beta,avg_mean,avg_var}``,
+        ``res2/a/conv1/W`` ... ``res5/b2/bn3/avg_var``; ``fc6`` is ignored), flip conv1 from
+        BGR to RGB input (resnet_extractor.py:53-56), fold every BatchNormalization into an
+        AffineChannel2D (:16-44, :59) and copy conv1 .. res4 into the extractor and res5 into
+        the head (mask_rcnn_resnet.py:68-76, 158-166).  ``src``: path of the ``.npz`` or a
+        name -> array mapping."""
+        from .resnet_extractor import _convert_bn_to_affine
+        if isinstance(src, str):
+            with np.load(src) as z:
+                src = {k: z[k] for k in z.files}
+        src = {k.lstrip('/'): v for k, v in src.items()}
+        if bgr_to_rgb and 'conv1/W' in src:
+            src['conv1/W'] = np.ascontiguousarray(np.asarray(src['conv1/W'])[:, ::-1])
+        params = {}
+        for key, value in _convert_bn_to_affine(src).items():
+            stage = key.split('/')[0]
+            if stage in ('conv1', 'bn1', 'res2', 'res3', 'res4'):
+                params['extractor/' + key] = value
+            elif stage == 'res5':
+                params['head/' + key] = value
+        missing = [n for n in self.ctx.names()
+                   if n.split('/')[1] in ('conv1', 'bn1', 'res2', 'res3', 'res4', 'res5') and
+                   n not in params]
+        if missing:
+            raise KeyError('ResNet snapshot lacks: ' + ', '.join(sorted(missing)[:5]))
+        self.load_state_dict(params, strict=False)
+
     def _init_params(self, seed, res_std, rpn_std, loc_std, score_std, mask_std):
         """Reference initialisers (mask_rcnn_resnet.py:57-64): Normal(0.01) for the RPN,
         score and mask layers, Normal(0.001) for cls_loc, zero biases.  The ImageNet

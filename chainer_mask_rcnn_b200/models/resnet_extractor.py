@@ -10,12 +10,65 @@ Input is the reference's (B, 3, H, W) float32 image batch; the returned feature 
 is shaped (B, 1024, H/16, W/16) like the reference's, as a channels-last view (the
 kernels work on NHWC memory).
 """
+import ctypes
+
+import numpy as np
 import torch
 
 from . import engine as E
 from .layers import BuildingBlock, Conv
 
 N_BLOCKS = {50: (3, 4, 6), 101: (3, 4, 23)}
+
+BN_EPS = 1e-5       # resnet_extractor.py:23
+_BN_LEAVES = ('gamma', 'beta', 'avg_mean', 'avg_var')
+
+
+def _get_affine_from_bn(bn):
+    """BatchNormalization -> AffineChannel2D (resnet_extractor.py:16-29):
+    ``W = gamma / sqrt(avg_var + 1e-5)``, ``b = beta - avg_mean * W``, computed on the device
+    by ``cmr_bn_fold`` one IEEE fp32 operation at a time (bit-exact with the reference's
+    NumPy expression).
+
+    ``bn``: an object with the reference's attribute names (``gamma`` / ``beta`` arrays or
+    objects holding ``.data``, ``avg_mean``, ``avg_var``) or a mapping with those keys.
+    -> (W, b) float32 CUDA tensors of shape (C,)."""
+    from .mask_rcnn import as_device_f32
+
+    def field(name):
+        v = bn[name] if isinstance(bn, dict) else getattr(bn, name)
+        v = getattr(v, 'data', v) if not isinstance(v, (np.ndarray, torch.Tensor)) else v
+        return as_device_f32(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) \
+            .contiguous().view(-1)
+
+    gamma, beta, mean, var = (field(n) for n in _BN_LEAVES)
+    C = gamma.numel()
+    if not (beta.numel() == mean.numel() == var.numel() == C):
+        raise ValueError('gamma, beta, avg_mean and avg_var must have the same size')
+    W = torch.empty_like(gamma)
+    b = torch.empty_like(gamma)
+    E._lib.call('cmr_bn_fold', E._p(gamma), E._p(beta), E._p(mean), E._p(var),
+                ctypes.c_float(BN_EPS), C, E._p(W), E._p(b), E.stream())
+    return W, b
+
+
+def _convert_bn_to_affine(params):
+    """The reference walks a chain and swaps every ``L.BatchNormalization`` for an
+    ``AffineChannel2D`` in place (resnet_extractor.py:32-44).  Here parameters are a flat
+    name -> array mapping (the npz snapshot): every ``<link>/{gamma,beta,avg_mean,avg_var}``
+    group becomes ``<link>/{W,b}`` (Chainer's batch counter ``<link>/N`` is dropped), every
+    other entry is passed through.  -> new dict; folded values are CUDA tensors."""
+    out = {}
+    for key, value in params.items():
+        root, _, leaf = key.rpartition('/')
+        if leaf in ('beta', 'avg_mean', 'avg_var', 'N') and (root + '/gamma') in params:
+            continue
+        if leaf == 'gamma':
+            out[root + '/W'], out[root + '/b'] = _get_affine_from_bn(
+                {n: params[root + '/' + n] for n in _BN_LEAVES})
+        else:
+            out[key] = value
+    return out
 
 
 class _Stem(Conv):

@@ -45,6 +45,8 @@ long long cmr_launch_count(void);
  *   1 cmr_conv_wgrad_tc       work = FLOPs
  *   2 cmr_roi_align_nhwc_fwd  work = bytes, 4*(R*C*oh*ow + N*C*H*W + 5R)
  *   3 cmr_roi_align_nhwc_bwd  work = bytes, same formula
+ *   6 cmr_roi_align_fwd_cl    work = bytes, same formula (the drop-in operator's kernels)
+ *   7 cmr_roi_align_bwd_cl    work = bytes, same formula (zero fill of gx included)
  *   4 / 5 the kind-0 launches again, split by what bounds them: 4 = tensor-bound (FLOPs
  *     >= 110 x algorithmic bytes; work = FLOPs), 5 = HBM-bound (work = algorithmic bytes:
  *     activations, filter, output, residual and mask operands once each).  Collect 4 and
@@ -68,6 +70,41 @@ int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int N, int C,
                       int H, int W, int outh, int outw, float spatial_scale,
                       int sampling_ratio, float* gx, void* stream);
 
+/* The same operator at speed: the feature map is read channels-last (vector loads of 4
+ * channels, whole 128-byte lines per warp), the pooled tensor stays in the reference's
+ * (R,C,outh,outw) layout -- each CTA stages its (64 channels x outh*outw) block, which is
+ * contiguous in that layout, in shared memory and moves it as full lines.  Same products as
+ * the reference, summed separably (a few ulp apart; cmr_roi_align_fwd / _bwd above keep the
+ * reference's summation order).
+ *   _cl  : x_nhwc (N,H,W,C) / gx_nhwc (N,H,W,C, zero-filled by the callee), C % 4 == 0;
+ *          CMR_ERR_UNSUPPORTED when cmr_roi_align_cl_supported(...) == 0.
+ *   _ws  : reference-layout x / gx plus a caller-owned workspace of
+ *          cmr_roi_align_workspace_bytes(N,C,H,W) bytes for the re-laid map (2 % of the
+ *          pooled tensor's bytes at R = 1000); falls back to cmr_roi_align_fwd / _bwd when
+ *          the workspace is NULL / too small or the shape is not supported.
+ * A RoI whose batch index is outside [0, N) produces zeros / no gradient in every variant. */
+int cmr_roi_align_cl_supported(int N, int C, int H, int W, int R, int outh, int outw);
+int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, int C,
+                         const float* rois, int R, int outh, int outw,
+                         float spatial_scale, int sampling_ratio, float* y,
+                         void* stream);
+int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, int N, int H,
+                         int W, int C, int outh, int outw, float spatial_scale,
+                         int sampling_ratio, float* gx_nhwc, void* stream);
+size_t cmr_roi_align_workspace_bytes(int N, int C, int H, int W);
+int cmr_roi_align_fwd_ws(const float* x, int N, int C, int H, int W,
+                         const float* rois, int R, int outh, int outw,
+                         float spatial_scale, int sampling_ratio, float* y,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int cmr_roi_align_bwd_ws(const float* gy, const float* rois, int R, int N, int C,
+                         int H, int W, int outh, int outw, float spatial_scale,
+                         int sampling_ratio, float* gx, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* (batch, rows, cols) -> (batch, cols, rows), fp32: NCHW <-> NHWC re-layout
+ * (rows = C, cols = H*W or the reverse). */
+int cmr_transpose_batched(const float* in, int batch, int rows, int cols, float* out,
+                          void* stream);
+
 /* Same operator on channels-last tensors, used inside the model
  * (ResNetRoIHead.__call__, models/mask_rcnn_resnet.py:168-181):
  * x (N,H,W,C), y (R,outh/bin_stride,outw/bin_stride,C).  Only the bins
@@ -84,6 +121,28 @@ int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N,
                            int H, int W, int C, int outh, int outw,
                            int bin_stride, float spatial_scale,
                            int sampling_ratio, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * AffineChannel2D as a stand-alone operator, reference layout (x (N,C,H,W) fp32
+ * contiguous, HW = H*W; W, b (C,)).  Replaces AffineChannel2DFunction.forward /
+ * backward (chainer_mask_rcnn/functions/affine_channel_2d.py:17-20, 48-55):
+ *   fwd: y = W[c] * x + b[c]      (a multiplication and an addition, as NumPy rounds)
+ *   bwd: gx = W[c] * gy;  gW[c] = sum over (n,h,w) of x * gy;  gb[c] = sum of gy
+ * (inside the model the affine is the convolution kernels' epilogue instead).  The
+ * backward's two-stage reduction is deterministic; workspace =
+ * cmr_affine_channel_bwd_workspace_bytes(N, C) bytes.
+ * ------------------------------------------------------------------------ */
+int cmr_affine_channel_fwd(const float* x, const float* W, const float* b, int N, int C,
+                           int HW, float* y, void* stream);
+size_t cmr_affine_channel_bwd_workspace_bytes(int N, int C);
+int cmr_affine_channel_bwd(const float* x, const float* W, const float* gy, int N, int C,
+                           int HW, float* gx, float* gW, float* gb, void* workspace,
+                           size_t workspace_bytes, void* stream);
+/* BatchNormalization -> AffineChannel2D (_get_affine_from_bn,
+ * chainer_mask_rcnn/models/resnet_extractor.py:16-29): W = gamma / sqrt(var + eps),
+ * b = beta - mean * W, each step one IEEE fp32 operation (bit-exact with NumPy). */
+int cmr_bn_fold(const float* gamma, const float* beta, const float* mean,
+                const float* var, float eps, int C, float* W, float* b, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Greedy NMS on score-sorted boxes (y1,x1,y2,x2), IoU >= thresh suppresses.

@@ -139,6 +139,8 @@ def bottleneck(p, root, x, stride, is_a, tape=None):
     sc = _conv_affine(p, root, 4, x, stride, 0, False, tape) if is_a else x
     y = nn.relu(h3 + sc)
     cache = (x, h1, h2, y)
+    if tape is not None:     # every tensor a per-layer parity test needs (tests/test_gpu_config0.py)
+        tape[root] = dict(x=x, h1=h1, h2=h2, h3=h3, sc=sc if is_a else None, y=y)
     return y, cache
 
 

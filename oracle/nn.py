@@ -156,6 +156,35 @@ def affine_channel_2d_backward(x, W, gy):
     return gx, gW, gb
 
 
+def bn_to_affine(gamma, beta, avg_mean, avg_var, eps=1e-5):
+    """_get_affine_from_bn (models/resnet_extractor.py:16-29): the AffineChannel2D that
+    replaces a BatchNormalization in test mode, W = gamma / sqrt(var + 1e-5),
+    b = beta - mean * W, all float32 (pinned: tests/golden/bn_fold.npz holds the outputs of
+    the reference function run verbatim)."""
+    std = np.sqrt(avg_var.astype(f32) + f32(eps))
+    W = (gamma.astype(f32) / std).astype(f32)
+    b = (beta.astype(f32) - avg_mean.astype(f32) * W).astype(f32)
+    return W, b
+
+
+def convert_bn_to_affine(params):
+    """_convert_bn_to_affine (models/resnet_extractor.py:32-44) on a flat parameter dict:
+    every '<link>/{gamma,beta,avg_mean,avg_var}' group (Chainer BatchNormalization; its
+    counter 'N' is dropped) becomes '<link>/{W,b}'; everything else is passed through."""
+    out = {}
+    for key, value in params.items():
+        root, _, leaf = key.rpartition('/')
+        if leaf in ('beta', 'avg_mean', 'avg_var', 'N') and (root + '/gamma') in params:
+            continue
+        if leaf == 'gamma':
+            out[root + '/W'], out[root + '/b'] = bn_to_affine(
+                value, params[root + '/beta'], params[root + '/avg_mean'],
+                params[root + '/avg_var'])
+        else:
+            out[key] = value
+    return out
+
+
 def relu(x):
     return np.maximum(x, 0)
 

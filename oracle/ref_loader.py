@@ -189,3 +189,105 @@ def ref_roi_align_backward(x_shape, rois_xy, gy, outh, outw, spatial_scale,
     f._bottom_data_shape = tuple(x_shape)
     gx, _ = f.backward_cpu((None, rois_xy), (gy,))
     return gx
+
+
+def load_resnet_extractor_module():
+    """-> module of chainer_mask_rcnn/models/resnet_extractor.py (``_get_affine_from_bn`` and
+    ``_convert_bn_to_affine``, :16-44, run verbatim), or None.  chainer.links gets a bare
+    ``BatchNormalization`` class, ``chainer_mask_rcnn.links.AffineChannel2D`` a two-array
+    stand-in with the reference's attribute names; ``fcn`` and the ResNet*Layers bases are
+    empty (only the two module-level functions are used)."""
+    import numpy
+
+    class _Var(object):
+        def __init__(self, a):
+            self.data = a
+            self.array = a
+            self.size = a.size
+
+    class BatchNormalization(object):
+        def __init__(self, gamma, beta, avg_mean, avg_var):
+            self.gamma, self.beta = _Var(gamma), _Var(beta)
+            self.avg_mean, self.avg_var = avg_mean, avg_var
+
+    class AffineChannel2D(object):
+        def __init__(self, channels):
+            self.W = _Var(numpy.zeros((channels,), numpy.float32))
+            self.b = _Var(numpy.zeros((channels,), numpy.float32))
+
+    stubs = _stub_chainer()
+    links = types.ModuleType('chainer.links')
+    links.BatchNormalization = BatchNormalization
+    stubs['chainer.links'] = links
+    stubs['chainer'].links = links
+    stubs['chainer'].dataset = types.SimpleNamespace(get_dataset_directory=lambda *a, **k: '')
+    for n in ('chainer.links.model', 'chainer.links.model.vision',
+              'chainer.links.model.vision.resnet'):
+        stubs[n] = types.ModuleType(n)
+    stubs['chainer.links.model.vision.resnet'].ResNet50Layers = type('ResNet50Layers', (), {})
+    stubs['chainer.links.model.vision.resnet'].ResNet101Layers = type('ResNet101Layers', (), {})
+    stubs['fcn'] = types.ModuleType('fcn')
+    for n in ('chainer_mask_rcnn', 'chainer_mask_rcnn.models', 'chainer_mask_rcnn.links'):
+        stubs[n] = types.ModuleType(n)
+        stubs[n].__path__ = []
+    stubs['chainer_mask_rcnn.links'].AffineChannel2D = AffineChannel2D
+    stubs['chainer_mask_rcnn'].links = stubs['chainer_mask_rcnn.links']
+    mod = _load('chainer_mask_rcnn/models/resnet_extractor.py',
+                'chainer_mask_rcnn.models.resnet_extractor', stubs)
+    if mod is not None:
+        mod._BatchNormalization = BatchNormalization
+        mod._AffineChannel2D = AffineChannel2D
+    return mod
+
+
+class StubChain(object):
+    """The three chainer.Chain methods ``_convert_bn_to_affine`` uses (namedlinks in
+    Chainer's order -- '/', then every child sorted by name, depth first --, add_link, and
+    attribute deletion)."""
+
+    def __init__(self):
+        object.__setattr__(self, '_children', [])
+
+    def add_link(self, name, link):
+        object.__setattr__(self, name, link)
+        self._children.append(name)
+
+    def __delattr__(self, name):
+        object.__delattr__(self, name)
+        if name in self._children:
+            self._children.remove(name)
+
+    def namedlinks(self, skipself=False):
+        if not skipself:
+            yield '/', self
+        for name in sorted(self._children):
+            child = getattr(self, name)
+            yield '/' + name, child
+            if hasattr(child, 'namedlinks'):
+                for path, link in child.namedlinks(True):
+                    yield '/' + name + path, link
+
+
+def ref_convert_bn_to_affine(bn_params):
+    """``_convert_bn_to_affine`` (resnet_extractor.py:32-44) run verbatim on a tree of stub
+    links built from ``{'res2/a/bn1': (gamma, beta, avg_mean, avg_var), ...}``.
+    -> {'res2/a/bn1': (W, b), ...} read back from the AffineChannel2D links it installed."""
+    mod = load_resnet_extractor_module()
+    root = StubChain()
+    for path, (gamma, beta, mean, var) in bn_params.items():
+        node = root
+        parts = path.split('/')
+        for key in parts[:-1]:
+            if not hasattr(node, key):
+                node.add_link(key, StubChain())
+            node = getattr(node, key)
+        node.add_link(parts[-1], mod._BatchNormalization(gamma, beta, mean, var))
+    mod._convert_bn_to_affine(root)
+    out = {}
+    for path in bn_params:
+        node = root
+        for key in path.split('/'):
+            node = getattr(node, key)
+        assert isinstance(node, mod._AffineChannel2D), path
+        out[path] = (node.W.data.copy(), node.b.data.copy())
+    return out

@@ -15,6 +15,8 @@ small .npz fixtures committed next to this script:
                         hides sampling-ratio errors): feature-stride-16 boxes,
                         7x7 and 14x14 outputs, sampling_ratio 0 and 2
   affine_channel.npz    functions/affine_channel_2d.py forward/backward
+  bn_fold.npz           models/resnet_extractor.py:16-44 (_get_affine_from_bn through
+                        _convert_bn_to_affine) on a small tree of BatchNormalization stubs
   proposal_targets.npz  models/utils/proposal_target_creator.py on a seeded scene
   detect.npz            MaskRCNN._to_bboxes (+ _suppress) and segm_results of
                         models/mask_rcnn.py on seeded head outputs (tests/synth.py
@@ -115,6 +117,29 @@ def affine_fixture():
     return dict(x=x, W=W, b=b, gy=gy, y=y, gx=gx, gW=gW, gb=gb)
 
 
+BN_FOLD_LINKS = (('bn1', 64), ('res2/a/bn1', 37), ('res2/a/bn4', 256), ('res3/b2/bn3', 8))
+
+
+def bn_fold_fixture():
+    """The reference's BatchNormalization -> AffineChannel2D conversion run verbatim
+    (ref_loader.ref_convert_bn_to_affine); variances from tiny to large so that the
+    1e-5 epsilon matters for some channels."""
+    rs = np.random.RandomState(3)
+    out = {}
+    tree = {}
+    for path, c in BN_FOLD_LINKS:
+        gamma = rs.uniform(0.2, 2.0, c).astype(np.float32)
+        beta = rs.standard_normal(c).astype(np.float32)
+        mean = (rs.standard_normal(c) * 3).astype(np.float32)
+        var = np.exp(rs.uniform(np.log(1e-7), np.log(50.), c)).astype(np.float32)
+        tree[path] = (gamma, beta, mean, var)
+        for name, a in zip(('gamma', 'beta', 'avg_mean', 'avg_var'), tree[path]):
+            out['%s/%s' % (path, name)] = a
+    for path, (W, b) in ref_loader.ref_convert_bn_to_affine(tree).items():
+        out[path + '/W'], out[path + '/b'] = W, b
+    return out
+
+
 def proposal_target_fixture():
     """The reference's own ProposalTargetCreator (models/utils/proposal_target_creator.py:
     63-184) run verbatim on a seeded scene (tests/synth.py detection_scene)."""
@@ -188,6 +213,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'roi_align_check.npz'), **check_fixture())
     np.savez_compressed(os.path.join(HERE, 'roi_align_random.npz'), **random_fixture())
     np.savez_compressed(os.path.join(HERE, 'affine_channel.npz'), **affine_fixture())
+    np.savez_compressed(os.path.join(HERE, 'bn_fold.npz'), **bn_fold_fixture())
     np.savez_compressed(os.path.join(HERE, 'proposal_targets.npz'), **proposal_target_fixture())
     np.savez_compressed(os.path.join(HERE, 'detect.npz'), **detect_fixture())
     np.savez_compressed(os.path.join(HERE, 'prepare.npz'), **prepare_fixture())

@@ -1,0 +1,187 @@
+"""BASELINE.json configs[0] at full width (SURVEY.md 8d "Config 1"): one VOC-sized image
+(3 x 600 x 1000) through MaskRCNNResNet50 (base 64, n_fg = 20, A = 12 anchors: scales
+4, 8, 16, 32), test mode (6000 -> 1000 proposals), head on a 64-RoI subset.
+
+Every convolution (+ its AffineChannel2D, ReLU and residual add), the pooling layer, ROIAlign,
+the deconvolution and the linear layers are run ON THE ORACLE'S OWN INPUT of that layer --
+identical inputs, one layer deep -- and must satisfy the north-star bound
+
+        max|got - want| / max|want|  <=  1e-3          (TOL below)
+
+(the GEMM inputs pass through the TF32 rounding that the producing layer's epilogue applies
+in the model).  Proposal indices and NMS keep masks on the oracle's RPN outputs must be
+equal.  The oracle (oracle/model.py: NumPy im2col + sgemm) needs ~20 s of host time for the
+full-width backbone, RPN and 64-RoI head."""
+import numpy as np
+import pytest
+import torch
+
+from chainer_mask_rcnn_b200 import functions, models, utils
+from chainer_mask_rcnn_b200.models import engine as E
+from oracle import bbox as ob
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+N_FG, SCALES, H, W = 20, (4, 8, 16, 32), 600, 1000
+N_ROI = 64
+
+
+def rel(got, want):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+def nhwc(a):
+    """oracle NCHW array -> the kernel's input: channels-last, TF32-rounded."""
+    return E.round_tf32(torch.from_numpy(np.ascontiguousarray(a.transpose(0, 2, 3, 1))).cuda())
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+@pytest.fixture(scope='module')
+def cfg0():
+    rs = np.random.RandomState(0)
+    cfg = om.Config(n_layers=50, n_fg_class=N_FG, anchor_scales=SCALES, roi_size=14, base=64)
+    params = om.make_params(cfg, rs)
+    for k in params:                # non-zero biases everywhere
+        if k.endswith('/b') and '/bn' not in k:
+            params[k] = (rs.standard_normal(params[k].shape) * 0.05).astype(np.float32)
+    x = (rs.uniform(0, 255, (1, 3, H, W)).astype(np.float32) -
+         np.asarray((123.152, 115.903, 103.063), np.float32)[None, :, None, None])
+    tape = {}
+    feat, _ = om.extractor(cfg, params, x, tape)
+    rpn_locs, rpn_scores, anchor, h_rpn = om.rpn_forward(cfg, params, feat)
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14)
+    model.load_state_dict(params)
+    model.ctx.prepare(backward=False)
+    return dict(cfg=cfg, params=params, x=x, tape=tape, feat=feat, rpn_locs=rpn_locs,
+                rpn_scores=rpn_scores, anchor=anchor, h_rpn=h_rpn, model=model)
+
+
+def _check_block(blk, t, errs, name, x=None):
+    """One bottleneck, every layer on the oracle's input of that layer."""
+    x = nhwc(t['x'] if x is None else x)
+    errs[name + '/conv1'] = rel(nchw(blk.conv1.forward(x, relu=True)), t['h1'])
+    errs[name + '/conv2'] = rel(nchw(blk.conv2.forward(nhwc(t['h1']), relu=True)), t['h2'])
+    errs[name + '/conv3'] = rel(nchw(blk.conv3.forward(nhwc(t['h2']), round_out=False)), t['h3'])
+    if blk.is_a:
+        errs[name + '/conv4'] = rel(nchw(blk.conv4.forward(x, round_out=False)), t['sc'])
+        sc = torch.from_numpy(np.ascontiguousarray(t['sc'].transpose(0, 2, 3, 1))).cuda()
+    else:
+        sc = x
+    # conv3 + affine + residual add + ReLU as the model runs it (one fused epilogue)
+    errs[name + '/out'] = rel(nchw(blk.conv3.forward(nhwc(t['h2']), relu=True, addend=sc)), t['y'])
+
+
+def test_extractor_every_layer_on_identical_inputs(cfg0):
+    m, tape = cfg0['model'], cfg0['tape']
+    ex = m.extractor
+    errs = {}
+    xt = torch.from_numpy(cfg0['x']).cuda()
+    h = ex.conv1.forward(xt)                                  # conv1 + bias + bn1 + ReLU
+    assert tuple(h.shape) == (1, 300, 500, 64)
+    errs['conv1'] = rel(nchw(h), tape['extractor/conv1'])
+    p = E.max_pool(nhwc(tape['extractor/conv1']), 3, 2, 1, cover_all=True)
+    assert tuple(p.shape) == (1, 151, 251, 64)               # Chainer's cover_all size
+    errs['pool1'] = rel(nchw(p), tape['extractor/pool1'])
+    for stage in ('res2', 'res3', 'res4'):
+        bb = getattr(ex, stage)
+        for nm, blk in zip(bb.names, bb.blocks):
+            root = 'extractor/%s/%s' % (stage, nm)
+            _check_block(blk, tape[root], errs, '%s/%s' % (stage, nm))
+    assert tape['extractor/res4'].shape == (1, 1024, 38, 63)
+    assert len(errs) == 2 + 16 * 4 + 3                       # 43 convolutions + pool + 16 sums
+    bad = {k: v for k, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+    # the whole extractor chained (40 TF32 layers deep) stays within 5e-3
+    got = m.extractor(cfg0['x'])
+    assert rel(got, cfg0['feat']) <= 5e-3
+
+
+def test_rpn_layers_and_bit_exact_proposals(cfg0):
+    m, cfg = cfg0['model'], cfg0['cfg']
+    rpn = m.rpn
+    feat, h_want = cfg0['feat'], cfg0['h_rpn']
+    h = rpn.conv1.forward(nhwc(feat), relu=True)
+    assert rel(nchw(h), h_want) <= TOL
+    locs = rpn.loc.forward(nhwc(h_want), round_out=False).view(1, -1, 4)
+    scores = rpn.score.forward(nhwc(h_want), round_out=False).view(1, -1)
+    assert rel(locs, cfg0['rpn_locs']) <= TOL
+    assert rel(scores, cfg0['rpn_scores']) <= TOL
+    # anchors: enumeration order and values
+    a_np, _ = rpn.anchors(38, 63, h.device)
+    np.testing.assert_array_equal(a_np, cfg0['anchor'])
+    assert len(a_np) == 38 * 63 * 12
+    # ProposalCreator on the ORACLE's RPN outputs: index lists equal, boxes to fp32 round-off
+    pc_want = ob.ProposalCreator(**cfg.proposal_creator_params)
+    want_roi, want_idx = pc_want(cfg0['rpn_locs'][0], cfg0['rpn_scores'][0], cfg0['anchor'],
+                                 (H, W), 1.0, train=False, return_index=True)
+    with utils.config.using_config('train', False):
+        roi, idx = utils.ProposalCreator(**cfg.proposal_creator_params)(
+            cfg0['rpn_locs'][0], cfg0['rpn_scores'][0], cfg0['anchor'], (H, W), 1.0,
+            return_index=True)
+    assert len(want_idx) > 100
+    np.testing.assert_array_equal(idx, want_idx)
+    np.testing.assert_allclose(roi, want_roi, rtol=1e-6, atol=1e-4)
+    # NMS keep list and the 64-bit suppression masks on the oracle's sorted candidates
+    cand = ob.loc2bbox(cfg0['anchor'], cfg0['rpn_locs'][0])
+    cand[:, 0::2] = np.clip(cand[:, 0::2], 0, H)
+    cand[:, 1::2] = np.clip(cand[:, 1::2], 0, W)
+    order = cfg0['rpn_scores'][0].argsort()[::-1][:6000]
+    cand = np.ascontiguousarray(cand[order][:2000])
+    keep, mask = utils.nms_suppression_bitmask(cand, 0.7)
+    np.testing.assert_array_equal(keep, ob.non_maximum_suppression(cand, 0.7))
+    want_mask = ob.nms_suppression_bitmask(cand, 0.7)
+    n, nb = len(cand), (len(cand) + 63) // 64
+    tri = np.arange(nb)[None, :] >= (np.arange(n) // 64)[:, None]   # words the sweep reads
+    np.testing.assert_array_equal(mask[tri], want_mask[tri])
+
+
+def test_roi_align_and_head_every_layer_on_identical_inputs(cfg0):
+    m, cfg, params = cfg0['model'], cfg0['cfg'], cfg0['params']
+    head = m.head
+    feat = cfg0['feat']
+    pc = ob.ProposalCreator(**cfg.proposal_creator_params)
+    rois = pc(cfg0['rpn_locs'][0], cfg0['rpn_scores'][0], cfg0['anchor'], (H, W), 1.0, train=False)
+    sel = np.linspace(0, len(rois) - 1, N_ROI).astype(np.int64)
+    rois = np.ascontiguousarray(rois[sel])
+    idx = np.zeros((N_ROI,), np.int32)
+    tape = {}
+    w_cl, w_sc, w_mask, cache = om.head_forward(cfg, params, feat, rois, idx, tape)
+    errs = {}
+    # ROIAlign: the drop-in operator (14x14, reference layout) and the model's strided form
+    idx_rois = np.concatenate((idx.astype(np.float32)[:, None], rois), axis=1)
+    got = functions.roi_align_2d(torch.from_numpy(feat).cuda(), torch.from_numpy(idx_rois).cuda(),
+                                 14, 14, 1. / 16, axes='yx')
+    errs['roi_align_2d'] = rel(got, tape['head/pool'])
+    ft = torch.from_numpy(np.ascontiguousarray(feat.transpose(0, 2, 3, 1))).cuda()
+    pool7 = E.roi_align_nhwc(ft, head._rois_xy(torch.from_numpy(rois).cuda(),
+                                               torch.from_numpy(idx).cuda()),
+                             14, 14, 2, 1. / 16, round_out=False)
+    errs['roi_align_strided'] = rel(nchw(pool7), tape['head/pool'][:, :, ::2, ::2])
+    # res5: block a reads the 14x14 pool with stride 2 = the 7x7 strided pool with stride 1
+    for nm, blk in zip(head.res5.names, head.res5.blocks):
+        t = tape['head/res5/' + nm]
+        _check_block(blk, t, errs, 'res5/' + nm,
+                     x=t['x'][:, :, ::2, ::2] if nm == 'a' else None)
+    res5 = tape['head/res5']
+    pool5 = E.avg_pool(nhwc(res5), round_out=False)
+    errs['avg_pool'] = rel(pool5, cache['pool5'].reshape(N_ROI, -1))
+    p4 = E.round_tf32(torch.from_numpy(cache['pool5'].reshape(N_ROI, 1, 1, -1)).cuda())
+    errs['cls_loc'] = rel(head.cls_loc.forward(p4, round_out=False).view(N_ROI, -1), w_cl)
+    errs['score'] = rel(head.score.forward(p4, round_out=False).view(N_ROI, -1), w_sc)
+    d6 = head.deconv6.forward(nhwc(res5))
+    errs['deconv6'] = rel(nchw(d6), tape['head/deconv6'])
+    mk = head.mask.forward(nhwc(tape['head/deconv6']), round_out=False)
+    errs['mask'] = rel(nchw(mk), w_mask)
+    assert len(errs) == 2 + (5 + 4 + 4) + 5
+    bad = {k: v for k, v in errs.items() if not v <= TOL}
+    assert not bad, bad
+    # the head chained on the oracle's feature map (13 TF32 layers deep)
+    cl, sc, mask = head(torch.from_numpy(feat).cuda(), rois, idx)
+    assert rel(cl, w_cl) <= 5e-3 and rel(sc, w_sc) <= 5e-3 and rel(mask, w_mask) <= 5e-3

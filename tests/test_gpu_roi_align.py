@@ -213,3 +213,99 @@ def test_full_size_against_torchvision_cpu():
     y.backward(torch.ones_like(y))
     total = float(xt.grad.double().sum())
     assert abs(total - y.numel()) / y.numel() < 1e-5
+
+
+# ----------------------------------------------------- channels-last fast path --
+@pytest.mark.parametrize('C,oh,ratio', [(64, 14, 0), (72, 7, 0), (132, 14, 2), (1024, 14, 0)])
+def test_operator_on_channels_last_map_and_plain_map_agree(C, oh, ratio):
+    """The drop-in operator on a channels-last feature map (what this package's extractor
+    returns: no re-layout) and on a plain NCHW map (re-laid once into a workspace): same
+    kernel, identical bits; both within 1e-5 of the oracle; gradients come back in the
+    layout of the map they belong to."""
+    rs = np.random.RandomState(C + oh)
+    N, H, W = 2, 21, 30
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = synth.rois_xy(rs, 50, N, H * 16, W * 16, lo=2., hi=500.)
+    rois = np.concatenate([rois, np.array([
+        [0, 0, 0, W * 16, H * 16], [1, -40, -30, 90, 70],
+        [0, W * 16 - 50, H * 16 - 60, W * 16 + 45, H * 16 + 70], [0, 100, 100, 100, 100],
+        [1, -200, 50, -100, 90]], np.float32)])
+    gy = rs.standard_normal((len(rois), C, oh, oh)).astype(np.float32)
+    want = ora.roi_align_forward(x, rois, oh, oh, 1. / 16, ratio)
+    want_gx = ora.roi_align_backward(x.shape, rois, gy, oh, oh, 1. / 16, ratio)
+    rt, gt = torch.from_numpy(rois).cuda(), torch.from_numpy(gy).cuda()
+    outs = []
+    for channels_last in (False, True):
+        xt = torch.from_numpy(x).cuda()
+        if channels_last:
+            xt = xt.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        xt.requires_grad_(True)
+        y = functions.roi_align_2d(xt, rt, oh, oh, 1. / 16, ratio)
+        assert y.is_contiguous() and tuple(y.shape) == want.shape
+        y.backward(gt)
+        assert xt.grad.permute(0, 2, 3, 1).is_contiguous() == channels_last
+        assert _rel(y.detach().cpu().numpy(), want) <= REL
+        assert _rel(xt.grad.cpu().numpy(), want_gx) <= REL
+        outs.append((y.detach(), xt.grad.contiguous()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in range(len(rois)):
+        got = outs[0][0][k].cpu().numpy()
+        assert np.abs(got - want[k]).max() <= 1e-5 * max(np.abs(want[k]).max(), 1e-3), k
+
+
+def test_rois_taller_than_the_row_table_take_the_generic_path():
+    """An output row that spans more than 8 feature rows (RoI taller than 8 * outh feature
+    pixels) leaves the merged-row tables: same results through the per-bin path."""
+    rs = np.random.RandomState(3)
+    N, C, H, W = 1, 8, 150, 40
+    x = rs.standard_normal((N, C, H, W)).astype(np.float32)
+    rois = np.array([[0, 10, 5, 600, 2390], [0, 0, 0, W * 16, H * 16], [0, 30, 40, 90, 200]],
+                    np.float32)
+    gy = rs.standard_normal((3, C, 2, 2)).astype(np.float32)
+    want = ora.roi_align_forward(x, rois, 2, 2, 1. / 16, 0)
+    want_gx = ora.roi_align_backward(x.shape, rois, gy, 2, 2, 1. / 16, 0)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    y = functions.roi_align_2d(xt, torch.from_numpy(rois).cuda(), 2, 2, 1. / 16)
+    y.backward(torch.from_numpy(gy).cuda())
+    assert _rel(y.detach().cpu().numpy(), want) <= REL
+    assert _rel(xt.grad.cpu().numpy(), want_gx) <= 1e-4      # ~10^3 samples per bin
+    got, got_gx = _nhwc(x, rois, 2, 2, 1, 0, gy)
+    assert _rel(got, want) <= REL
+    assert _rel(got_gx, want_gx) <= 1e-4
+
+
+@pytest.mark.parametrize('exact', [False, True])
+def test_batch_index_outside_the_batch_is_an_empty_roi(exact):
+    """A malformed batch index (negative, >= N, NaN) never reads or writes out of bounds: the
+    RoI pools to zeros and passes no gradient, in every kernel."""
+    rs = np.random.RandomState(4)
+    x = rs.standard_normal((2, 8, 9, 11)).astype(np.float32)
+    rois = synth.rois_xy(rs, 6, 2, 9 * 16, 11 * 16)
+    bad = rois.copy()
+    bad[1, 0], bad[3, 0], bad[4, 0] = -1, 2, np.nan
+    good = np.array([0, 2, 5])
+    functions.ROIAlign2D.exact_order = exact
+    try:
+        xt = torch.from_numpy(x).cuda().requires_grad_(True)
+        y = functions.roi_align_2d(xt, torch.from_numpy(bad).cuda(), 7, 7, 1. / 16)
+        y.backward(torch.ones_like(y))
+        xr = torch.from_numpy(x).cuda().requires_grad_(True)
+        yr = functions.roi_align_2d(xr, torch.from_numpy(rois[good]).cuda(), 7, 7, 1. / 16)
+        yr.backward(torch.ones_like(yr))
+    finally:
+        functions.ROIAlign2D.exact_order = False
+    assert float(y[[1, 3, 4]].abs().max()) == 0.
+    assert torch.equal(y[good], yr)
+    assert _rel(xt.grad.cpu().numpy(), xr.grad.cpu().numpy()) <= 1e-6
+    got, got_gx = _nhwc(x, bad, 7, 7, 1, 0, np.ones((6, 8, 7, 7), np.float32))
+    assert np.abs(got[[1, 3, 4]]).max() == 0. and np.isfinite(got_gx).all()
+
+
+def test_transpose_batched_round_trip():
+    rs = np.random.RandomState(0)
+    for shape in ((2, 37, 50), (1, 1024, 3400), (3, 5, 1)):
+        a = torch.from_numpy(rs.standard_normal(shape).astype(np.float32)).cuda()
+        b = torch.empty((shape[0], shape[2], shape[1]), device='cuda')
+        _lib.call('cmr_transpose_batched', _lib.ptr(a), shape[0], shape[1], shape[2], _lib.ptr(b),
+                  _lib.stream_ptr())
+        assert torch.equal(b, a.transpose(1, 2).contiguous())

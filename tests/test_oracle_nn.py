@@ -171,3 +171,15 @@ def test_smooth_l1_and_loc_loss(sigma):
     assert abs(float(loss) - lt.item()) <= 2e-6 * max(abs(lt.item()), 1.)
     lt.backward()
     close(g, pt.grad, tol=1e-5)
+
+
+def test_affine_channel_matches_reference_golden(golden_dir):
+    """tests/golden/affine_channel.npz: functions/affine_channel_2d.py run verbatim."""
+    import os
+    g = np.load(os.path.join(golden_dir, 'affine_channel.npz'))
+    y = onn.affine_channel_2d(g['x'], g['W'].reshape(-1), g['b'].reshape(-1))
+    np.testing.assert_array_equal(y, g['y'])
+    gx, gW, gb = onn.affine_channel_2d_backward(g['x'], g['W'].reshape(-1), g['gy'])
+    np.testing.assert_array_equal(gx, g['gx'])
+    np.testing.assert_allclose(gW, g['gW'].reshape(-1), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(gb, g['gb'].reshape(-1), rtol=1e-6, atol=1e-6)
