@@ -11,5 +11,6 @@ from . import functions  # noqa: F401
 from . import utils  # noqa: F401
 from . import models  # noqa: F401
 from . import optimizers  # noqa: F401
+from . import datasets  # noqa: F401
 
 __version__ = '0.2.0'

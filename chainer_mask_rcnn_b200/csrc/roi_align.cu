@@ -696,20 +696,32 @@ struct RoiTileSmem {
   float4 xt[kColTaps];
 };
 
-template <int CH>
+// Element (channel c, bin p) of the CTA's staging tile.  kVec (outw even, outh*outw % 4 == 0,
+// the 14 x 14 case): rows of PS = round_up(P, 32) floats whose 16-byte groups are XOR-ed with
+// the channel quad's index -- the walkers access it a channel quad x two bins at a time
+// (8-byte accesses, banks spread by the XOR), the copy to / from global memory runs over whole
+// float4s of one channel (conflict-free, 512 B per warp instruction).  Otherwise: plain rows
+// of P + 1 floats, scalar accesses.
+template <bool kVec>
+__device__ __forceinline__ int tile_index(int c, int p, int PS) {
+  return kVec ? c * PS + (p ^ (((c >> 2) & 7) << 2)) : c * PS + p;
+}
+
+template <int CH, bool kVec>
 __global__ void __launch_bounds__(256)
 roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                         float* __restrict__ dst, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int chunks, int n_img) {
   extern __shared__ __align__(16) unsigned char roi_smem[];
   RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
-  RowBlend* rb = reinterpret_cast<RowBlend*>(roi_smem + sizeof(RoiTileSmem));
-  float* tile = reinterpret_cast<float*>(rb + outh);
+  float* tile = reinterpret_cast<float*>(roi_smem + sizeof(RoiTileSmem));
   constexpr int Q = CH / 4;
   const int r = blockIdx.x / chunks;
   const int c0 = (blockIdx.x - r * chunks) * CH;
   const int nch = min(CH, C - c0);
-  const int P = outh * outw, PS = P + 1;
+  const int P = outh * outw;
+  const int PS = kVec ? (P + 31) / 32 * 32 : P + 1;
+  RowBlend* rb = reinterpret_cast<RowBlend*>(tile + (size_t)CH * PS);
   const int C4 = C >> 2;
   const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
@@ -725,11 +737,26 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
   if (4 * quad < nch) {
     const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 +
                                                     (c0 >> 2) + quad);
-    float* t0 = tile + (size_t)(4 * quad) * PS;
+    const int cq = 4 * quad;
     for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
-      float* trow = t0 + ph * outw;
+      const int p0 = ph * outw;
+      float4 even = make_float4(0.f, 0.f, 0.f, 0.f);
       auto emit = [&](int pw, int, const float4& v) {
-        trow[pw] = v.x; trow[PS + pw] = v.y; trow[2 * PS + pw] = v.z; trow[3 * PS + pw] = v.w;
+        if (kVec) {
+          // two bins of a channel are 8 contiguous bytes of the tile (p0 + pw is even)
+          if ((pw & 1) == 0) {
+            even = v;
+          } else {
+            const int p = p0 + pw - 1;
+            *reinterpret_cast<float2*>(tile + tile_index<true>(cq, p, PS)) = make_float2(even.x, v.x);
+            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 1, p, PS)) = make_float2(even.y, v.y);
+            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 2, p, PS)) = make_float2(even.z, v.z);
+            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 3, p, PS)) = make_float2(even.w, v.w);
+          }
+        } else {
+          float* t = tile + (size_t)cq * PS + p0 + pw;
+          t[0] = v.x; t[PS] = v.y; t[2 * PS] = v.z; t[3 * PS] = v.w;
+        }
       };
       if (fast) {
         walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, emit);
@@ -740,40 +767,60 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
     }
   }
   __syncthreads();
+  // the CTA's (nch, P) block is contiguous in the pooled tensor
   float* out = dst + ((size_t)r * C + c0) * P;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < nch; c += nwarp) {
-    const float* tp = tile + (size_t)c * PS;
-    float* op = out + (size_t)c * P;
-    for (int p = lane; p < P; p += 32) op[p] = tp[p];
+  if (kVec) {
+    const int P4 = P >> 2;
+    for (int i = threadIdx.x; i < nch * P4; i += blockDim.x) {
+      const int c = i / P4, g4 = i - c * P4;
+      reinterpret_cast<float4*>(out)[i] =
+          *reinterpret_cast<const float4*>(tile + tile_index<true>(c, 4 * g4, PS));
+    }
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int c = warp; c < nch; c += nwarp) {
+      const float* tp = tile + (size_t)c * PS;
+      float* op = out + (size_t)c * P;
+      for (int p = lane; p < P; p += 32) op[p] = tp[p];
+    }
   }
 }
 
-template <int CH>
+template <int CH, bool kVec>
 __global__ void __launch_bounds__(256)
 roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int chunks, int n_img) {
   extern __shared__ __align__(16) unsigned char roi_smem[];
   RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
-  RowBlend* rb = reinterpret_cast<RowBlend*>(roi_smem + sizeof(RoiTileSmem));
-  float* tile = reinterpret_cast<float*>(rb + outh);
+  float* tile = reinterpret_cast<float*>(roi_smem + sizeof(RoiTileSmem));
   constexpr int Q = CH / 4;
   const int r = blockIdx.x / chunks;
   const int c0 = (blockIdx.x - r * chunks) * CH;
   const int nch = min(CH, C - c0);
-  const int P = outh * outw, PS = P + 1;
+  const int P = outh * outw;
+  const int PS = kVec ? (P + 31) / 32 * 32 : P + 1;
+  RowBlend* rb = reinterpret_cast<RowBlend*>(tile + (size_t)CH * PS);
   const int C4 = C >> 2;
   const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
   if (threadIdx.x == 0) sm->ok = outw * g.grid_w <= kColTaps ? 1 : 0;
   // the CTA's block of the pooled gradient: (nch, P) contiguous floats
   const float* in = gy + ((size_t)r * C + c0) * P;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int c = warp; c < nch; c += nwarp) {
-    float* tp = tile + (size_t)c * PS;
-    const float* ip = in + (size_t)c * P;
-    for (int p = lane; p < P; p += 32) tp[p] = __ldg(ip + p);
+  if (kVec) {
+    const int P4 = P >> 2;
+    for (int i = threadIdx.x; i < nch * P4; i += blockDim.x) {
+      const int c = i / P4, g4 = i - c * P4;
+      *reinterpret_cast<float4*>(tile + tile_index<true>(c, 4 * g4, PS)) =
+          __ldg(reinterpret_cast<const float4*>(in) + i);
+    }
+  } else {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int c = warp; c < nch; c += nwarp) {
+      float* tp = tile + (size_t)c * PS;
+      const float* ip = in + (size_t)c * P;
+      for (int p = lane; p < P; p += 32) tp[p] = __ldg(ip + p);
+    }
   }
   __syncthreads();
   build_row_blends(rb, &sm->ok, g, 0, 1, outh, H, row_bytes);
@@ -785,11 +832,23 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   const int rows_per_pass = blockDim.x / Q;
   if (4 * quad >= nch) return;
   char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4 + (c0 >> 2) + quad);
-  const float* t0 = tile + (size_t)(4 * quad) * PS;
+  const int cq = 4 * quad;
   for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
-    const float* trow = t0 + ph * outw;
+    const int p0 = ph * outw;
+    float4 odd = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch = [&](int pw, int) {
-      return make_float4(trow[pw], trow[PS + pw], trow[2 * PS + pw], trow[3 * PS + pw]);
+      if (kVec) {
+        if (pw & 1) return odd;
+        const int p = p0 + pw;
+        const float2 a = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq, p, PS));
+        const float2 b = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 1, p, PS));
+        const float2 c = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 2, p, PS));
+        const float2 d = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 3, p, PS));
+        odd = make_float4(a.y, b.y, c.y, d.y);
+        return make_float4(a.x, b.x, c.x, d.x);
+      }
+      const float* t = tile + (size_t)cq * PS + p0 + pw;
+      return make_float4(t[0], t[PS], t[2 * PS], t[3 * PS]);
     };
     if (fast) {
       walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, fetch);
@@ -802,9 +861,13 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 
 constexpr int kClChannels = 64;   // channels per CTA of the two kernels above
 
+bool cl_vec(int outh, int outw) { return (outw & 1) == 0 && ((outh * outw) & 3) == 0; }
+
 size_t cl_smem_bytes(int outh, int outw) {
-  return sizeof(RoiTileSmem) + sizeof(RowBlend) * (size_t)outh +
-         sizeof(float) * (size_t)kClChannels * (outh * outw + 1);
+  const int P = outh * outw;
+  const int PS = cl_vec(outh, outw) ? (P + 31) / 32 * 32 : P + 1;
+  return sizeof(RoiTileSmem) + sizeof(float) * (size_t)kClChannels * PS +
+         sizeof(RowBlend) * (size_t)outh;
 }
 
 int cl_threads(int outh) {
@@ -953,13 +1016,22 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(x_nhwc && rois && y);
   const size_t smem = cl_smem_bytes(outh, outw);
-  int rc = cl_configure(roi_align_cl_fwd_kernel<kClChannels>, smem);
+  const bool vec = cl_vec(outh, outw);
+  int rc = vec ? cl_configure(roi_align_cl_fwd_kernel<kClChannels, true>, smem)
+               : cl_configure(roi_align_cl_fwd_kernel<kClChannels, false>, smem);
   if (rc != CMR_OK) return rc;
   const int chunks = ceil_div(C, kClChannels);
   prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
-  roi_align_cl_fwd_kernel<kClChannels><<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
-      sampling_ratio, chunks, N);
+  if (vec)
+    roi_align_cl_fwd_kernel<kClChannels, true>
+        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
+            sampling_ratio, chunks, N);
+  else
+    roi_align_cl_fwd_kernel<kClChannels, false>
+        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
+            sampling_ratio, chunks, N);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -973,7 +1045,9 @@ extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, i
   if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
   CMR_REQUIRE(R == 0 || (gy && rois));
   const size_t smem = cl_smem_bytes(outh, outw);
-  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels>, smem);
+  const bool vec = cl_vec(outh, outw);
+  int rc = vec ? cl_configure(roi_align_cl_bwd_kernel<kClChannels, true>, smem)
+               : cl_configure(roi_align_cl_bwd_kernel<kClChannels, false>, smem);
   if (rc != CMR_OK) return rc;
   prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
   cudaError_t me =
@@ -984,9 +1058,16 @@ extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, i
     return CMR_OK;
   }
   const int chunks = ceil_div(C, kClChannels);
-  roi_align_cl_bwd_kernel<kClChannels><<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-      gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
-      sampling_ratio, chunks, N);
+  if (vec)
+    roi_align_cl_bwd_kernel<kClChannels, true>
+        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+            gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
+            sampling_ratio, chunks, N);
+  else
+    roi_align_cl_bwd_kernel<kClChannels, false>
+        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
+            gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
+            sampling_ratio, chunks, N);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;

@@ -302,7 +302,9 @@ class MaskRCNN(object):
         if allb.size == 0:
             return [torch.zeros((0, n_fg, M, M), dtype=torch.float32, device=feat.device)
                     for _ in range(B)]
-        scales = np.asarray(scales, np.float32)
+        # float32 boxes times the float64 scales concat_examples returns, rounded once to
+        # float32 (mask_rcnn.py:281-282)
+        scales = np.asarray(scales, np.float64)
         rois = torch.from_numpy((allb * scales[roi_indices][:, None]).astype(np.float32))
         rois = rois.to(feat.device)
         idx = torch.from_numpy(np.asarray(roi_indices, np.int32)).to(feat.device)
@@ -332,7 +334,7 @@ class MaskRCNN(object):
         """imgs: list of (3, H, W) float32 RGB arrays in [0, 255].
         -> bboxes, masks, labels, scores (lists per image; mask_rcnn.py:307-337)."""
         x, sizes, scales = self._prepare_device(imgs)
-        scales = np.asarray(scales, np.float32)
+        scales = np.asarray(scales, np.float64)        # as concat_examples returns them
         with config.using_config('train', False), torch.no_grad():
             feat, rois, cnt, cls_locs, scores, _ = self._forward_padded(x, scales, False)
             bboxes, labels, scores = self._cut(

@@ -265,8 +265,9 @@ class MaskRCNNResNet(MaskRCNN):
             elif stage == 'res5':
                 params['head/' + key] = value
         missing = [n for n in self.ctx.names()
-                   if n.split('/')[1] in ('conv1', 'bn1', 'res2', 'res3', 'res4', 'res5') and
-                   n not in params]
+                   if ((n.startswith('extractor/') and
+                        n.split('/')[1] in ('conv1', 'bn1', 'res2', 'res3', 'res4')) or
+                       n.startswith('head/res5/')) and n not in params]
         if missing:
             raise KeyError('ResNet snapshot lacks: ' + ', '.join(sorted(missing)[:5]))
         self.load_state_dict(params, strict=False)

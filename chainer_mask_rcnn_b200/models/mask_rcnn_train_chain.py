@@ -8,11 +8,12 @@ flat gradient buffer.
 
 Targets.  By default anchors and proposals are labelled / sampled on the device
 (models/utils/device_targets.py, csrc/targets.cu).  Mask targets are rasterised on the
-device as well when ``masks`` is a torch tensor ((B,G,H,W) uint8 / int32, CUDA or
-pinned host) or a bit-packed ``models.utils.PackedMasks`` -- the step then has no host synchronisation at all and can be captured
-in a CUDA graph (optimizers.GraphedUpdater); with the reference's host NumPy masks they
-are rasterised on the host (cv2, as in the reference), overlapped with the head's
-forward pass.  Passing the host ``AnchorTargetCreator`` / ``ProposalTargetCreator``
+device as well when ``masks`` is one (B,G,H,W) array -- the reference's own batch format
+(a host NumPy int32 array from ``datasets.concat_examples``), a torch tensor (uint8 / int32,
+CUDA or pinned host) or a bit-packed ``models.utils.PackedMasks`` -- the step then has no
+host synchronisation at all and can be captured in a CUDA graph
+(optimizers.GraphedUpdater); a list of per-image mask arrays is rasterised on the host
+(cv2, as in the reference), overlapped with the head's forward pass.  Passing the host ``AnchorTargetCreator`` / ``ProposalTargetCreator``
 objects instead reproduces the reference's NumPy-seeded sampling exactly (:126-158).
 """
 import numpy as np
@@ -113,6 +114,13 @@ class MaskRCNNTrainChain(object):
                 gt = GroundTruth(bboxes, labels, dev)
                 self.h2d_bytes += gt.nbytes
             masks_dev = None
+            if isinstance(masks, np.ndarray) and masks.ndim == 4 and dev_prop and \
+                    masks.dtype in (np.int32, np.uint8, np.bool_):
+                # the reference's batch format (datasets.concat_examples: (B,G,H,W) int32 on
+                # the host, models/mask_rcnn_train_chain.py:76-111): uploaded as it is and
+                # rasterised on the device -- bit-identical to the host cv2 path
+                masks = torch.from_numpy(masks.view(np.uint8) if masks.dtype == np.bool_
+                                         else masks)
             if isinstance(masks, (torch.Tensor, PackedMasks)):
                 if not dev_prop:
                     raise TypeError('tensor masks need the device proposal target creator')

@@ -33,12 +33,25 @@ class MomentumSGD(object):
         self.comm = None
         self.target = None
         self.t = 0
+        self._needs_broadcast = False
 
     def setup(self, link):
         self.target = link
         self.ctx = link.ctx
         self.velocity = torch.zeros_like(self.ctx.train.data)
+        self.broadcast_params()
         return self
+
+    def broadcast_params(self):
+        """Rank 0's trainable and frozen parameters and momenta to every rank (once)."""
+        if not self._needs_broadcast or self.target is None:
+            return
+        import torch.distributed as dist
+        for buf in (self.ctx.train.data, self.ctx.frozen.data, self.velocity):
+            dist.broadcast(buf, src=dist.get_global_rank(self.comm.group, 0)
+                           if self.comm.group is not None else 0, group=self.comm.group)
+        self.ctx.mark_dirty()
+        self._needs_broadcast = False
 
     def add_hook(self, hook):
         if isinstance(hook, WeightDecay):
@@ -51,6 +64,7 @@ class MomentumSGD(object):
             torch.distributed.all_reduce(self.ctx.grads, group=self.comm.group)
 
     def update(self, lossfun=None, *args, **kwds):
+        self.broadcast_params()
         loss = None
         if lossfun is not None:
             self.ctx.grads.zero_()
@@ -90,7 +104,14 @@ def create_communicator(group=None):
 
 
 def create_multi_node_optimizer(optimizer, comm):
+    """chainermn.create_multi_node_optimizer: gradients are averaged over the ranks before
+    every update, and -- like chainermn's optimizer does on its first update -- rank 0's
+    parameters are broadcast once (``setup`` / first ``update``), so replicas that were
+    initialised with different seeds, or of which only rank 0 loaded a snapshot, agree."""
     optimizer.comm = comm
+    optimizer._needs_broadcast = comm is not None and comm.size > 1
+    if optimizer.target is not None:
+        optimizer.broadcast_params()
     return optimizer
 
 
@@ -121,23 +142,39 @@ class GraphedUpdater(object):
     pinned host memory for asynchronous copies);
     bboxes / labels: lists of per-image NumPy arrays.
 
+    NumPy arrays in the reference's own batch format are accepted as well
+    (``datasets.concat_examples``: imgs (B,3,H,W) float32, masks (B,G,H,W) int32 / uint8 /
+    bool): they are viewed, not copied, on the host; when their memory is page-locked
+    (``datasets.concat_examples(..., pinned=True)`` / ``datasets.pinned_empty``) the uploads are
+    asynchronous, otherwise the driver stages them.
+
     The first call for a key runs eagerly (it is also the warm-up that sizes every
-    workspace), the second captures and replays, later calls replay.
+    workspace), the second captures and replays, later calls replay.  A key is the batch
+    geometry (image and mask shapes / dtypes) and the hyper-parameters; the per-image
+    scales are part of it only when the proposal layer's ``min_size`` uses them.  At most
+    ``max_states`` keys are kept (least recently used first out; an evicted key's graph,
+    its private memory pool and its input buffers are freed), so a data set whose batches
+    come in many shapes cannot grow the device memory without bound -- pad batches to a few
+    canvas sizes (``datasets.concat_examples(..., canvas=(H, W))``) to stay on replays.
     """
 
-    def __init__(self, optimizer, lossfun, max_boxes=64, use_graph=True):
+    def __init__(self, optimizer, lossfun, max_boxes=64, use_graph=True, max_states=4):
+        import collections
         from .models.utils import GroundTruth
         self.use_graph = use_graph
         self._GroundTruth = GroundTruth
         self.optimizer = optimizer
         self.lossfun = lossfun
         self.max_boxes = max_boxes
-        self._states = {}
+        self.max_states = max(1, int(max_states))
+        self._states = collections.OrderedDict()
         self._copy_stream = None
         self._prefetched = None
+        self._seed_word = None          # ONE device word for all keys: draws never restart
         self.launches_per_replay = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.evictions = 0
 
     class _State(object):
         pass
@@ -146,13 +183,30 @@ class GraphedUpdater(object):
     def _mask_tensor(masks):
         return masks.data if hasattr(masks, 'width') else masks
 
+    @staticmethod
+    def _as_tensor(a):
+        """NumPy arrays (the reference's batch format) become zero-copy host tensors."""
+        import numpy as np
+        if isinstance(a, np.ndarray):
+            if a.dtype == np.bool_:
+                a = a.view(np.uint8)
+            return torch.from_numpy(a if a.flags.c_contiguous else np.ascontiguousarray(a))
+        return a
+
+    def _scales_matter(self):
+        rpn = getattr(getattr(self.lossfun, 'mask_rcnn', None), 'rpn', None)
+        layer = getattr(rpn, 'proposal_layer', None)
+        return layer is None or getattr(layer, 'min_size', 1) != 0
+
     def _key(self, imgs, masks, scales):
         o = self.optimizer
         packed = hasattr(masks, 'width')
         masks = self._mask_tensor(masks)
-        return (tuple(imgs.shape), tuple(masks.shape), str(masks.dtype), packed,
-                tuple(float(s) for s in scales), float(o.lr), float(o.momentum),
-                float(o.weight_decay), o.comm.size if o.comm is not None else 1)
+        # the scales only enter the step through ProposalCreator's min_size * scale
+        sc = tuple(float(s) for s in scales) if self._scales_matter() else ()
+        return (tuple(imgs.shape), tuple(masks.shape), str(masks.dtype), packed, sc,
+                float(o.lr), float(o.momentum), float(o.weight_decay),
+                o.comm.size if o.comm is not None else 1)
 
     def _new_state(self, imgs, bboxes, labels, masks):
         dev = self.optimizer.ctx.device
@@ -165,7 +219,9 @@ class GraphedUpdater(object):
         st.masks = torch.zeros(tuple(mt.shape), dtype=mt.dtype, device=dev)
         st.masks_arg = type(masks)(st.masks, masks.width) if hasattr(masks, 'width') else st.masks
         st.gt = self._GroundTruth(bboxes, labels, dev, capacity=G)
-        st.seed_word = torch.zeros((1,), dtype=torch.int64, device=dev)
+        if self._seed_word is None:
+            self._seed_word = torch.zeros((1,), dtype=torch.int64, device=dev)
+        st.seed_word = self._seed_word
         st.graph = None
         st.loss = None
         st.calls = 0
@@ -199,17 +255,39 @@ class GraphedUpdater(object):
         scales = [float(s) for s in (scales.tolist() if hasattr(scales, 'tolist') else scales)]
         if not (isinstance(imgs, torch.Tensor) and
                 isinstance(self._mask_tensor(masks), torch.Tensor)):
-            raise TypeError('GraphedUpdater needs torch tensors (or PackedMasks) for imgs and '
-                            'masks (CUDA or pinned host memory)')
+            raise TypeError('GraphedUpdater needs arrays for imgs and masks: torch tensors '
+                            '(CUDA or host), PackedMasks, or NumPy arrays')
         key = self._key(imgs, masks, scales)
         st = self._states.get(key)
         if st is None:
+            while len(self._states) >= self.max_states:
+                self._evict()
             st = self._states[key] = self._new_state(imgs, bboxes, labels, masks)
+        else:
+            self._states.move_to_end(key)
         return st, scales
+
+    def _evict(self):
+        """Drop the least recently used key: its CUDA graph (and the graph's private memory
+        pool holding every activation of the step), input and staging buffers."""
+        _, st = self._states.popitem(last=False)
+        if self._prefetched is not None and self._prefetched[0] is st:
+            self._prefetched = None
+        torch.cuda.current_stream().synchronize()     # nothing of it is still running
+        for name in list(vars(st)):
+            if name != 'seed_word':
+                setattr(st, name, None)
+        self.evictions += 1
 
     def _run(self, st, scales):
         o = self.optimizer
         lib = _lib.load()
+        o.broadcast_params()
+        if o.ctx._train_dirty or o.ctx._frozen_dirty:
+            # weights were loaded / edited since the last step (load_state_dict, load_npz):
+            # a captured graph holds no refresh of the tf32 forward copies (the update
+            # kernel maintains them from step to step), so refresh them here
+            o.ctx.prepare(backward=True)
         if st.calls == 0 or not self.use_graph:
             loss = self._step(st, scales)                       # eager: warm-up + real step
         else:
@@ -232,6 +310,7 @@ class GraphedUpdater(object):
         return _GraphedLoss(loss, self)
 
     def __call__(self, imgs, bboxes, labels, masks, scales):
+        imgs, masks = self._as_tensor(imgs), self._as_tensor(masks)
         st, scales = self._lookup(imgs, bboxes, labels, masks, scales)
         self._stage(st, imgs, bboxes, labels, masks)
         return self._run(st, scales)
@@ -242,6 +321,7 @@ class GraphedUpdater(object):
         (into staging buffers), so that they overlap the iteration that is running;
         ``step()`` then moves them into the graph's input buffers with device-to-device
         copies (tens of microseconds) and runs the iteration."""
+        imgs, masks = self._as_tensor(imgs), self._as_tensor(masks)
         st, scales = self._lookup(imgs, bboxes, labels, masks, scales)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()

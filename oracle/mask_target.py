@@ -86,3 +86,40 @@ def mask_targets(sample_roi, gt_assign, n_pos, masks, mask_size=14):
         for j in range(int(n_pos[b])):
             out[b, j] = roi_mask_target(sample_roi[b, j], masks[b][gt_assign[b, j]], mask_size)
     return out
+
+
+def proposal_targets(roi, bbox, label, mask, n_sample=512, pos_ratio=0.25, pos_iou_thresh=0.5,
+                     neg_iou_thresh_hi=0.5, neg_iou_thresh_lo=0.0, mask_size=14,
+                     loc_normalize_mean=(0., 0., 0., 0.), loc_normalize_std=(0.1, 0.1, 0.2, 0.2),
+                     rs=np.random):
+    """ProposalTargetCreator.__call__ (models/utils/proposal_target_creator.py:115-184):
+    concat proposals + ground truth, IoU, sample <= round(n_sample * pos_ratio) foreground
+    and the rest background RoIs with ``rs.choice`` (the reference uses the global NumPy
+    RNG), normalised bbox2loc, and the per-foreground-RoI mask rasterisation.  Used by the
+    CPU baseline (oracle/cpu_step.py); the product's host sampler is pinned separately against
+    the reference file run verbatim (tests/test_host_targets.py)."""
+    from . import bbox as ob
+    roi = np.concatenate((np.asarray(roi, f32), np.asarray(bbox, f32)), axis=0)
+    pos_per_image = np.round(n_sample * pos_ratio)
+    iou = ob.bbox_iou(roi, bbox)
+    assign = iou.argmax(axis=1)
+    max_iou = iou.max(axis=1)
+    gt_label = label[assign] + 1
+    pos = np.where(max_iou >= pos_iou_thresh)[0]
+    n_pos = int(min(pos_per_image, pos.size))
+    if pos.size > 0:
+        pos = rs.choice(pos, size=n_pos, replace=False)
+    neg = np.where((max_iou < neg_iou_thresh_hi) & (max_iou >= neg_iou_thresh_lo))[0]
+    n_neg = int(min(n_sample - n_pos, neg.size))
+    if neg.size > 0:
+        neg = rs.choice(neg, size=n_neg, replace=False)
+    keep = np.append(pos, neg)
+    gt_label = gt_label[keep]
+    gt_label[n_pos:] = 0
+    sample_roi = roi[keep]
+    loc = ob.bbox2loc(sample_roi, bbox[assign[keep]])
+    loc = (loc - np.array(loc_normalize_mean, f32)) / np.array(loc_normalize_std, f32)
+    gt_mask = -np.ones((len(sample_roi), mask_size, mask_size), np.int32)
+    for i, p in enumerate(pos):
+        gt_mask[i] = roi_mask_target(sample_roi[i], mask[assign[p]], mask_size)
+    return sample_roi, loc.astype(f32), gt_label.astype(np.int32), gt_mask

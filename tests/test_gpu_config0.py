@@ -43,6 +43,21 @@ def nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def tie_free(score):
+    """Real RPN logits collide (28 728 fp32 values within +-0.3: a few dozen exact ties) and
+    NumPy's argsort()[::-1] orders equal keys arbitrarily, so index lists can only be compared
+    on tie-free scores: equal neighbours are moved apart by one ulp each."""
+    s = score.astype(np.float32).copy()
+    order = np.argsort(s, kind='stable')
+    v = s[order]
+    for i in range(1, len(v)):
+        if v[i] <= v[i - 1]:
+            v[i] = np.nextafter(v[i - 1], np.float32(np.inf))
+    s[order] = v
+    assert len(np.unique(s)) == len(s)
+    return s
+
+
 @pytest.fixture(scope='module')
 def cfg0():
     rs = np.random.RandomState(0)
@@ -95,7 +110,7 @@ def test_extractor_every_layer_on_identical_inputs(cfg0):
             root = 'extractor/%s/%s' % (stage, nm)
             _check_block(blk, tape[root], errs, '%s/%s' % (stage, nm))
     assert tape['extractor/res4'].shape == (1, 1024, 38, 63)
-    assert len(errs) == 2 + 16 * 4 + 3                       # 43 convolutions + pool + 16 sums
+    assert len(errs) == 2 + 13 * 4 + 3       # conv1, pool1, 13 blocks x (3 convs + sum), 3 shortcuts
     bad = {k: v for k, v in errs.items() if not v <= TOL}
     assert not bad, bad
     # the whole extractor chained (40 TF32 layers deep) stays within 5e-3
@@ -119,12 +134,14 @@ def test_rpn_layers_and_bit_exact_proposals(cfg0):
     assert len(a_np) == 38 * 63 * 12
     # ProposalCreator on the ORACLE's RPN outputs: index lists equal, boxes to fp32 round-off
     pc_want = ob.ProposalCreator(**cfg.proposal_creator_params)
-    want_roi, want_idx = pc_want(cfg0['rpn_locs'][0], cfg0['rpn_scores'][0], cfg0['anchor'],
+    score = tie_free(cfg0['rpn_scores'][0])
+    n_ties = int((score != cfg0['rpn_scores'][0]).sum())
+    want_roi, want_idx = pc_want(cfg0['rpn_locs'][0], score, cfg0['anchor'],
                                  (H, W), 1.0, train=False, return_index=True)
     with utils.config.using_config('train', False):
         roi, idx = utils.ProposalCreator(**cfg.proposal_creator_params)(
-            cfg0['rpn_locs'][0], cfg0['rpn_scores'][0], cfg0['anchor'], (H, W), 1.0,
-            return_index=True)
+            cfg0['rpn_locs'][0], score, cfg0['anchor'], (H, W), 1.0, return_index=True)
+    print('config0 proposals: %d tied scores nudged, %d proposals' % (n_ties, len(want_idx)))
     assert len(want_idx) > 100
     np.testing.assert_array_equal(idx, want_idx)
     np.testing.assert_allclose(roi, want_roi, rtol=1e-6, atol=1e-4)
@@ -132,7 +149,7 @@ def test_rpn_layers_and_bit_exact_proposals(cfg0):
     cand = ob.loc2bbox(cfg0['anchor'], cfg0['rpn_locs'][0])
     cand[:, 0::2] = np.clip(cand[:, 0::2], 0, H)
     cand[:, 1::2] = np.clip(cand[:, 1::2], 0, W)
-    order = cfg0['rpn_scores'][0].argsort()[::-1][:6000]
+    order = score.argsort()[::-1][:6000]
     cand = np.ascontiguousarray(cand[order][:2000])
     keep, mask = utils.nms_suppression_bitmask(cand, 0.7)
     np.testing.assert_array_equal(keep, ob.non_maximum_suppression(cand, 0.7))

@@ -112,7 +112,7 @@ def _gemm_case(key, g):
 
 def test_every_forward_and_data_gradient_gemm_shape(shapes):
     gemms, _ = shapes
-    assert len(gemms) >= 40
+    assert len(gemms) >= 30
     g = torch.Generator(device='cuda').manual_seed(0)
     errs = {k: _gemm_case(k, g) for k in sorted(gemms, key=repr)}
     bad = {k: v for k, v in errs.items() if not v <= TOL}
@@ -160,7 +160,7 @@ def _wgrad_case(key, g):
 
 def test_every_weight_gradient_gemm_shape(shapes):
     _, wgrads = shapes
-    assert len(wgrads) >= 25
+    assert len(wgrads) >= 20
     g = torch.Generator(device='cuda').manual_seed(1)
     errs = {k: _wgrad_case(k, g) for k in sorted(wgrads, key=repr)}
     bad = {k: v for k, v in errs.items() if not v <= TOL}

@@ -460,3 +460,79 @@ def test_ragged_image_size_train_and_predict():
     for i, im in enumerate(raw):
         assert mm[i].shape == (len(bb[i]),) + im.shape[1:]
         assert np.isfinite(bb[i]).all() and np.isfinite(ss[i]).all()
+
+
+def test_reference_format_numpy_batch_replays_the_graph():
+    """The reference's own batch (datasets.concat_examples: imgs float32, masks (B,G,H,W)
+    int32 NumPy arrays on the host, page-locked or not) goes through GraphedUpdater's graph
+    replay and gives the losses of the same batch passed as device tensors / packed bits;
+    MaskRCNNTrainChain.__call__ takes the same arrays on the device-target fast path."""
+    from chainer_mask_rcnn_b200 import datasets, optimizers
+    rs = np.random.RandomState(31)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    examples = [(imgs[i], bboxes[i], labels[i], masks[i][:len(bboxes[i])], 1.0) for i in range(2)]
+    hists = {}
+    for form in ('tensor', 'numpy', 'pinned'):
+        model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                      base_channels=BASE, seed=3)
+        chain = models.MaskRCNNTrainChain(model, seed=8)
+        opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+        up = optimizers.GraphedUpdater(opt, chain, max_boxes=8)
+        if form == 'tensor':
+            a_i = torch.from_numpy(imgs).cuda()
+            a_m = torch.from_numpy(np.stack(masks).astype(np.uint8)[:, :3]).cuda()
+        else:
+            a_i, _, _, a_m, _ = datasets.concat_examples(
+                examples, padding=0, indices_concat=[0, 2, 3, 4], indices_to_device=[],
+                pinned=form == 'pinned')
+            assert isinstance(a_m, np.ndarray) and a_m.dtype == np.int32 and a_m.ndim == 4
+            assert torch.from_numpy(a_m).is_pinned() == (form == 'pinned')
+        hists[form] = [up(a_i, bboxes, labels, a_m, scales).item() for _ in range(4)]
+        assert up.launches_per_replay > 100
+        if form == 'numpy':         # the chain itself on the reference-format arrays
+            chain2 = models.MaskRCNNTrainChain(model, seed=8)
+            loss = chain2(a_i, bboxes, labels, a_m, scales)
+            assert np.isfinite(loss.item()) and chain2.d2h_bytes == 0
+    assert all(np.isfinite(sum(hists.values(), [])))
+    for form in ('numpy', 'pinned'):
+        np.testing.assert_allclose(hists[form][0], hists['tensor'][0], rtol=1e-5)
+        np.testing.assert_allclose(hists[form], hists['tensor'], rtol=5e-2)
+
+
+def test_graphed_updater_bounds_its_states_and_sees_reloaded_weights():
+    """ At most max_states (batch geometry) keys are kept -- least recently used
+    first out, its graph and buffers freed; the random draws continue through ONE seed word
+    across keys; weights loaded after a graph was captured reach the next replay."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(41)
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE, seed=5)
+    chain = models.MaskRCNNTrainChain(model, seed=2)
+    opt = optimizers.MomentumSGD(lr=0.0, momentum=0.0).setup(chain)     # parameters stay put
+    up = optimizers.GraphedUpdater(opt, chain, max_boxes=8, max_states=2)
+    batches = {}
+    for k, (H, W) in enumerate(((160, 192), (128, 160), (144, 176))):
+        imgs, bboxes, labels, masks, scales = _tiny_batch(np.random.RandomState(50 + k), H, W)
+        batches[k] = (torch.from_numpy(imgs).cuda(), bboxes, labels,
+                      torch.from_numpy(np.stack(masks).astype(np.uint8)).cuda(), scales)
+    for k in (0, 1, 0, 1):
+        up(*batches[k])
+    assert len(up._states) == 2 and up.evictions == 0
+    assert int(up._seed_word.item()) == 4                   # one word across both keys
+    torch.cuda.synchronize()
+    up(*batches[2])                                          # third geometry: evicts key 0's
+    assert len(up._states) == 2 and up.evictions == 1
+    assert [k[0][2:] for k in up._states] == [(128, 160), (144, 176)]
+    # scales are not part of the key when the proposal layer ignores them (min_size = 0)
+    n = len(up._states)
+    up(batches[2][0], batches[2][1], batches[2][2], batches[2][3], np.array([1.3, 0.7]))
+    assert len(up._states) == n
+    # reload: zero the RPN score layer -> the rpn_cls loss becomes log(2) on the next REPLAY
+    st = list(up._states.values())[-1]
+    assert st.graph is not None
+    sd = model.state_dict()
+    sd['rpn/score/W'][:] = 0
+    sd['rpn/score/b'][:] = 0
+    model.load_state_dict(sd)
+    up(*batches[2])
+    assert abs(float(chain.observation['rpn_cls_loss'].item()) - np.log(2.)) < 1e-4
