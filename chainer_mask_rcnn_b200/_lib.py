@@ -70,6 +70,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'cmr_split_tf32x3': (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
     'cmr_pack_image_nhwc4': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
     'cmr_max_pool_nhwc': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

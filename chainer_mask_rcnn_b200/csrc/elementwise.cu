@@ -22,10 +22,59 @@ round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, size_t 
     for (size_t k = i; k < n; k += stride) out[k] = tc::round_tf32(in[k]);
   }
 }
+
+// x = hi + lo + O(2^-22 |x|) with hi = tf32(x), lo = tf32(x - hi): the operand split of the
+// 3 x TF32 parity mode.  One thread per channel quad of a row.
+__global__ void __launch_bounds__(256)
+split_tf32x3_kernel(const float* __restrict__ x, float* __restrict__ out, size_t rows, int c_in,
+                    int c_pad, int order) {
+  const int qpr = c_pad >> 2;
+  const size_t total = rows * (size_t)qpr;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const bool vec = (c_in & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t row = i / qpr;
+    const int c = (int)(i - row * qpr) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = x + row * (size_t)c_in + c;
+    if (vec && c + 3 < c_in) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c + e < c_in) v[e] = __ldg(src + e);
+    }
+    float hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = tc::round_tf32(v[e]);
+      lo[e] = tc::round_tf32(__fsub_rn(v[e], hi[e]));
+    }
+    const float4 h4 = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    const float4 l4 = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    float4* dst = reinterpret_cast<float4*>(out + row * (size_t)(3 * c_pad) + c);
+    dst[0] = h4;
+    dst[qpr] = order == 0 ? l4 : h4;
+    dst[2 * qpr] = order == 0 ? h4 : l4;
+  }
+}
 }  // namespace
 }  // namespace cmr
 
 using namespace cmr;
+
+extern "C" int cmr_split_tf32x3(const float* x, size_t rows, int c_in, int c_pad, int order,
+                                float* out, void* stream) {
+  if (rows == 0) return CMR_OK;
+  CMR_REQUIRE(x && out && c_in > 0 && c_pad >= c_in && (c_pad & 3) == 0 && (order == 0 || order == 1));
+  CMR_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const size_t quads = rows * (size_t)(c_pad >> 2);
+  const int blocks = (int)min((size_t)sm_count() * 8, (quads + 255) / 256);
+  split_tf32x3_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, out, rows, c_in, c_pad, order);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
 
 extern "C" int cmr_round_tf32(const float* in, float* out, size_t n, void* stream) {
   if (n == 0) return CMR_OK;

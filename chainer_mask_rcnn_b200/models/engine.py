@@ -118,6 +118,17 @@ def round_tf32(src, dst=None):
     return dst
 
 
+def split3(x, order=0, c_pad=None):
+    """(..., C) fp32 -> (..., 3 * c_pad): [hi | lo | hi] (order 0, activations) or
+    [hi | hi | lo] (order 1, filters) of the 3 x TF32 parity mode (cmr_split_tf32x3)."""
+    C = x.shape[-1]
+    c_pad = C if c_pad is None else c_pad
+    x = x.contiguous()
+    out = torch.empty(tuple(x.shape[:-1]) + (3 * c_pad,), dtype=f32, device=x.device)
+    _lib.call('cmr_split_tf32x3', _p(x), x.numel() // C, C, c_pad, order, _p(out), stream())
+    return out
+
+
 def column_sums(g, c0, n, out):
     """out[:n] = sum over all leading axes of g[..., c0:c0+n] (g contiguous)."""
     ld = g.shape[-1]

@@ -32,6 +32,11 @@ class Context(object):
         self.frozen_rounded = None
         self.device = None
         self.recording = False          # save activations for the backward pass
+        # 'tf32': operands rounded to TF32 by the producing epilogue (the speed path).
+        # 'tf32x3': forward GEMMs on hi/lo-split operands (3 x the work, fp32-level results;
+        # the parity mode of SURVEY.md 7.3); forward only.
+        self.precision = 'tf32'
+        self.version = 0                # bumped whenever parameters change
         self._train_dirty = True
         self._frozen_dirty = True
         self._dgrad_dirty = True
@@ -67,6 +72,7 @@ class Context(object):
         return self.frozen.view(name, self.frozen_rounded)
 
     def mark_dirty(self, frozen=True):
+        self.version += 1
         self._train_dirty = True
         self._dgrad_dirty = True
         if frozen:
@@ -75,6 +81,9 @@ class Context(object):
     def prepare(self, backward):
         """Refresh the derived weight copies the kernels read (tf32-rounded forward
         banks; transposed, affine-scaled banks of the data-gradient GEMMs)."""
+        if backward and self.precision != 'tf32':
+            raise RuntimeError("precision '%s' is a forward-only parity mode; train in 'tf32'"
+                               % self.precision)
         if self._frozen_dirty:
             E.round_tf32(self.frozen.data, self.frozen_rounded)
             for l in self.layers:
@@ -175,8 +184,19 @@ class Conv(object):
         return scale, bias
 
     # ---- passes
+    def _w3(self):
+        """[hi | hi | lo] split of the master fp32 filter bank (3 x TF32 parity mode)."""
+        c = self.ctx
+        if getattr(self, '_w3_cache', (None, None))[0] != c.version:
+            self._w3_cache = (c.version, E.split3(c.param(self.W), order=1))
+        return self._w3_cache[1]
+
     def forward(self, x, relu=False, addend=None, round_out=True, out=None):
         scale, bias = self._epilogue()
+        if self.ctx.precision == 'tf32x3':
+            return E.conv_gemm(E.split3(x), self._w3(), self.cout, self.k, self.k, self.stride,
+                               self.pad, out=out, scale=scale, bias=bias, addend=addend,
+                               relu=relu, round_out=False)
         return E.conv_gemm(x, self.ctx.fwd(self.W), self.cout, self.k, self.k, self.stride,
                            self.pad, out=out, scale=scale, bias=bias, addend=addend, relu=relu,
                            round_out=round_out)

@@ -44,6 +44,14 @@ class _Deconv2x2(object):
     def forward(self, x):
         R, h, w, _ = x.shape
         out = torch.empty((R, 2 * h, 2 * w, self.cout), dtype=torch.float32, device=x.device)
+        if self.ctx.precision == 'tf32x3':
+            c = self.ctx
+            if getattr(self, '_w3_cache', (None, None))[0] != c.version:
+                self._w3_cache = (c.version, E.split3(c.param(self.W), order=1))
+            E.conv_gemm(E.split3(x), self._w3_cache[1], 4 * self.cout, out=out,
+                        bias=c.param(self.b), relu=True, round_out=False, d_stride=2,
+                        tap_cols=self.cout)
+            return out
         wt = self.ctx.fwd(self.W)                       # (4, cout, cin): tap-major rows
         E.conv_gemm(x, wt, 4 * self.cout, out=out, bias=self.ctx.param(self.b), relu=True,
                     d_stride=2, tap_cols=self.cout)
@@ -133,20 +141,23 @@ class ResNetRoIHead(object):
         """feat (N,H,W,C) NHWC; rois (R,4) yx; -> (R,4*n_class), (R,n_class),
         (R,14,14,n_fg) [a view of a mask_ld-wide buffer]."""
         rois_xy = self._rois_xy(rois, roi_indices)
+        rnd = self.ctx.precision == 'tf32'      # operands are TF32-rounded by their producer
         if self.pooling_func is functions.roi_align_2d:
             pool = E.roi_align_nhwc(feat, rois_xy, self.roi_size, self.roi_size, self.bin_stride,
-                                    self.spatial_scale)
+                                    self.spatial_scale, round_out=rnd)
         else:   # a user-supplied pooler works on the reference's NCHW arrays
             p = self.pooling_func(E.as_nchw_view(feat),
                                   torch.cat((roi_indices.to(torch.float32)[:, None], rois), 1),
                                   outh=self.roi_size, outw=self.roi_size,
                                   spatial_scale=self.spatial_scale, axes='yx')
             p = p[:, :, ::self.bin_stride, ::self.bin_stride]
-            pool = E.round_tf32(p.permute(0, 2, 3, 1).contiguous())
+            pool = p.permute(0, 2, 3, 1).contiguous()
+            if rnd:
+                pool = E.round_tf32(pool)
         res5 = self.res5.forward(pool)
         cls_locs = scores = masks = pool5 = d6 = None
         if pred_bbox:
-            pool5 = E.avg_pool(res5)
+            pool5 = E.avg_pool(res5, round_out=rnd)
             p4 = pool5.view(-1, 1, 1, self.feat)
             cls_locs = self.cls_loc.forward(p4, round_out=False).view(-1, 4 * self.n_class)
             scores = self.score.forward(p4, round_out=False).view(-1, self.n_class)
@@ -215,7 +226,7 @@ class MaskRCNNResNet(MaskRCNN):
                  proposal_creator_params=dict(min_size=0, n_test_pre_nms=6000,
                                               n_test_post_nms=1000),
                  pooling_func=functions.roi_align_2d, rpn_hidden=1024, roi_size=7,
-                 base_channels=64, device=None, seed=0):
+                 base_channels=64, device=None, seed=0, precision='tf32'):
         if n_layers not in (50, 101):
             raise ValueError('n_layers must be 50 or 101')
         if len(mean) != 3:
@@ -233,6 +244,7 @@ class MaskRCNNResNet(MaskRCNN):
         head = ResNetRoIHead(ctx, n_layers, n_fg_class + 1, roi_size, 1. / self.feat_stride,
                              pooling_func=pooling_func, base=b)
         ctx.finalize(device)
+        self.precision = precision
         super(MaskRCNNResNet, self).__init__(
             extractor, rpn, head, mean=np.asarray(mean, dtype=np.float32)[:, None, None],
             min_size=min_size, max_size=max_size)
@@ -240,6 +252,20 @@ class MaskRCNNResNet(MaskRCNN):
                           mask_initialW)
         if pretrained_model:
             self.load_npz(pretrained_model)
+
+    @property
+    def precision(self):
+        """'tf32' (default: TF32 tensor-core products of operands rounded by their producer --
+        the speed path, <= 1e-3 per operator) or 'tf32x3' (forward only: every GEMM on
+        hi/lo-split operands, three times the work, fp32-level results through the whole
+        chained model -- the parity mode)."""
+        return self.ctx.precision
+
+    @precision.setter
+    def precision(self, value):
+        if value not in ('tf32', 'tf32x3'):
+            raise ValueError("precision must be 'tf32' or 'tf32x3'")
+        self.ctx.precision = value
 
     def load_imagenet_resnet(self, src, bgr_to_rgb=True):
         """What the reference does when no ``pretrained_model`` is given

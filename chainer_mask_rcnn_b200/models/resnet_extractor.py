@@ -85,6 +85,19 @@ class _Stem(Conv):
 
     def forward(self, x_nchw):
         B, _, H, W = x_nchw.shape
+        if self.ctx.precision == 'tf32x3':
+            # parity mode: a plain 7x7 convolution over [hi | lo | hi] pixels of 3 -> 32
+            # zero-padded channels each (K = 49 x 96)
+            c = self.ctx
+            px = torch.empty((B, H * W, 3), dtype=torch.float32, device=x_nchw.device)
+            E._lib.call('cmr_transpose_batched', E._p(x_nchw.contiguous()), B, 3, H * W, E._p(px),
+                        E.stream())
+            x96 = E.split3(px.view(B, H, W, 3), order=0, c_pad=32)
+            if getattr(self, '_w96', (None, None))[0] != c.version:
+                self._w96 = (c.version, E.split3(c.param(self.W), order=1, c_pad=32))
+            scale, bias = self._epilogue()
+            return E.conv_gemm(x96, self._w96[1], self.cout, 7, 7, 2, 3, scale=scale, bias=bias,
+                               relu=True, round_out=False)
         oh, ow = E.conv_out(H, 7, 2, 3), E.conv_out(W, 7, 2, 3)
         hp = H + 6
         wp = max(W + 6, 2 * (ow - 1) + 8)

@@ -268,6 +268,17 @@ int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* 
 /* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
 int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
 
+/* Operand split of the 3 x TF32 parity mode: every fp32 value is written as
+ * hi = tf32(x) and lo = tf32(x - hi), x = hi + lo up to 2^-22 |x|.  x (rows, c_in) ->
+ * out (rows, 3 * c_pad): three column blocks of c_pad >= c_in channels (zero padded),
+ * order 0 = [hi | lo | hi] (activations), order 1 = [hi | hi | lo] (filters).  A GEMM over
+ * the concatenated K axis, sum_k a3[k] * w3[k] = sum_c hi_a*hi_w + lo_a*hi_w + hi_a*lo_w,
+ * is the fp32 product up to the dropped lo*lo term: the tensor-core convolution kernel run
+ * on split operands reproduces an fp32 sgemm to ~1e-6 (three times the work; used to verify
+ * the chained model against the fp32 reference, not for speed). */
+int cmr_split_tf32x3(const float* x, size_t rows, int c_in, int c_pad, int order,
+                     float* out, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * HBM-bound pieces of the graph around the convolutions (csrc/misc.cu).
  * ------------------------------------------------------------------------ */

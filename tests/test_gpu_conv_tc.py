@@ -211,3 +211,28 @@ def test_fused_deconvolution_tap_columns():
     _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w_taps), _lib.ptr(out),
               None, _lib.ptr(bias), None, None, _lib.stream_ptr())
     assert rel(out, want) <= 1e-4
+
+
+def test_split_tf32x3_and_fp32_level_convolution():
+    """cmr_split_tf32x3: hi + lo reproduces x to 2^-21 |x|, both parts are TF32 values; a
+    convolution on [hi|lo|hi] x [hi|hi|lo] operands matches the fp64 reference of the RAW fp32
+    operands to 2e-6 (the plain TF32 path: ~4e-4)."""
+    from chainer_mask_rcnn_b200.models import engine as E
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn((2, 25, 42, 256), device='cuda', generator=g)
+    w = torch.randn((256, 3, 3, 256), device='cuda', generator=g) / 48
+    x3 = E.split3(x)
+    hi, lo, hi2 = x3[..., :256], x3[..., 256:512], x3[..., 512:]
+    assert torch.equal(hi, hi2) and torch.equal(hi, round_tf32(x.clone()))
+    assert torch.equal(lo.contiguous(), round_tf32(lo.contiguous().clone()))
+    assert float(((hi + lo) - x).abs().max() / x.abs().max()) <= 2 ** -21
+    w3 = E.split3(w, order=1)
+    assert torch.equal(w3[..., 256:512], w3[..., :256])
+    want = ref_conv(x, w, 1, 1)
+    got = E.conv_gemm(x3, w3, 256, 3, 3, 1, 1, round_out=False)
+    assert rel(got, want) <= 2e-6
+    # zero-padded narrow rows (the stem: 3 -> 32 channels per part)
+    px = torch.randn((5, 7, 3), device='cuda', generator=g)
+    p3 = E.split3(px, c_pad=32)
+    assert p3.shape == (5, 7, 96) and float(p3[..., 3:32].abs().max()) == 0.
+    assert torch.equal(p3[..., :3], round_tf32(px.clone()))
