@@ -35,6 +35,9 @@ _SIGNATURES = {
     'cmr_roi_align_nhwc_bwd': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                        c_int, c_int, c_int, c_int, c_float, c_int,
                                        c_void_p, c_void_p]),
+    'cmr_roi_align_nhwc_bwd_accum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, c_int, c_int, c_float, c_int,
+                                             c_void_p, c_void_p]),
     'cmr_roi_align_cl_supported': (c_int, [c_int] * 7),
     'cmr_roi_align_fwd_cl': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                      c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
@@ -70,6 +73,7 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'cmr_relu_mask': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'cmr_split_tf32x3': (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
     'cmr_pack_image_nhwc4': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),

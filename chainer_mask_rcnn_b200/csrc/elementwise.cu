@@ -59,10 +59,42 @@ split_tf32x3_kernel(const float* __restrict__ x, float* __restrict__ out, size_t
     dst[2 * qpr] = order == 0 ? h4 : l4;
   }
 }
+
+// out = mask > 0 ? g : 0, optionally rounded to tf32 (ReLU backward as its own pass).
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(const float4* __restrict__ g, const float4* __restrict__ mask,
+                 float4* __restrict__ out, size_t n4, int round_out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = g[i];
+    const float4 m = __ldg(mask + i);
+    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+    v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+    if (round_out) {
+      v.x = tc::round_tf32(v.x); v.y = tc::round_tf32(v.y);
+      v.z = tc::round_tf32(v.z); v.w = tc::round_tf32(v.w);
+    }
+    out[i] = v;
+  }
+}
 }  // namespace
 }  // namespace cmr
 
 using namespace cmr;
+
+extern "C" int cmr_relu_mask(const float* g, const float* mask, float* out, size_t n,
+                             int round_tf32, void* stream) {
+  if (n == 0) return CMR_OK;
+  CMR_REQUIRE(g && mask && out && n % 4 == 0);
+  CMR_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(mask) |
+                reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  const int blocks = (int)min((size_t)sm_count() * 8, (n / 4 + 255) / 256);
+  relu_mask_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(mask),
+      reinterpret_cast<float4*>(out), n / 4, round_tf32);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
 
 extern "C" int cmr_split_tf32x3(const float* x, size_t rows, int c_in, int c_pad, int order,
                                 float* out, void* stream) {

@@ -953,10 +953,10 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
   return CMR_OK;
 }
 
-extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N, int H,
-                                      int W, int C, int outh, int outw, int bin_stride,
-                                      float spatial_scale, int sampling_ratio, float* gx,
-                                      void* stream) {
+namespace {
+int roi_align_nhwc_bwd_impl(const float* gy, const float* rois, int R, int N, int H, int W, int C,
+                            int outh, int outw, int bin_stride, float spatial_scale,
+                            int sampling_ratio, float* gx, bool zero_fill, void* stream) {
   CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
   CMR_REQUIRE(sampling_ratio >= 0 && bin_stride >= 1 && C % 4 == 0 && gx);
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
@@ -966,7 +966,9 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   CMR_REQUIRE(R == 0 || (gy && rois));
   // the zero fill of gx is part of the operator: it is inside the timed bracket
   prof_begin(kProfRoiAlignBwd, roi_align_bytes(R, C, oh_s, ow_s, N, H, W), as_stream(stream));
-  cudaError_t me = cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)N * C * H * W, as_stream(stream));
+  cudaError_t me = zero_fill ? cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)N * C * H * W,
+                                               as_stream(stream))
+                             : cudaSuccess;
   if (me != cudaSuccess || R == 0) {
     prof_end(as_stream(stream));
     CMR_CUDA_TRY(me);
@@ -978,6 +980,23 @@ extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R,
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
+}
+}  // namespace
+
+extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N, int H,
+                                      int W, int C, int outh, int outw, int bin_stride,
+                                      float spatial_scale, int sampling_ratio, float* gx,
+                                      void* stream) {
+  return roi_align_nhwc_bwd_impl(gy, rois, R, N, H, W, C, outh, outw, bin_stride, spatial_scale,
+                                 sampling_ratio, gx, true, stream);
+}
+
+extern "C" int cmr_roi_align_nhwc_bwd_accum(const float* gy, const float* rois, int R, int N,
+                                            int H, int W, int C, int outh, int outw,
+                                            int bin_stride, float spatial_scale,
+                                            int sampling_ratio, float* gx, void* stream) {
+  return roi_align_nhwc_bwd_impl(gy, rois, R, N, H, W, C, outh, outw, bin_stride, spatial_scale,
+                                 sampling_ratio, gx, false, stream);
 }
 
 // ---- reference-layout operator through the channels-last kernels -----------------------

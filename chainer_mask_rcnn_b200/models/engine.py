@@ -219,12 +219,25 @@ def roi_align_nhwc(x, rois_xy, outh, outw, bin_stride, spatial_scale, sampling_r
 
 
 def roi_align_nhwc_bwd(gy, rois_xy, x_shape, outh, outw, bin_stride, spatial_scale,
-                       sampling_ratio=0):
+                       sampling_ratio=0, accum=None):
+    """-> gx (N,H,W,C); with ``accum`` (N,H,W,C) the RoI gradients are added to it in place
+    (no zero fill)."""
     N, H, W, C = x_shape
+    if accum is not None:
+        _lib.call('cmr_roi_align_nhwc_bwd_accum', _p(gy), _p(rois_xy), rois_xy.shape[0], N, H,
+                  W, C, outh, outw, bin_stride, float(spatial_scale), sampling_ratio, _p(accum),
+                  stream())
+        return accum
     gx = torch.empty((N, H, W, C), dtype=f32, device=gy.device)
     _lib.call('cmr_roi_align_nhwc_bwd', _p(gy), _p(rois_xy), rois_xy.shape[0], N, H, W, C, outh,
               outw, bin_stride, float(spatial_scale), sampling_ratio, _p(gx), stream())
     return gx
+
+
+def relu_mask(g, mask, round_out=True):
+    """g * [mask > 0] in place (rounded to tf32)."""
+    _lib.call('cmr_relu_mask', _p(g), _p(mask), _p(g), g.numel(), int(round_out), stream())
+    return g
 
 
 def as_nchw_view(x_nhwc):

@@ -186,9 +186,11 @@ class ResNetRoIHead(object):
             masks = E.as_nchw_view(masks)
         return cls_locs, scores, masks
 
-    def backward(self, g_lin, g_mask):
+    def backward(self, g_lin, g_mask, accum=None):
         """g_lin (R, lin_ld): [d cls_loc | d score | 0]; g_mask (R,14,14,mask_ld).
-        Returns dL/dfeat (N,H,W,C), not masked."""
+        Returns dL/dfeat (N,H,W,C), not masked; ``accum``: a zero-argument callable returning
+        the (N,H,W,C) tensor the gradient is added to instead (called right before the
+        ROIAlign backward, so that whatever produces it may still be running until then)."""
         s, c, nc = self.saved, self.ctx, self.n_class
         self.saved = None
         res5, d6, pool5 = s['res5'], s['d6'], s['pool5']
@@ -212,7 +214,8 @@ class ResNetRoIHead(object):
         g_res5 = self.deconv6.backward(gd6, res5, bcast=g_pool5, mask=res5)
         g_pool = self.res5.backward(g_res5, input_is_relu=False)
         return E.roi_align_nhwc_bwd(g_pool, s['rois_xy'], s['feat_shape'], self.roi_size,
-                                    self.roi_size, self.bin_stride, self.spatial_scale)
+                                    self.roi_size, self.bin_stride, self.spatial_scale,
+                                    accum=accum() if accum is not None else None)
 
 
 class MaskRCNNResNet(MaskRCNN):

@@ -79,6 +79,16 @@ class MaskRCNNTrainChain(object):
         self._calls = 0
         self._pinned = {}
         self._roi_index = {}
+        # The RPN branch (anchor targets -> RPN losses [-> RPN backward]) depends on the RPN
+        # convolutions only; the proposal chain that follows them on the main stream (decode,
+        # sort, NMS sweep: ~0.5 ms of one-CTA-per-image, latency-bound kernels) leaves the
+        # SMs idle.  The branch is forked onto a side stream there.  Its backward half
+        # (loc / score / conv1 weight gradients and conv1's data gradient, ~0.5 ms of
+        # tensor-core work) runs ahead too when `eager_rpn_backward` is set -- the optimizer
+        # entry points set it, because they always call loss.backward() on zeroed gradients.
+        self.overlap_rpn_branch = True
+        self.eager_rpn_backward = False
+        self._rpn_stream = None
 
     def cleargrads(self):
         self.ctx.grads.zero_()
@@ -100,19 +110,27 @@ class MaskRCNNTrainChain(object):
             bboxes = [_host(b).astype(np.float32) for b in bboxes]
             labels = [_host(l) for l in labels]
         self._calls += 1
+        dev_anchor = isinstance(self.anchor_target_creator, DeviceAnchorTargetCreator)
+        dev_prop = isinstance(self.proposal_target_creator, DeviceProposalTargetCreator)
+        if gt is not None and not (dev_anchor and dev_prop):
+            raise TypeError('a packed GroundTruth needs the device target creators')
+        if gt is None and (dev_anchor or dev_prop):
+            gt = GroundTruth(bboxes, labels, dev)
+            self.h2d_bytes += gt.nbytes
+        seed = (self._seed << 20) + 2 * self._calls
         ctx.recording = True
         try:
+            branch = [None]
+
+            def fork_rpn_branch(rpn_locs, rpn_scores, anchor):
+                branch[0] = self._start_rpn_branch(feat, rpn_locs, rpn_scores, anchor, gt,
+                                                   img_size, seed)
+
             with config.using_config('train', True):
                 feat = m.extractor.forward_nhwc(x)
                 rpn_locs, rpn_scores, rois, _, cnt, (anchor_np, anchor) = m.rpn.forward_nhwc(
-                    feat, img_size, scales)
-            dev_anchor = isinstance(self.anchor_target_creator, DeviceAnchorTargetCreator)
-            dev_prop = isinstance(self.proposal_target_creator, DeviceProposalTargetCreator)
-            if gt is not None and not (dev_anchor and dev_prop):
-                raise TypeError('a packed GroundTruth needs the device target creators')
-            if gt is None and (dev_anchor or dev_prop):
-                gt = GroundTruth(bboxes, labels, dev)
-                self.h2d_bytes += gt.nbytes
+                    feat, img_size, scales,
+                    between=fork_rpn_branch if dev_anchor and self.overlap_rpn_branch else None)
             masks_dev = None
             if isinstance(masks, np.ndarray) and masks.ndim == 4 and dev_prop and \
                     masks.dtype in (np.int32, np.uint8, np.bool_):
@@ -128,9 +146,10 @@ class MaskRCNNTrainChain(object):
                     self.h2d_bytes += masks.numel() * masks.element_size() \
                         if isinstance(masks, torch.Tensor) else masks.nbytes
                 masks_dev = masks.to(dev, non_blocking=True)
-            seed = (self._seed << 20) + 2 * self._calls
             # ---- RPN targets
-            if dev_anchor:
+            if branch[0] is not None:
+                gt_rpn_locs, gt_rpn_labels = branch[0]['gt_rpn_locs'], branch[0]['gt_rpn_labels']
+            elif dev_anchor:
                 gt_rpn_locs, gt_rpn_labels = self.anchor_target_creator(
                     gt, anchor, img_size, seed, seed_dev=self.seed_dev)
                 gt_rpn_locs = gt_rpn_locs.view(-1, 4)
@@ -194,9 +213,47 @@ class MaskRCNNTrainChain(object):
                                 gt_roi_locs=gt_roi_locs, gt_roi_labels=gt_roi_labels,
                                 gt_roi_masks=gt_roi_masks, gt_rpn_locs=gt_rpn_locs,
                                 gt_rpn_labels=gt_rpn_labels)
-            return self.forward_with_targets(feat, rpn_locs, rpn_scores, **self.targets)
+            return self.forward_with_targets(feat, rpn_locs, rpn_scores, rpn_branch=branch[0],
+                                             **self.targets)
         finally:
             ctx.recording = False
+
+    def _start_rpn_branch(self, feat, rpn_locs, rpn_scores, anchor, gt, img_size, seed):
+        """Anchor targets, the two RPN losses and (eager_rpn_backward) the RPN's backward pass
+        on a side stream, forked after the RPN convolutions.  Buffers that the main stream
+        reads later are allocated here, on the main stream, before the fork."""
+        rpn = self.mask_rcnn.rpn
+        dev = feat.device
+        n, hh, ww, _ = feat.shape
+        A = rpn.n_anchor
+        eager = bool(self.eager_rpn_backward)
+        b = dict(eager=eager,
+                 losses=torch.zeros((8,), dtype=torch.float32, device=dev),
+                 g_rpn=torch.empty((n, hh, ww, rpn.g_ld), dtype=torch.float32, device=dev),
+                 g_feat=torch.empty(tuple(feat.shape), dtype=torch.float32, device=dev)
+                 if eager else None)
+        if self._rpn_stream is None:
+            self._rpn_stream = torch.cuda.Stream()
+        side = self._rpn_stream
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            gl, glab = self.anchor_target_creator(gt, anchor, img_size, seed,
+                                                  seed_dev=self.seed_dev)
+            b['gt_rpn_locs'], b['gt_rpn_labels'] = gl.view(-1, 4), glab.view(-1)
+            _lib.call('cmr_rpn_loss', E._p(rpn_locs), 4 * A, E._p(rpn_scores), A,
+                      E._p(b['gt_rpn_locs']), E._p(b['gt_rpn_labels']), n * hh * ww, A,
+                      float(self.rpn_sigma), E._p(b['g_rpn']), rpn.g_ld, E._p(b['losses']),
+                      E.stream())
+            b['loss_done'] = torch.cuda.Event()
+            b['loss_done'].record(side)
+            if eager:
+                rpn.backward(b['g_rpn'], out=b['g_feat'], masked=False)
+            b['done'] = torch.cuda.Event()
+            b['done'].record(side)
+        b['keep'] = (feat, rpn_locs, rpn_scores)      # alive until the branch has been joined
+        return b
 
     def _upload(self, a, dtype, dev):
         a = np.ascontiguousarray(a, dtype=dtype)
@@ -212,7 +269,7 @@ class MaskRCNNTrainChain(object):
 
     def forward_with_targets(self, feat, rpn_locs, rpn_scores, sample_rois, sample_roi_indices,
                              gt_roi_locs, gt_roi_labels, gt_roi_masks, gt_rpn_locs,
-                             gt_rpn_labels):
+                             gt_rpn_labels, rpn_branch=None):
         """Head forward + losses for given samples/targets (everything on the device).
         ``gt_roi_masks`` may be a callable producing the tensor; it is called after the
         head's forward pass has been enqueued, so host work inside it overlaps."""
@@ -227,20 +284,25 @@ class MaskRCNNTrainChain(object):
         R = cls_locs.shape[0]
         n, hh, ww, _ = feat.shape
         A = rpn.n_anchor
-        losses = torch.zeros((8,), dtype=torch.float32, device=dev)
-        g_rpn = torch.empty((n, hh, ww, rpn.g_ld), dtype=torch.float32, device=dev)
         g_lin = torch.empty((R, head.lin_ld), dtype=torch.float32, device=dev)
         g_mask = torch.empty((R, 14, 14, head.mask_ld), dtype=torch.float32, device=dev)
         st = E.stream()
-        _lib.call('cmr_rpn_loss', E._p(rpn_locs), 4 * A, E._p(rpn_scores), A, E._p(gt_rpn_locs),
-                  E._p(gt_rpn_labels), n * hh * ww, A, float(self.rpn_sigma), E._p(g_rpn),
-                  rpn.g_ld, E._p(losses), st)
+        if rpn_branch is not None:       # RPN losses were enqueued on the side stream
+            losses, g_rpn = rpn_branch['losses'], rpn_branch['g_rpn']
+        else:
+            losses = torch.zeros((8,), dtype=torch.float32, device=dev)
+            g_rpn = torch.empty((n, hh, ww, rpn.g_ld), dtype=torch.float32, device=dev)
+            _lib.call('cmr_rpn_loss', E._p(rpn_locs), 4 * A, E._p(rpn_scores), A,
+                      E._p(gt_rpn_locs), E._p(gt_rpn_labels), n * hh * ww, A,
+                      float(self.rpn_sigma), E._p(g_rpn), rpn.g_ld, E._p(losses), st)
         _lib.call('cmr_roi_loss', E._p(cls_locs), 4 * head.n_class, E._p(scores), head.n_class,
                   E._p(gt_roi_locs), E._p(gt_roi_labels), R, head.n_class, float(self.roi_sigma),
                   E._p(g_lin), head.lin_ld, E._p(losses), st)
         _lib.call('cmr_mask_loss', E._p(masks), head.mask_ld, E._p(gt_roi_labels),
                   E._p(gt_roi_masks), R, 14 * 14, head.n_fg, E._p(g_mask), head.mask_ld,
                   E._p(losses), st)
+        if rpn_branch is not None:
+            torch.cuda.current_stream().wait_event(rpn_branch['loss_done'])
         loss = losses[:5].sum()
         self.observation = {k: losses[i] for i, k in enumerate(LOSS_NAMES)}
         self.observation['loss'] = loss
@@ -251,8 +313,18 @@ class MaskRCNNTrainChain(object):
             # weight / bias gradients run on a side stream next to the data-gradient chain
             E.grad_side.begin()
             try:
-                g_feat = head.backward(g_lin, g_mask)
-                g_feat = rpn.backward(g_rpn, g_feat)
+                if rpn_branch is not None and rpn_branch['eager']:
+                    # the RPN branch's gradient of the feature map is already there (or
+                    # still being produced on the side stream): the head adds to it
+                    def rpn_grad():
+                        torch.cuda.current_stream().wait_event(rpn_branch['done'])
+                        return rpn_branch['g_feat']
+                    g_feat = E.relu_mask(head.backward(g_lin, g_mask, accum=rpn_grad), feat)
+                else:
+                    if rpn_branch is not None:
+                        torch.cuda.current_stream().wait_event(rpn_branch['done'])
+                    g_feat = head.backward(g_lin, g_mask)
+                    g_feat = rpn.backward(g_rpn, g_feat)
                 m.extractor.backward(g_feat)
             finally:
                 E.grad_side.join()

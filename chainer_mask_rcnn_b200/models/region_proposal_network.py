@@ -67,9 +67,12 @@ class RegionProposalNetwork(object):
             self._anchor_cache[key] = (a, torch.from_numpy(a).to(device))
         return self._anchor_cache[key]
 
-    def forward_nhwc(self, feat, img_size, scales):
+    def forward_nhwc(self, feat, img_size, scales, between=None):
         """feat (N,H,W,C) -> rpn_locs (N,HWA,4), rpn_scores (N,HWA), rois (N,n_post,4),
-        anchor index (N,n_post), counts (N,), anchor (host, device)."""
+        anchor index (N,n_post), counts (N,), anchor (host, device).
+        ``between(rpn_locs, rpn_scores, anchor)``, when given, is called after the three
+        convolutions and before the proposal layer is enqueued (the train chain forks the
+        RPN loss / backward branch there, next to the latency-bound proposal chain)."""
         n, hh, ww, _ = feat.shape
         anchor_np, anchor = self.anchors(hh, ww, feat.device)
         h = self.conv1.forward(feat, relu=True)
@@ -79,6 +82,8 @@ class RegionProposalNetwork(object):
             self.saved = (feat, h)
         rpn_locs = locs.view(n, -1, 4)
         rpn_scores = scores.view(n, -1)
+        if between is not None:
+            between(rpn_locs, rpn_scores, anchor)
         scale = float(np.asarray(scales).ravel()[0]) if np.size(scales) else 1.
         if np.size(scales) > 1 and self.proposal_layer.min_size != 0 and \
                 not np.all(np.asarray(scales) == scale):
@@ -100,10 +105,12 @@ class RegionProposalNetwork(object):
         rois, roi_indices = flatten_proposals(rois, cnt)
         return rpn_locs, rpn_scores, rois, roi_indices, anchor
 
-    def backward(self, g, g_feat_other):
+    def backward(self, g, g_feat_other=None, out=None, masked=True):
         """g: (N,H,W,g_ld) gradient of the losses w.r.t. [loc | score] (cmr_rpn_loss);
         g_feat_other: gradient already flowing into the feature map (from the RoI head),
-        added in the epilogue.  Returns dL/dfeat * ReLU mask of feat."""
+        added in the epilogue.  Returns dL/dfeat * ReLU mask of feat; with ``masked=False``
+        the RPN branch's own contribution, not masked and not rounded, written to ``out``
+        (the branch then runs ahead of the head's backward pass, which adds to it)."""
         feat, h = self.saved
         self.saved = None
         c, A = self.ctx, self.n_anchor
@@ -114,7 +121,10 @@ class RegionProposalNetwork(object):
         E.column_sums(g, 4 * A, A, c.grad(self.score.b))
         gh = E.conv_gemm(g, self.w_dgrad, self.mid, mask=h)
         self.conv1.backward_w(gh, feat)
-        return self.conv1.backward_x(gh, feat.shape[1:3], addend=g_feat_other, mask=feat)
+        if not masked:
+            return self.conv1.backward_x(gh, feat.shape[1:3], out=out, round_out=False)
+        return self.conv1.backward_x(gh, feat.shape[1:3], addend=g_feat_other, mask=feat,
+                                     out=out)
 
 
 def flatten_proposals(rois, cnt):

@@ -17,6 +17,24 @@ from . import _lib
 from .models import engine as E
 
 
+class _eager_rpn_backward(object):
+    """Lets a MaskRCNNTrainChain run its RPN branch's backward pass ahead, during the forward
+    call: valid here because the gradients were just zeroed and loss.backward() follows."""
+
+    def __init__(self, chain):
+        self.chain = chain if hasattr(chain, 'eager_rpn_backward') else None
+
+    def __enter__(self):
+        if self.chain is not None:
+            self.old = self.chain.eager_rpn_backward
+            self.chain.eager_rpn_backward = True
+
+    def __exit__(self, *exc):
+        if self.chain is not None:
+            self.chain.eager_rpn_backward = self.old
+        return False
+
+
 class WeightDecay(object):
     name = 'WeightDecay'
 
@@ -68,7 +86,8 @@ class MomentumSGD(object):
         loss = None
         if lossfun is not None:
             self.ctx.grads.zero_()
-            loss = lossfun(*args, **kwds)
+            with _eager_rpn_backward(lossfun):
+                loss = lossfun(*args, **kwds)
             loss.backward()
         self.allreduce_grad()
         self.apply_update()
@@ -242,7 +261,8 @@ class GraphedUpdater(object):
         chain._calls = 0        # fixed host seed: the draws advance through seed_word only
         try:
             o.ctx.grads.zero_()
-            loss = chain(st.imgs, st.gt, None, st.masks_arg, scales)
+            with _eager_rpn_backward(chain):
+                loss = chain(st.imgs, st.gt, None, st.masks_arg, scales)
             loss.backward()
             if o.comm is None or o.comm.size == 1:
                 o.apply_update()

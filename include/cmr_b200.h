@@ -70,6 +70,14 @@ int cmr_roi_align_bwd(const float* gy, const float* rois, int R, int N, int C,
                       int H, int W, int outh, int outw, float spatial_scale,
                       int sampling_ratio, float* gx, void* stream);
 
+/* cmr_roi_align_nhwc_bwd without the zero fill: the RoI gradients are ADDED to what gx holds
+ * (the train step starts gx with the RPN branch's gradient of the same feature map, which
+ * was computed earlier on another stream). */
+int cmr_roi_align_nhwc_bwd_accum(const float* gy, const float* rois, int R, int N,
+                                 int H, int W, int C, int outh, int outw,
+                                 int bin_stride, float spatial_scale,
+                                 int sampling_ratio, float* gx, void* stream);
+
 /* The same operator at speed: the feature map is read channels-last (vector loads of 4
  * channels, whole 128-byte lines per warp), the pooled tensor stays in the reference's
  * (R,C,outh,outw) layout -- each CTA stages its (64 channels x outh*outw) block, which is
@@ -267,6 +275,11 @@ int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* 
 
 /* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
 int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
+
+/* out[i] = mask[i] > 0 ? g[i] : 0 (the backward of F.relu as its own pass; out == g
+ * allowed), rounded to tf32 when round_tf32 != 0.  n % 4 == 0, 16-byte aligned. */
+int cmr_relu_mask(const float* g, const float* mask, float* out, size_t n,
+                  int round_tf32, void* stream);
 
 /* Operand split of the 3 x TF32 parity mode: every fp32 value is written as
  * hi = tf32(x) and lo = tf32(x - hi), x = hi + lo up to 2^-22 |x|.  x (rows, c_in) ->

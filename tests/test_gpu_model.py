@@ -536,3 +536,36 @@ def test_graphed_updater_bounds_its_states_and_sees_reloaded_weights():
     model.load_state_dict(sd)
     up(*batches[2])
     assert abs(float(chain.observation['rpn_cls_loss'].item()) - np.log(2.)) < 1e-4
+
+
+def test_rpn_branch_on_side_stream_gives_the_same_step():
+    """The RPN branch forked onto a side stream next to the proposal chain -- losses only
+    (default), and with its backward pass run ahead (what optimizer.update / GraphedUpdater
+    do) -- computes the same losses and gradients as the single-stream schedule."""
+    rs = np.random.RandomState(17)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    imgs_t = torch.from_numpy(imgs).cuda()
+    masks_t = torch.from_numpy(np.stack(masks).astype(np.uint8)).cuda()
+    model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                  base_channels=BASE, seed=4)
+    out = {}
+    for mode in ('serial', 'side_losses', 'side_backward'):
+        chain = models.MaskRCNNTrainChain(model, seed=9)
+        chain.overlap_rpn_branch = mode != 'serial'
+        chain.eager_rpn_backward = mode == 'side_backward'
+        chain.cleargrads()
+        loss = chain(imgs_t, bboxes, labels, masks_t, scales)
+        obs = {k: float(v.item()) for k, v in chain.observation.items()}
+        loss.backward()
+        torch.cuda.synchronize()
+        out[mode] = (obs, model.ctx.grads.clone())
+    for mode in ('side_losses', 'side_backward'):
+        for k, v in out['serial'][0].items():
+            assert abs(out[mode][0][k] - v) <= 1e-6 * max(abs(v), 1e-3), (mode, k)
+        g0, g1 = out['serial'][1], out[mode][1]
+        # atomic weight-gradient reductions: equal up to summation order
+        assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max()), mode
+        for name in ('rpn/conv1/W', 'rpn/loc/W', 'extractor/res4/b5/conv3/W',
+                     'extractor/res3/a/conv1/W'):
+            a, b = model.ctx.train.view(name, g0), model.ctx.train.view(name, g1)
+            assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (mode, name)
