@@ -17,6 +17,8 @@
 //    evaluated separably over a two-column register window (see the kernels).
 //    `bin_stride` produces only every bin_stride-th bin (res5.a reads the 14x14 pool
 //    with stride 2).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cmr {
@@ -707,8 +709,20 @@ __device__ __forceinline__ int tile_index(int c, int p, int PS) {
   return kVec ? c * PS + (p ^ (((c >> 2) & 7) << 2)) : c * PS + p;
 }
 
-template <int CH, bool kVec>
-__global__ void __launch_bounds__(256)
+// kSeg: threads per (row, channel quad): the bins of a row are split into kSeg runs walked by
+// different threads -- the staging tile fixes the shared memory per output element, so more
+// threads per tile is what buys loads in flight (the kernels are L2-latency-bound).
+constexpr int kSeg = 2;
+
+__device__ __forceinline__ void seg_range(int seg, int outw, int& pw0, int& npw) {
+  // even split point, so that bin pairs (8-byte tile accesses) never straddle two threads
+  const int split = ((outw + 1) / 2 + 1) & ~1;
+  pw0 = seg == 0 ? 0 : min(split, outw);
+  npw = seg == 0 ? min(split, outw) : outw - pw0;
+}
+
+template <int CH, bool kVec, int kMinCtas>
+__global__ void __launch_bounds__(448, kMinCtas)
 roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                         float* __restrict__ dst, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int chunks, int n_img) {
@@ -733,13 +747,15 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
   const bool fast = sm->ok != 0;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const int quad = threadIdx.x % Q;
-  const int rows_per_pass = blockDim.x / Q;
+  const int rows_per_pass = blockDim.x / (Q * kSeg);
   if (4 * quad < nch) {
     const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 +
                                                     (c0 >> 2) + quad);
     const int cq = 4 * quad;
-    for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
-      const int p0 = ph * outw;
+    int pw0, npw;
+    seg_range((threadIdx.x / Q) % kSeg, outw, pw0, npw);
+    for (int ph = threadIdx.x / (Q * kSeg); ph < outh; ph += rows_per_pass) {
+      const int p0 = ph * outw + pw0;
       float4 even = make_float4(0.f, 0.f, 0.f, 0.f);
       auto emit = [&](int pw, int, const float4& v) {
         if (kVec) {
@@ -759,10 +775,10 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
         }
       };
       if (fast) {
-        walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, emit);
+        walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, pw0, 1, npw, img, row_bytes, 0, inv, emit);
       } else {
-        for (int pw = 0; pw < outw; ++pw)
-          emit(pw, 0, bin_fwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv));
+        for (int q = 0; q < npw; ++q)
+          emit(q, 0, bin_fwd_generic(g, ph, pw0 + q, H, W, img, row_bytes, px_bytes, inv));
       }
     }
   }
@@ -786,8 +802,8 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
   }
 }
 
-template <int CH, bool kVec>
-__global__ void __launch_bounds__(256)
+template <int CH, bool kVec, int kMinCtas>
+__global__ void __launch_bounds__(448, kMinCtas)
 roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int chunks, int n_img) {
@@ -829,12 +845,15 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   const bool fast = sm->ok != 0;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const int quad = threadIdx.x % Q;
-  const int rows_per_pass = blockDim.x / Q;
+  const int rows_per_pass = blockDim.x / (Q * kSeg);
   if (4 * quad >= nch) return;
   char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4 + (c0 >> 2) + quad);
   const int cq = 4 * quad;
-  for (int ph = threadIdx.x / Q; ph < outh; ph += rows_per_pass) {
-    const int p0 = ph * outw;
+  int pw0, npw;
+  seg_range((threadIdx.x / Q) % kSeg, outw, pw0, npw);
+  if (npw <= 0) return;
+  for (int ph = threadIdx.x / (Q * kSeg); ph < outh; ph += rows_per_pass) {
+    const int p0 = ph * outw + pw0;
     float4 odd = make_float4(0.f, 0.f, 0.f, 0.f);
     auto fetch = [&](int pw, int) {
       if (kVec) {
@@ -851,10 +870,10 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
       return make_float4(t[0], t[PS], t[2 * PS], t[3 * PS]);
     };
     if (fast) {
-      walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, fetch);
+      walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, pw0, 1, npw, img, row_bytes, 0, inv, fetch);
     } else {
-      for (int pw = 0; pw < outw; ++pw)
-        bin_bwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv, fetch(pw, 0));
+      for (int q = 0; q < npw; ++q)
+        bin_bwd_generic(g, ph, pw0 + q, H, W, img, row_bytes, px_bytes, inv, fetch(q, 0));
     }
   }
 }
@@ -871,9 +890,9 @@ size_t cl_smem_bytes(int outh, int outw) {
 }
 
 int cl_threads(int outh) {
-  int t = outh * (kClChannels / 4);
+  int t = outh * kSeg * (kClChannels / 4);
   t = (t + 31) / 32 * 32;
-  return t > 256 ? 256 : (t < 64 ? 64 : t);
+  return t > 448 ? 448 : (t < 64 ? 64 : t);
 }
 
 int pick_threads(int positions) {
@@ -1025,6 +1044,60 @@ extern "C" int cmr_roi_align_cl_supported(int N, int C, int H, int W, int R, int
   return cl_supported(N, C, H, W, R, outh, outw) ? 1 : 0;
 }
 
+namespace {
+// Measurement knob: CMR_ROI_CL_CTAS=3 compiles the walkers for three CTAs per SM (40
+// registers, a few spilled words) instead of two (64 registers).
+int cl_min_ctas() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CMR_ROI_CL_CTAS");
+    v = e ? atoi(e) : 2;
+    if (v != 3) v = 2;
+  }
+  return v;
+}
+
+template <bool kVec, int kMinCtas>
+int launch_cl_fwd(const float* x_nhwc, int N, int H, int W, int C, const float* rois, int R,
+                  int outh, int outw, float spatial_scale, int sampling_ratio, float* y,
+                  cudaStream_t st) {
+  const size_t smem = cl_smem_bytes(outh, outw);
+  int rc = cl_configure(roi_align_cl_fwd_kernel<kClChannels, kVec, kMinCtas>, smem);
+  if (rc != CMR_OK) return rc;
+  const int chunks = ceil_div(C, kClChannels);
+  prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), st);
+  roi_align_cl_fwd_kernel<kClChannels, kVec, kMinCtas><<<R * chunks, cl_threads(outh), smem, st>>>(
+      reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
+      sampling_ratio, chunks, N);
+  prof_end(st);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+
+template <bool kVec, int kMinCtas>
+int launch_cl_bwd(const float* gy, const float* rois, int R, int N, int H, int W, int C, int outh,
+                  int outw, float spatial_scale, int sampling_ratio, float* gx_nhwc,
+                  cudaStream_t st) {
+  const size_t smem = cl_smem_bytes(outh, outw);
+  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels, kVec, kMinCtas>, smem);
+  if (rc != CMR_OK) return rc;
+  prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), st);
+  cudaError_t me = cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, st);
+  if (me != cudaSuccess || R == 0) {
+    prof_end(st);
+    CMR_CUDA_TRY(me);
+    return CMR_OK;
+  }
+  const int chunks = ceil_div(C, kClChannels);
+  roi_align_cl_bwd_kernel<kClChannels, kVec, kMinCtas><<<R * chunks, cl_threads(outh), smem, st>>>(
+      gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
+      sampling_ratio, chunks, N);
+  prof_end(st);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
+}  // namespace
+
 extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, int C,
                                     const float* rois, int R, int outh, int outw,
                                     float spatial_scale, int sampling_ratio, float* y,
@@ -1034,26 +1107,12 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(x_nhwc && rois && y);
-  const size_t smem = cl_smem_bytes(outh, outw);
-  const bool vec = cl_vec(outh, outw);
-  int rc = vec ? cl_configure(roi_align_cl_fwd_kernel<kClChannels, true>, smem)
-               : cl_configure(roi_align_cl_fwd_kernel<kClChannels, false>, smem);
-  if (rc != CMR_OK) return rc;
-  const int chunks = ceil_div(C, kClChannels);
-  prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
-  if (vec)
-    roi_align_cl_fwd_kernel<kClChannels, true>
-        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-            reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
-            sampling_ratio, chunks, N);
-  else
-    roi_align_cl_fwd_kernel<kClChannels, false>
-        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-            reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
-            sampling_ratio, chunks, N);
-  prof_end(as_stream(stream));
-  CMR_LAUNCH_CHECK();
-  return CMR_OK;
+  cudaStream_t st = as_stream(stream);
+  const bool vec = cl_vec(outh, outw), three = cl_min_ctas() == 3;
+#define CMR_CL_ARGS x_nhwc, N, H, W, C, rois, R, outh, outw, spatial_scale, sampling_ratio, y, st
+  if (vec) return three ? launch_cl_fwd<true, 3>(CMR_CL_ARGS) : launch_cl_fwd<true, 2>(CMR_CL_ARGS);
+  return three ? launch_cl_fwd<false, 3>(CMR_CL_ARGS) : launch_cl_fwd<false, 2>(CMR_CL_ARGS);
+#undef CMR_CL_ARGS
 }
 
 extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, int N, int H,
@@ -1063,33 +1122,12 @@ extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, i
   CMR_REQUIRE(sampling_ratio >= 0 && gx_nhwc);
   if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
   CMR_REQUIRE(R == 0 || (gy && rois));
-  const size_t smem = cl_smem_bytes(outh, outw);
-  const bool vec = cl_vec(outh, outw);
-  int rc = vec ? cl_configure(roi_align_cl_bwd_kernel<kClChannels, true>, smem)
-               : cl_configure(roi_align_cl_bwd_kernel<kClChannels, false>, smem);
-  if (rc != CMR_OK) return rc;
-  prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), as_stream(stream));
-  cudaError_t me =
-      cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, as_stream(stream));
-  if (me != cudaSuccess || R == 0) {
-    prof_end(as_stream(stream));
-    CMR_CUDA_TRY(me);
-    return CMR_OK;
-  }
-  const int chunks = ceil_div(C, kClChannels);
-  if (vec)
-    roi_align_cl_bwd_kernel<kClChannels, true>
-        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-            gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
-            sampling_ratio, chunks, N);
-  else
-    roi_align_cl_bwd_kernel<kClChannels, false>
-        <<<R * chunks, cl_threads(outh), smem, as_stream(stream)>>>(
-            gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
-            sampling_ratio, chunks, N);
-  prof_end(as_stream(stream));
-  CMR_LAUNCH_CHECK();
-  return CMR_OK;
+  cudaStream_t st = as_stream(stream);
+  const bool vec = cl_vec(outh, outw), three = cl_min_ctas() == 3;
+#define CMR_CL_ARGS gy, rois, R, N, H, W, C, outh, outw, spatial_scale, sampling_ratio, gx_nhwc, st
+  if (vec) return three ? launch_cl_bwd<true, 3>(CMR_CL_ARGS) : launch_cl_bwd<true, 2>(CMR_CL_ARGS);
+  return three ? launch_cl_bwd<false, 3>(CMR_CL_ARGS) : launch_cl_bwd<false, 2>(CMR_CL_ARGS);
+#undef CMR_CL_ARGS
 }
 
 extern "C" size_t cmr_roi_align_workspace_bytes(int N, int C, int H, int W) {

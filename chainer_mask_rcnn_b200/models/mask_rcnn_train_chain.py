@@ -40,11 +40,16 @@ class Loss(object):
 
     data = property(lambda self: self.array)
 
-    def backward(self):
+    def backward(self, after_head=None):
+        """Runs the backward schedule.  ``after_head``: optional callable invoked once the
+        gradients of the RPN and RoI-head parameters are final (every kernel that writes them
+        has been enqueued and joined onto the current stream) and before the backbone's
+        backward pass is enqueued -- the data-parallel optimizer starts the all-reduce of
+        that bucket there, under the backbone's backward pass."""
         if self._backward_fn is None:
             raise RuntimeError('backward() was already called for this loss')
         fn, self._backward_fn = self._backward_fn, None
-        fn()
+        fn(after_head)
 
     def item(self):
         return float(self.array.item())
@@ -309,7 +314,7 @@ class MaskRCNNTrainChain(object):
         self.outputs = dict(rpn_locs=rpn_locs, rpn_scores=rpn_scores, roi_cls_locs=cls_locs,
                             roi_scores=scores, roi_masks=masks)
 
-        def backward():
+        def backward(after_head=None):
             # weight / bias gradients run on a side stream next to the data-gradient chain
             E.grad_side.begin()
             try:
@@ -325,6 +330,10 @@ class MaskRCNNTrainChain(object):
                         torch.cuda.current_stream().wait_event(rpn_branch['done'])
                     g_feat = head.backward(g_lin, g_mask)
                     g_feat = rpn.backward(g_rpn, g_feat)
+                if after_head is not None:
+                    E.grad_side.join()
+                    after_head()
+                    E.grad_side.begin()
                 m.extractor.backward(g_feat)
             finally:
                 E.grad_side.join()

@@ -81,6 +81,47 @@ class MomentumSGD(object):
         if self.comm is not None and self.comm.size > 1:
             torch.distributed.all_reduce(self.ctx.grads, group=self.comm.group)
 
+    def grad_buckets(self):
+        """The flat gradient buffer as two views: (backbone, RPN + RoI head).  Parameters are
+        laid out in creation order -- extractor, rpn, head -- and the backward pass finishes
+        them in the reverse order, so the second view is final while the backbone's backward
+        pass still runs."""
+        store = self.ctx.train
+        split = store.size
+        for name, _, off in store.specs:
+            if not name.startswith('extractor/'):
+                split = off
+                break
+        return self.ctx.grads[:split], self.ctx.grads[split:]
+
+    def update_overlapped(self, lossfun, *args, **kwds):
+        """update() with the gradient exchange split in two all-reduces, the first (RPN +
+        RoI head, ~3/4 of the R50 bytes) issued as soon as those gradients are final and
+        running on NCCL's stream under the backbone's backward pass, the second after it;
+        then the fused update.  Same result as update() (a sum is a sum).  Capturable in a
+        CUDA graph: the collectives become graph nodes."""
+        import torch.distributed as dist
+        self.broadcast_params()
+        self.ctx.grads.zero_()
+        with _eager_rpn_backward(lossfun):
+            loss = lossfun(*args, **kwds)
+        multi = self.comm is not None and self.comm.size > 1
+        backbone, heads = self.grad_buckets()
+        pending = []
+
+        def after_head():
+            if multi and heads.numel():
+                pending.append(dist.all_reduce(heads, group=self.comm.group, async_op=True))
+
+        loss.backward(after_head=after_head)
+        if multi and backbone.numel():
+            pending.append(dist.all_reduce(backbone, group=self.comm.group, async_op=True))
+        for work in pending:
+            work.wait()                     # the current stream waits; the host does not
+        self.apply_update()
+        self.t += 1
+        return loss
+
     def update(self, lossfun=None, *args, **kwds):
         self.broadcast_params()
         loss = None
@@ -177,8 +218,17 @@ class GraphedUpdater(object):
     canvas sizes (``datasets.concat_examples(..., canvas=(H, W))``) to stay on replays.
     """
 
-    def __init__(self, optimizer, lossfun, max_boxes=64, use_graph=True, max_states=4):
+    def __init__(self, optimizer, lossfun, max_boxes=64, use_graph=True, max_states=4,
+                 graph_allreduce=None):
         import collections
+        import os
+        # More than one rank: the two bucketed all-reduces and the update are captured INSIDE
+        # the graph (MomentumSGD.update_overlapped), the first one overlapping the backbone's
+        # backward pass.  graph_allreduce=False (or CMR_GRAPH_ALLREDUCE=0) keeps the collective
+        # outside: replay, then one all-reduce over the whole buffer, then the update.
+        if graph_allreduce is None:
+            graph_allreduce = os.environ.get('CMR_GRAPH_ALLREDUCE', '1') != '0'
+        self.graph_allreduce = bool(graph_allreduce)
         from .models.utils import GroundTruth
         self.use_graph = use_graph
         self._GroundTruth = GroundTruth
@@ -259,13 +309,18 @@ class GraphedUpdater(object):
         o, chain = self.optimizer, self.lossfun
         chain.seed_dev = st.seed_word
         chain._calls = 0        # fixed host seed: the draws advance through seed_word only
+        multi = o.comm is not None and o.comm.size > 1
         try:
-            o.ctx.grads.zero_()
-            with _eager_rpn_backward(chain):
-                loss = chain(st.imgs, st.gt, None, st.masks_arg, scales)
-            loss.backward()
-            if o.comm is None or o.comm.size == 1:
-                o.apply_update()
+            if multi and self.graph_allreduce:
+                loss = o.update_overlapped(chain, st.imgs, st.gt, None, st.masks_arg, scales)
+                o.t -= 1                     # counted by _run
+            else:
+                o.ctx.grads.zero_()
+                with _eager_rpn_backward(chain):
+                    loss = chain(st.imgs, st.gt, None, st.masks_arg, scales)
+                loss.backward()
+                if not multi:
+                    o.apply_update()
             st.seed_word += 1
         finally:
             chain.seed_dev = None
@@ -321,7 +376,7 @@ class GraphedUpdater(object):
                 st.graph = g
             st.graph.replay()
             loss = st.loss
-        if o.comm is not None and o.comm.size > 1:
+        if o.comm is not None and o.comm.size > 1 and not self.graph_allreduce:
             o.allreduce_grad()
             o.apply_update()
         st.calls += 1

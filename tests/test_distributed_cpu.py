@@ -127,3 +127,98 @@ def test_flat_store_slots_are_tma_aligned():
         assert off % E.ALIGN == 0
         assert tuple(s.view(name).shape) == tuple(shape)
     assert s.size % E.ALIGN == 0
+
+
+class _FakeLoss(object):
+    """A loss whose backward() fills the flat gradient buffer in the real order -- RPN and
+    head parameters first, the after_head hook, then the backbone's."""
+
+    def __init__(self, ctx, image_ids):
+        self.ctx, self.ids = ctx, image_ids
+        self.hook_saw_heads_only = None
+
+    def backward(self, after_head=None):
+        store = self.ctx.train
+        full = sum(_fake_grad(store, i) for i in self.ids) / len(self.ids)
+        heads = [n for n in store.names() if not n.startswith('extractor/')]
+        for n in heads:
+            store.view(n, self.ctx.grads).add_(store.view(n, full))
+        if after_head is not None:
+            before = self.ctx.grads.clone()
+            after_head()
+            self.hook_saw_heads_only = all(
+                float(store.view(n, before).abs().sum()) == 0.
+                for n in store.names() if n.startswith('extractor/'))
+        for n in store.names():
+            if n.startswith('extractor/'):
+                store.view(n, self.ctx.grads).add_(store.view(n, full))
+
+
+def _make_store4():
+    s = E.FlatStore()
+    s.add('extractor/res4/a/conv1/W', (6, 1, 1, 4))
+    s.add('extractor/res4/a/conv2/W', (6, 3, 3, 6))
+    s.add('rpn/conv1/W', (8, 3, 3, 4))
+    s.add('head/score/W', (5, 7))
+    return s.allocate('cpu')
+
+
+def _worker_overlapped(rank, world, port, n_images, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        comm = optimizers.create_communicator()
+        opt = optimizers.MomentumSGD(lr=0.005, momentum=0.9)
+        store = _make_store4()
+        # replicas start DIFFERENT (per-rank seed): the broadcast makes them rank 0's
+        store.data.copy_(torch.from_numpy(
+            np.random.RandomState(rank).standard_normal(store.data.shape).astype(np.float32)))
+        ctx = _Ctx(store)
+        ctx.frozen = E.FlatStore()
+        ctx.frozen.add('extractor/conv1/W', (4, 7, 7, 3))
+        ctx.frozen.allocate('cpu')
+        ctx.frozen.data.fill_(float(rank + 1))
+        ctx.mark_dirty = lambda frozen=True: None
+
+        class Chain(object):
+            pass
+        chain = Chain()
+        chain.ctx = ctx
+        opt.setup(chain)
+        opt = optimizers.create_multi_node_optimizer(opt, comm)
+        assert not opt._needs_broadcast                      # done at attach time
+        np.save(os.path.join(out_dir, 'p0_%d.npy' % rank), store.data.numpy().copy())
+        np.save(os.path.join(out_dir, 'f0_%d.npy' % rank), ctx.frozen.data.numpy().copy())
+        backbone, heads = opt.grad_buckets()
+        assert backbone.numel() + heads.numel() == ctx.grads.numel()
+        assert backbone.data_ptr() == ctx.grads.data_ptr() and heads.numel() > 0
+        mine = list(optimizers.shard_indices(n_images, comm.size, comm.rank))
+        fake = _FakeLoss(ctx, mine)
+        applied = []
+        opt.apply_update = lambda: applied.append(ctx.grads.clone())
+        opt.update_overlapped(lambda: fake)
+        assert fake.hook_saw_heads_only is True and len(applied) == 1
+        np.save(os.path.join(out_dir, 'og_%d.npy' % rank), applied[0].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_bucketed_overlapped_update_and_parameter_broadcast(tmp_path):
+    """MomentumSGD.update_overlapped: two all-reduces (RPN + head bucket from the after_head
+    hook, backbone bucket at the end) give the gradient sum of one all-reduce; and
+    create_multi_node_optimizer broadcasts rank 0's parameters (trainable and frozen) like
+    chainermn's optimizer does on its first update."""
+    world, n_images = 2, 4
+    port = _free_port()
+    mp.spawn(_worker_overlapped, args=(world, port, n_images, str(tmp_path)), nprocs=world,
+             join=True)
+    g0, g1 = np.load(tmp_path / 'og_0.npy'), np.load(tmp_path / 'og_1.npy')
+    assert np.array_equal(g0, g1)
+    store = _make_store4()
+    want = sum(_fake_grad(store, i) for i in range(n_images)).numpy() / n_images
+    np.testing.assert_allclose(g0 / world, want, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(np.load(tmp_path / 'p0_0.npy'), np.load(tmp_path / 'p0_1.npy'))
+    assert np.array_equal(np.load(tmp_path / 'f0_1.npy'), np.load(tmp_path / 'f0_0.npy'))
+    assert float(np.load(tmp_path / 'f0_1.npy')[0]) == 1.0          # rank 0's value

@@ -102,8 +102,9 @@ def _gemm_case(key, g):
         got = torch.zeros(outs, device='cuda')
         E.conv_gemm(xr, wr, n, kh, kw, stride, pad, out=got, round_out=False, d_stride=d_stride)
         oh, ow = want.shape[1:3]
-        sub = got[:, ::d_stride, ::d_stride][:, :oh, :ow]
-        assert float(got.abs().sum()) == float(sub.abs().sum())     # nothing written elsewhere
+        sub = got[:, ::d_stride, ::d_stride][:, :oh, :ow].clone()
+        got[:, ::d_stride, ::d_stride] = 0
+        assert float(got.abs().max()) == 0.                         # nothing written elsewhere
         return rel(sub, want)
     got = torch.zeros(outs, device='cuda')
     E.conv_gemm(xr, wr, n, kh, kw, stride, pad, out=got, round_out=False)

@@ -563,9 +563,11 @@ def test_rpn_branch_on_side_stream_gives_the_same_step():
         for k, v in out['serial'][0].items():
             assert abs(out[mode][0][k] - v) <= 1e-6 * max(abs(v), 1e-3), (mode, k)
         g0, g1 = out['serial'][1], out[mode][1]
-        # atomic weight-gradient reductions: equal up to summation order
+        # atomic reductions (weight gradients; the RoI head's gradient added to the RPN's
+        # or the other way round) -> equal up to summation order, and the tf32 rounding of the
+        # feature-map gradient turns a last-bit difference into 2^-11 of single entries
         assert float((g1 - g0).abs().max()) <= 2e-5 * float(g0.abs().max()), mode
         for name in ('rpn/conv1/W', 'rpn/loc/W', 'extractor/res4/b5/conv3/W',
                      'extractor/res3/a/conv1/W'):
             a, b = model.ctx.train.view(name, g0), model.ctx.train.view(name, g1)
-            assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()), (mode, name)
+            assert float((a - b).abs().max()) <= 1e-3 * float(a.abs().max()), (mode, name)
