@@ -1,6 +1,6 @@
 #!/bin/bash
 # ncu --set full captures.  usage: gpu_ncu.sh <tag> <target>:<kernel-regex> ...
-tag=$1; shift
+tag=$1; shift; export CMR_ROI_CL_CTAS=${CMR_ROI_CL_CTAS:-2}
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || tail -20 gpurun_out/build.log
 for spec in "$@"; do

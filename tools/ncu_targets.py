@@ -5,7 +5,9 @@ few times.
   small     res4 3x3 (8568 x 256 x 2304)
   wgrad     res5 3x3 weight gradient, all 9 taps (512 x 512 over 50176 pixels)
   wgrad1x1  res5 conv3 weight gradient (2048 x 512 over 50176 pixels)
-  roi       ROIAlign NHWC forward + backward, train shape (1024 RoIs, 2x51x84x1024, 7x7 bins)"""
+  roi       ROIAlign NHWC forward + backward, train shape (1024 RoIs, 2x51x84x1024, 7x7 bins)
+  roi_cl    the drop-in operator's kernels (functions.roi_align_2d forward + backward):
+            1000 RoIs on a 1x1024x50x68 map, 14x14 bins (BASELINE.json configs[4])"""
 import os
 import sys
 
@@ -18,6 +20,8 @@ sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from chainer_mask_rcnn_b200.models import engine as E  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'conv'
+if what not in ('conv1x1', 'wgrad1x1'):
+    what = what.rstrip('0123456789')      # 'roi2' = a second capture of target 'roi'
 dev = 'cuda'
 x = E.round_tf32(torch.randn((1024, 7, 7, 512), device=dev))
 w = E.round_tf32(torch.randn((512, 3, 3, 512), device=dev) / 68.)
@@ -36,7 +40,18 @@ if what == 'roi':
     rs = np.random.RandomState(0)
     feat = torch.randn((2, 51, 84, 1024), device=dev)
     rois = torch.from_numpy(synth.rois_xy(rs, 1024, 2, 800, 1333)).cuda()
+if what == 'roi_cl':
+    import synth
+    from chainer_mask_rcnn_b200 import functions
+    rs = np.random.RandomState(0)
+    xm = torch.from_numpy(rs.standard_normal((1, 1024, 50, 68)).astype(np.float32)).cuda()
+    xm = xm.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+    rois = torch.from_numpy(synth.rois_xy(rs, 1000, 1, 800, 1088)).cuda()
 for _ in range(4):
+    if what == 'roi_cl':
+        y = functions.roi_align_2d(xm, rois, 14, 14, 1. / 16)
+        y.backward(torch.ones_like(y))
+        xm.grad = None
     if what == 'conv':
         E.conv_gemm(x, w, 512, 3, 3, 1, 1, scale=scale, bias=bias, relu=True)
     if what == 'conv1x1':
