@@ -595,7 +595,7 @@ struct RowKernelSmem {
   float4 xt[kColTaps];
 };
 
-__global__ void __launch_bounds__(128)   // (128, 8) = 64 registers was measured: slower
+__global__ void __launch_bounds__(128, 6)   // (128, 8) = 64 registers was measured: slower
 roi_align_nhwc_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                           float4* __restrict__ dst, int H, int W, int C4, int outh, int outw,
                           int bin_stride, int oh_s, int ow_s, float scale, int sampling_ratio,
@@ -709,30 +709,20 @@ __device__ __forceinline__ int tile_index(int c, int p, int PS) {
   return kVec ? c * PS + (p ^ (((c >> 2) & 7) << 2)) : c * PS + p;
 }
 
-// kSeg: threads per (row, channel quad): the bins of a row are split into kSeg runs walked by
-// different threads -- the staging tile fixes the shared memory per output element, so more
-// threads per tile is what buys loads in flight (the kernels are L2-latency-bound).
-constexpr int kSeg = 2;
-
-__device__ __forceinline__ void seg_range(int seg, int outw, int& pw0, int& npw) {
-  // even split point, so that bin pairs (8-byte tile accesses) never straddle two threads
-  const int split = ((outw + 1) / 2 + 1) & ~1;
-  pw0 = seg == 0 ? 0 : min(split, outw);
-  npw = seg == 0 ? min(split, outw) : outw - pw0;
-}
-
-template <int CH, bool kVec, int kMinCtas>
-__global__ void __launch_bounds__(448, kMinCtas)
+// One CTA serves `cpc` consecutive channel chunks of its RoI, so the tap tables are built
+// once per cpc * CH channels (they are 15 % of the instructions when built per chunk).
+template <int CH, bool kVec>
+__global__ void __launch_bounds__(256, 3)      // the staging tile allows three CTAs per SM
 roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                         float* __restrict__ dst, int H, int W, int C, int outh, int outw,
-                        float scale, int sampling_ratio, int chunks, int n_img) {
+                        float scale, int sampling_ratio, int groups, int cpc, int n_img) {
   extern __shared__ __align__(16) unsigned char roi_smem[];
   RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
   float* tile = reinterpret_cast<float*>(roi_smem + sizeof(RoiTileSmem));
   constexpr int Q = CH / 4;
-  const int r = blockIdx.x / chunks;
-  const int c0 = (blockIdx.x - r * chunks) * CH;
-  const int nch = min(CH, C - c0);
+  const int r = blockIdx.x / groups;
+  const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
+  const int c_end = min(C, c_begin + cpc * CH);
   const int P = outh * outw;
   const int PS = kVec ? (P + 31) / 32 * 32 : P + 1;
   RowBlend* rb = reinterpret_cast<RowBlend*>(tile + (size_t)CH * PS);
@@ -747,73 +737,75 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
   const bool fast = sm->ok != 0;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const int quad = threadIdx.x % Q;
-  const int rows_per_pass = blockDim.x / (Q * kSeg);
-  if (4 * quad < nch) {
-    const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 +
-                                                    (c0 >> 2) + quad);
-    const int cq = 4 * quad;
-    int pw0, npw;
-    seg_range((threadIdx.x / Q) % kSeg, outw, pw0, npw);
-    for (int ph = threadIdx.x / (Q * kSeg); ph < outh; ph += rows_per_pass) {
-      const int p0 = ph * outw + pw0;
-      float4 even = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto emit = [&](int pw, int, const float4& v) {
-        if (kVec) {
-          // two bins of a channel are 8 contiguous bytes of the tile (p0 + pw is even)
-          if ((pw & 1) == 0) {
-            even = v;
+  const int row0 = threadIdx.x / Q, rows_per_pass = blockDim.x / Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int cq = 4 * quad;
+  // this thread's four channel rows of the tile and the XOR of its 16-byte groups
+  float* const t0 = tile + (size_t)cq * PS;
+  const int swz = kVec ? (quad & 7) << 2 : 0;
+  for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+    const int nch = min(CH, C - c0);
+    if (cq < nch) {
+      const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 +
+                                                      (c0 >> 2) + quad);
+      for (int ph = row0; ph < outh; ph += rows_per_pass) {
+        const int p0 = ph * outw;
+        float4 even = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto emit = [&](int pw, int, const float4& v) {
+          if (kVec) {
+            // two bins of a channel are 8 contiguous bytes of the tile (p0 + pw is even)
+            if ((pw & 1) == 0) {
+              even = v;
+            } else {
+              float* t = t0 + ((p0 + pw - 1) ^ swz);
+              *reinterpret_cast<float2*>(t) = make_float2(even.x, v.x);
+              *reinterpret_cast<float2*>(t + PS) = make_float2(even.y, v.y);
+              *reinterpret_cast<float2*>(t + 2 * PS) = make_float2(even.z, v.z);
+              *reinterpret_cast<float2*>(t + 3 * PS) = make_float2(even.w, v.w);
+            }
           } else {
-            const int p = p0 + pw - 1;
-            *reinterpret_cast<float2*>(tile + tile_index<true>(cq, p, PS)) = make_float2(even.x, v.x);
-            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 1, p, PS)) = make_float2(even.y, v.y);
-            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 2, p, PS)) = make_float2(even.z, v.z);
-            *reinterpret_cast<float2*>(tile + tile_index<true>(cq + 3, p, PS)) = make_float2(even.w, v.w);
+            float* t = t0 + p0 + pw;
+            t[0] = v.x; t[PS] = v.y; t[2 * PS] = v.z; t[3 * PS] = v.w;
           }
+        };
+        if (fast) {
+          walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, emit);
         } else {
-          float* t = tile + (size_t)cq * PS + p0 + pw;
-          t[0] = v.x; t[PS] = v.y; t[2 * PS] = v.z; t[3 * PS] = v.w;
+          for (int pw = 0; pw < outw; ++pw)
+            emit(pw, 0, bin_fwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv));
         }
-      };
-      if (fast) {
-        walk_row_fwd<1>(rb[ph], sm->xt, g.grid_w, pw0, 1, npw, img, row_bytes, 0, inv, emit);
-      } else {
-        for (int q = 0; q < npw; ++q)
-          emit(q, 0, bin_fwd_generic(g, ph, pw0 + q, H, W, img, row_bytes, px_bytes, inv));
       }
     }
-  }
-  __syncthreads();
-  // the CTA's (nch, P) block is contiguous in the pooled tensor
-  float* out = dst + ((size_t)r * C + c0) * P;
-  if (kVec) {
-    const int P4 = P >> 2;
-    for (int i = threadIdx.x; i < nch * P4; i += blockDim.x) {
-      const int c = i / P4, g4 = i - c * P4;
-      reinterpret_cast<float4*>(out)[i] =
-          *reinterpret_cast<const float4*>(tile + tile_index<true>(c, 4 * g4, PS));
-    }
-  } else {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    __syncthreads();
+    // the chunk's (nch, P) block is contiguous in the pooled tensor: a warp per channel
+    float* out = dst + ((size_t)r * C + c0) * P;
     for (int c = warp; c < nch; c += nwarp) {
       const float* tp = tile + (size_t)c * PS;
       float* op = out + (size_t)c * P;
-      for (int p = lane; p < P; p += 32) op[p] = tp[p];
+      if (kVec) {
+        const int sw = ((c >> 2) & 7) << 2;
+        for (int q4 = lane; q4 < (P >> 2); q4 += 32)
+          reinterpret_cast<float4*>(op)[q4] = *reinterpret_cast<const float4*>(tp + ((4 * q4) ^ sw));
+      } else {
+        for (int p = lane; p < P; p += 32) op[p] = tp[p];
+      }
     }
+    if (c0 + CH < c_end) __syncthreads();      // the tile is rewritten by the next chunk
   }
 }
 
-template <int CH, bool kVec, int kMinCtas>
-__global__ void __launch_bounds__(448, kMinCtas)
+template <int CH, bool kVec>
+__global__ void __launch_bounds__(256, 3)
 roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
-                        float scale, int sampling_ratio, int chunks, int n_img) {
+                        float scale, int sampling_ratio, int groups, int cpc, int n_img) {
   extern __shared__ __align__(16) unsigned char roi_smem[];
   RoiTileSmem* sm = reinterpret_cast<RoiTileSmem*>(roi_smem);
   float* tile = reinterpret_cast<float*>(roi_smem + sizeof(RoiTileSmem));
   constexpr int Q = CH / 4;
-  const int r = blockIdx.x / chunks;
-  const int c0 = (blockIdx.x - r * chunks) * CH;
-  const int nch = min(CH, C - c0);
+  const int r = blockIdx.x / groups;
+  const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
+  const int c_end = min(C, c_begin + cpc * CH);
   const int P = outh * outw;
   const int PS = kVec ? (P + 31) / 32 * 32 : P + 1;
   RowBlend* rb = reinterpret_cast<RowBlend*>(tile + (size_t)CH * PS);
@@ -821,23 +813,6 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
   if (threadIdx.x == 0) sm->ok = outw * g.grid_w <= kColTaps ? 1 : 0;
-  // the CTA's block of the pooled gradient: (nch, P) contiguous floats
-  const float* in = gy + ((size_t)r * C + c0) * P;
-  if (kVec) {
-    const int P4 = P >> 2;
-    for (int i = threadIdx.x; i < nch * P4; i += blockDim.x) {
-      const int c = i / P4, g4 = i - c * P4;
-      *reinterpret_cast<float4*>(tile + tile_index<true>(c, 4 * g4, PS)) =
-          __ldg(reinterpret_cast<const float4*>(in) + i);
-    }
-  } else {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int c = warp; c < nch; c += nwarp) {
-      float* tp = tile + (size_t)c * PS;
-      const float* ip = in + (size_t)c * P;
-      for (int p = lane; p < P; p += 32) tp[p] = __ldg(ip + p);
-    }
-  }
   __syncthreads();
   build_row_blends(rb, &sm->ok, g, 0, 1, outh, H, row_bytes);
   if (outw * g.grid_w <= kColTaps) build_col_taps(sm->xt, g, outw, W, px_bytes);
@@ -845,36 +820,56 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   const bool fast = sm->ok != 0;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const int quad = threadIdx.x % Q;
-  const int rows_per_pass = blockDim.x / (Q * kSeg);
-  if (4 * quad >= nch) return;
-  char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4 + (c0 >> 2) + quad);
+  const int row0 = threadIdx.x / Q, rows_per_pass = blockDim.x / Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int cq = 4 * quad;
-  int pw0, npw;
-  seg_range((threadIdx.x / Q) % kSeg, outw, pw0, npw);
-  if (npw <= 0) return;
-  for (int ph = threadIdx.x / (Q * kSeg); ph < outh; ph += rows_per_pass) {
-    const int p0 = ph * outw + pw0;
-    float4 odd = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fetch = [&](int pw, int) {
+  const float* const t0 = tile + (size_t)cq * PS;
+  const int swz = kVec ? (quad & 7) << 2 : 0;
+  for (int c0 = c_begin; c0 < c_end; c0 += CH) {
+    const int nch = min(CH, C - c0);
+    // the chunk's block of the pooled gradient: (nch, P) contiguous floats
+    const float* in = gy + ((size_t)r * C + c0) * P;
+    for (int c = warp; c < nch; c += nwarp) {
+      float* tp = tile + (size_t)c * PS;
+      const float* ip = in + (size_t)c * P;
       if (kVec) {
-        if (pw & 1) return odd;
-        const int p = p0 + pw;
-        const float2 a = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq, p, PS));
-        const float2 b = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 1, p, PS));
-        const float2 c = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 2, p, PS));
-        const float2 d = *reinterpret_cast<const float2*>(tile + tile_index<true>(cq + 3, p, PS));
-        odd = make_float4(a.y, b.y, c.y, d.y);
-        return make_float4(a.x, b.x, c.x, d.x);
+        const int sw = ((c >> 2) & 7) << 2;
+        for (int q4 = lane; q4 < (P >> 2); q4 += 32)
+          *reinterpret_cast<float4*>(tp + ((4 * q4) ^ sw)) =
+              __ldg(reinterpret_cast<const float4*>(ip) + q4);
+      } else {
+        for (int p = lane; p < P; p += 32) tp[p] = __ldg(ip + p);
       }
-      const float* t = tile + (size_t)cq * PS + p0 + pw;
-      return make_float4(t[0], t[PS], t[2 * PS], t[3 * PS]);
-    };
-    if (fast) {
-      walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, pw0, 1, npw, img, row_bytes, 0, inv, fetch);
-    } else {
-      for (int q = 0; q < npw; ++q)
-        bin_bwd_generic(g, ph, pw0 + q, H, W, img, row_bytes, px_bytes, inv, fetch(q, 0));
     }
+    __syncthreads();
+    if (cq < nch) {
+      char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4 + (c0 >> 2) + quad);
+      for (int ph = row0; ph < outh; ph += rows_per_pass) {
+        const int p0 = ph * outw;
+        float4 odd = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&](int pw, int) {
+          if (kVec) {
+            if (pw & 1) return odd;
+            const float* t = t0 + ((p0 + pw) ^ swz);
+            const float2 a = *reinterpret_cast<const float2*>(t);
+            const float2 b = *reinterpret_cast<const float2*>(t + PS);
+            const float2 c = *reinterpret_cast<const float2*>(t + 2 * PS);
+            const float2 d = *reinterpret_cast<const float2*>(t + 3 * PS);
+            odd = make_float4(a.y, b.y, c.y, d.y);
+            return make_float4(a.x, b.x, c.x, d.x);
+          }
+          const float* t = t0 + p0 + pw;
+          return make_float4(t[0], t[PS], t[2 * PS], t[3 * PS]);
+        };
+        if (fast) {
+          walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, fetch);
+        } else {
+          for (int pw = 0; pw < outw; ++pw)
+            bin_bwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv, fetch(pw, 0));
+        }
+      }
+    }
+    if (c0 + CH < c_end) __syncthreads();      // the tile is refilled by the next chunk
   }
 }
 
@@ -890,9 +885,18 @@ size_t cl_smem_bytes(int outh, int outw) {
 }
 
 int cl_threads(int outh) {
-  int t = outh * kSeg * (kClChannels / 4);
+  int t = outh * (kClChannels / 4);
   t = (t + 31) / 32 * 32;
-  return t > 448 ? 448 : (t < 64 ? 64 : t);
+  return t > 256 ? 256 : (t < 64 ? 64 : t);
+}
+
+// Chunks per CTA: as many as keep >= 8 CTAs per SM in the grid (a power of two <= 16).
+int cl_chunks_per_cta(int R, int chunks) {
+  int cpc = 1;
+  while (cpc < 16 && cpc * 2 <= chunks &&
+         (long long)R * ceil_div(chunks, cpc * 2) >= 8ll * sm_count())
+    cpc *= 2;
+  return cpc;
 }
 
 int pick_threads(int positions) {
@@ -1045,41 +1049,30 @@ extern "C" int cmr_roi_align_cl_supported(int N, int C, int H, int W, int R, int
 }
 
 namespace {
-// Measurement knob: CMR_ROI_CL_CTAS=3 compiles the walkers for three CTAs per SM (40
-// registers, a few spilled words) instead of two (64 registers).
-int cl_min_ctas() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CMR_ROI_CL_CTAS");
-    v = e ? atoi(e) : 2;
-    if (v != 3) v = 2;
-  }
-  return v;
-}
-
-template <bool kVec, int kMinCtas>
+template <bool kVec>
 int launch_cl_fwd(const float* x_nhwc, int N, int H, int W, int C, const float* rois, int R,
                   int outh, int outw, float spatial_scale, int sampling_ratio, float* y,
                   cudaStream_t st) {
   const size_t smem = cl_smem_bytes(outh, outw);
-  int rc = cl_configure(roi_align_cl_fwd_kernel<kClChannels, kVec, kMinCtas>, smem);
+  int rc = cl_configure(roi_align_cl_fwd_kernel<kClChannels, kVec>, smem);
   if (rc != CMR_OK) return rc;
   const int chunks = ceil_div(C, kClChannels);
+  const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
   prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), st);
-  roi_align_cl_fwd_kernel<kClChannels, kVec, kMinCtas><<<R * chunks, cl_threads(outh), smem, st>>>(
+  roi_align_cl_fwd_kernel<kClChannels, kVec><<<R * groups, cl_threads(outh), smem, st>>>(
       reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
-      sampling_ratio, chunks, N);
+      sampling_ratio, groups, cpc, N);
   prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
 
-template <bool kVec, int kMinCtas>
+template <bool kVec>
 int launch_cl_bwd(const float* gy, const float* rois, int R, int N, int H, int W, int C, int outh,
                   int outw, float spatial_scale, int sampling_ratio, float* gx_nhwc,
                   cudaStream_t st) {
   const size_t smem = cl_smem_bytes(outh, outw);
-  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels, kVec, kMinCtas>, smem);
+  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels, kVec>, smem);
   if (rc != CMR_OK) return rc;
   prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), st);
   cudaError_t me = cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, st);
@@ -1089,9 +1082,10 @@ int launch_cl_bwd(const float* gy, const float* rois, int R, int N, int H, int W
     return CMR_OK;
   }
   const int chunks = ceil_div(C, kClChannels);
-  roi_align_cl_bwd_kernel<kClChannels, kVec, kMinCtas><<<R * chunks, cl_threads(outh), smem, st>>>(
+  const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
+  roi_align_cl_bwd_kernel<kClChannels, kVec><<<R * groups, cl_threads(outh), smem, st>>>(
       gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
-      sampling_ratio, chunks, N);
+      sampling_ratio, groups, cpc, N);
   prof_end(st);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
@@ -1108,11 +1102,11 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(x_nhwc && rois && y);
   cudaStream_t st = as_stream(stream);
-  const bool vec = cl_vec(outh, outw), three = cl_min_ctas() == 3;
-#define CMR_CL_ARGS x_nhwc, N, H, W, C, rois, R, outh, outw, spatial_scale, sampling_ratio, y, st
-  if (vec) return three ? launch_cl_fwd<true, 3>(CMR_CL_ARGS) : launch_cl_fwd<true, 2>(CMR_CL_ARGS);
-  return three ? launch_cl_fwd<false, 3>(CMR_CL_ARGS) : launch_cl_fwd<false, 2>(CMR_CL_ARGS);
-#undef CMR_CL_ARGS
+  if (cl_vec(outh, outw))
+    return launch_cl_fwd<true>(x_nhwc, N, H, W, C, rois, R, outh, outw, spatial_scale,
+                               sampling_ratio, y, st);
+  return launch_cl_fwd<false>(x_nhwc, N, H, W, C, rois, R, outh, outw, spatial_scale,
+                              sampling_ratio, y, st);
 }
 
 extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, int N, int H,
@@ -1123,11 +1117,11 @@ extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, i
   if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
   CMR_REQUIRE(R == 0 || (gy && rois));
   cudaStream_t st = as_stream(stream);
-  const bool vec = cl_vec(outh, outw), three = cl_min_ctas() == 3;
-#define CMR_CL_ARGS gy, rois, R, N, H, W, C, outh, outw, spatial_scale, sampling_ratio, gx_nhwc, st
-  if (vec) return three ? launch_cl_bwd<true, 3>(CMR_CL_ARGS) : launch_cl_bwd<true, 2>(CMR_CL_ARGS);
-  return three ? launch_cl_bwd<false, 3>(CMR_CL_ARGS) : launch_cl_bwd<false, 2>(CMR_CL_ARGS);
-#undef CMR_CL_ARGS
+  if (cl_vec(outh, outw))
+    return launch_cl_bwd<true>(gy, rois, R, N, H, W, C, outh, outw, spatial_scale,
+                               sampling_ratio, gx_nhwc, st);
+  return launch_cl_bwd<false>(gy, rois, R, N, H, W, C, outh, outw, spatial_scale,
+                              sampling_ratio, gx_nhwc, st);
 }
 
 extern "C" size_t cmr_roi_align_workspace_bytes(int N, int C, int H, int W) {
