@@ -873,6 +873,196 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------ two-pass form of the same operator --
+// The walkers above spend ~100 instructions per output float4 on window bookkeeping (ncu:
+// issue-bound, 0.6 IPC).  For the usual pooled sizes the bilinear sum is cheaper as two small
+// dense products through shared memory, both branch-free:
+//   pass A  G[c][ph][x] = sum_k wy[ph][k] * F[y0(ph) + k][xf + x][c]     (vertical blend of
+//           every footprint column, float4 loads over channel quads, merged row weights)
+//   pass B  out[c][ph][pw] = sum_j wx[pw][j] * G[c][ph][x0(pw) - xf + j]  (merged column
+//           weights, 1 / count folded in; lanes run over bins, so the (c, ph, pw) results of
+//           a chunk leave as full, contiguous float4 lines of the reference-layout tensor)
+// G is channel-major, so pass B needs no transposing tile; its size (channels x outh x
+// footprint columns) sets how many channels one round covers (64 for RoIs up to ~13 columns,
+// fewer for wide ones).  Same products as the reference, merged weights (a few ulp).
+constexpr int kBlendSlots = 8;
+constexpr int kTwoPassThreads = 256;
+constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA: four CTAs per SM
+
+struct AxisBlend {
+  int first;                // index of the first feature row / column
+  int n;                    // rows / columns spanned (0: every sample skipped)
+  float w[kBlendSlots];
+};
+
+// ab[i], i < count: merged taps of output index i along one axis.  *ok = 0 when an output
+// spans more than kBlendSlots rows / columns.
+__device__ __forceinline__ void build_axis_blends(AxisBlend* ab, int* ok, float start, float bin,
+                                                  int grid, int count, int limit, float wscale) {
+  for (int e = threadIdx.x; e < count * kBlendSlots; e += blockDim.x) {
+    const int i = e / kBlendSlots, k = e - i * kBlendSlots;
+    int lo = 1 << 30, hi = -1;
+    for (int s = 0; s < grid; ++s) {
+      const AxisTap t = axis_tap(start, bin, i, s, grid, limit);
+      if (!t.valid) continue;
+      lo = min(lo, t.low);
+      hi = max(hi, t.high);
+    }
+    const int idx = lo + k;
+    float w = 0.f;
+    if (hi >= 0 && idx <= hi) {
+      for (int s = 0; s < grid; ++s) {
+        const AxisTap t = axis_tap(start, bin, i, s, grid, limit);
+        if (!t.valid) continue;
+        if (t.low == idx) w += t.h;
+        if (t.high == idx) w += t.l;
+      }
+    }
+    ab[i].w[k] = w * wscale;
+    if (k == 0) {
+      ab[i].first = hi >= 0 ? lo : 0;
+      ab[i].n = hi >= 0 ? hi - lo + 1 : 0;
+      if (hi - lo + 1 > kBlendSlots) atomicExch(ok, 0);
+    }
+  }
+}
+
+struct TwoPassSmem {
+  int ok, xf, ncol, pad_;
+  AxisBlend rows[64];       // outh <= 64
+  AxisBlend cols[64];       // outw <= 64
+};
+
+template <int CH>
+__global__ void __launch_bounds__(kTwoPassThreads, 4)
+roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
+                         float* __restrict__ dst, int H, int W, int C, int outh, int outw,
+                         float scale, int sampling_ratio, int groups, int cpc, int n_img) {
+  extern __shared__ __align__(16) unsigned char roi_smem[];
+  TwoPassSmem* sm = reinterpret_cast<TwoPassSmem*>(roi_smem);
+  float* G = reinterpret_cast<float*>(roi_smem + sizeof(TwoPassSmem));
+  const int T = blockDim.x;
+  const int r = blockIdx.x / groups;
+  const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
+  const int c_end = min(C, c_begin + cpc * CH);
+  const int P = outh * outw, P4 = P >> 2;
+  const int C4 = C >> 2;
+  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
+  if (threadIdx.x == 0) sm->ok = 1;
+  __syncthreads();
+  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
+  build_axis_blends(sm->rows, &sm->ok, g.start_h, g.bin_h, g.grid_h, outh, H, 1.0f);
+  build_axis_blends(sm->cols, &sm->ok, g.start_w, g.bin_w, g.grid_w, outw, W, inv);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int xf = 1 << 30, xl = -1;
+    for (int pw = 0; pw < outw; ++pw) {
+      if (sm->cols[pw].n <= 0) continue;
+      xf = min(xf, sm->cols[pw].first);
+      xl = max(xl, sm->cols[pw].first + sm->cols[pw].n - 1);
+    }
+    sm->xf = xl >= 0 ? xf : 0;
+    sm->ncol = xl >= 0 ? xl - xf + 1 : 1;
+  }
+  __syncthreads();
+  const int xf = sm->xf, ncol = sm->ncol;
+  const int GS = (outh * ncol) | 1;            // odd plane stride: channels spread over banks
+  // channels per round: the largest power of two whose G planes fit
+  int che = CH;
+  while (che > 4 && che * GS > kTwoPassGFloats) che >>= 1;
+  const bool fits = sm->ok != 0 && che * GS <= kTwoPassGFloats;
+  float* out_roi = dst + (size_t)r * C * P;
+  if (!fits) {
+    // very wide / tall RoI: per-bin evaluation straight from the map (rare, correct, slow)
+    const int row_bytes = W * C4 * 16, px_bytes = C4 * 16;
+    for (int c4 = (c_begin >> 2) + threadIdx.x; c4 < (c_end >> 2); c4 += T) {
+      const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 + c4);
+      for (int p = 0; p < P; ++p) {
+        const float4 v = bin_fwd_generic(g, p / outw, p % outw, H, W, img, row_bytes, px_bytes, inv);
+        float* o = out_roi + (size_t)(4 * c4) * P + p;
+        o[0] = v.x; o[P] = v.y; o[2 * P] = v.z; o[3 * P] = v.w;
+      }
+    }
+    return;
+  }
+  int lq = 0;
+  while ((4 << lq) < che) ++lq;               // che = 4 << lq channels = 1 << lq quads
+  const int Qe = 1 << lq;
+  const int M = ncol * Qe;                     // pass A items per output row
+  // pass B: thread = (float4 group p4 of the plane, channel lane); its four bins' merged
+  // column taps live in registers for the whole CTA
+  const int nct = T / P4;                      // channel lanes (P4 <= T is a launch condition)
+  const int p4 = threadIdx.x % P4, cl = threadIdx.x / P4;
+  int goff[4], nx[4];
+  float wx[4][4];
+  bool narrow = true;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int p = 4 * p4 + e, ph = p / outw, pw = p - ph * outw;
+    const AxisBlend& cb = sm->cols[pw];
+    goff[e] = ph * ncol + cb.first - xf;
+    nx[e] = cb.n;
+    if (cb.n <= 0) goff[e] = 0;
+    narrow = narrow && cb.n <= 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wx[e][j] = j < cb.n ? cb.w[j] : 0.f;
+  }
+  const float4* img0 = src + (size_t)g.batch * H * W * C4;
+  for (int c0 = c_begin; c0 < c_end; c0 += che) {
+    const int nch = min(che, c_end - c0);
+    // ---- pass A
+    {
+      int ph = threadIdx.x / M, k = threadIdx.x - ph * M;
+      while (ph < outh) {
+        const AxisBlend& rbl = sm->rows[ph];
+        const int x = k >> lq, q = k & (Qe - 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (4 * q < nch) {
+          const float4* p = img0 + ((size_t)rbl.first * W + xf + x) * C4 + (c0 >> 2) + q;
+          const size_t rs = (size_t)W * C4;
+          int j = 0;
+          for (; j + 1 < rbl.n; j += 2, p += 2 * rs) {
+            const float4 v0 = __ldg(p), v1 = __ldg(p + rs);
+            fma4(acc, rbl.w[j], v0);
+            fma4(acc, rbl.w[j + 1], v1);
+          }
+          if (j < rbl.n) fma4(acc, rbl.w[j], __ldg(p));
+          float* gp = G + (size_t)(4 * q) * GS + ph * ncol + x;
+          gp[0] = acc.x; gp[GS] = acc.y; gp[2 * GS] = acc.z; gp[3 * GS] = acc.w;
+        }
+        k += T;
+        while (k >= M) { k -= M; ++ph; }
+      }
+    }
+    __syncthreads();
+    // ---- pass B
+    if (cl < nct) {
+      float4* outp = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P) + p4;
+      for (int c = cl; c < nch; c += nct) {
+        const float* Gc = G + (size_t)c * GS;
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a = 0.f;
+          const float* gp = Gc + goff[e];
+          if (narrow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nx[e]) a = fmaf(wx[e][j], gp[j], a);
+          } else {
+            const int p = 4 * p4 + e, pw = p % outw;
+            const AxisBlend& cb = sm->cols[pw];
+            for (int j = 0; j < cb.n; ++j) a = fmaf(cb.w[j], gp[j], a);
+          }
+          o[e] = a;
+        }
+        outp[(size_t)c * P4] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 constexpr int kClChannels = 64;   // channels per CTA of the two kernels above
 
 bool cl_vec(int outh, int outw) { return (outw & 1) == 0 && ((outh * outw) & 3) == 0; }
@@ -1049,6 +1239,19 @@ extern "C" int cmr_roi_align_cl_supported(int N, int C, int H, int W, int R, int
 }
 
 namespace {
+// The two-pass kernel needs whole float4 groups per plane that one CTA's threads can cover.
+// CMR_ROI_TWO_PASS=0 keeps the walker kernels (A/B measurements).
+bool two_pass_ok(int outh, int outw, const void* y) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CMR_ROI_TWO_PASS");
+    on = e ? atoi(e) != 0 : 1;
+  }
+  const int P = outh * outw;
+  return on && (P & 3) == 0 && (P >> 2) <= kTwoPassThreads && outh <= 64 && outw <= 64 &&
+         (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+}
+
 template <bool kVec>
 int launch_cl_fwd(const float* x_nhwc, int N, int H, int W, int C, const float* rois, int R,
                   int outh, int outw, float spatial_scale, int sampling_ratio, float* y,
@@ -1102,6 +1305,20 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   if (R == 0) return CMR_OK;
   CMR_REQUIRE(x_nhwc && rois && y);
   cudaStream_t st = as_stream(stream);
+  if (two_pass_ok(outh, outw, y)) {
+    const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * kTwoPassGFloats;
+    int rc = cl_configure(roi_align_cl2_fwd_kernel<kClChannels>, smem);
+    if (rc != CMR_OK) return rc;
+    const int chunks = ceil_div(C, kClChannels);
+    const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
+    prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), st);
+    roi_align_cl2_fwd_kernel<kClChannels><<<R * groups, kTwoPassThreads, smem, st>>>(
+        reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
+        sampling_ratio, groups, cpc, N);
+    prof_end(st);
+    CMR_LAUNCH_CHECK();
+    return CMR_OK;
+  }
   if (cl_vec(outh, outw))
     return launch_cl_fwd<true>(x_nhwc, N, H, W, C, rois, R, outh, outw, spatial_scale,
                                sampling_ratio, y, st);
