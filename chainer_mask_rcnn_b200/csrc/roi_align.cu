@@ -888,6 +888,7 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 constexpr int kBlendSlots = 8;
 constexpr int kTwoPassThreads = 256;
 constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA: four CTAs per SM
+constexpr int kTwoPassGSlack = 4;               // floats readable past the last plane
 
 struct AxisBlend {
   int first;                // index of the first feature row / column
@@ -928,55 +929,87 @@ __device__ __forceinline__ void build_axis_blends(AxisBlend* ab, int* ok, float 
 }
 
 struct TwoPassSmem {
-  int ok, xf, ncol, pad_;
-  AxisBlend rows[64];       // outh <= 64
+  int ok, xf, ncol, nx_max;
+  AxisBlend rows[64];       // outh <= 64; `first` is turned into a byte offset for pass A
   AxisBlend cols[64];       // outw <= 64
 };
 
+// Pass B for one thread: its float4 group (four bins) of every channel cl, cl + nct, ...
+// NT = taps per bin (the CTA's widest bin; narrower bins carry zero weights and read the
+// next floats of G, which exist: G has four floats of slack).
+template <int NT>
+__device__ __forceinline__ void two_pass_b(const float* __restrict__ g0, float4* __restrict__ op,
+                                           int nch, int cl, int nct, int GS, int P4,
+                                           const int (&goff)[4], const float (&wx)[4][4]) {
+  const float* ga = g0 + goff[0];
+  const float* gb = g0 + goff[1];
+  const float* gc = g0 + goff[2];
+  const float* gd = g0 + goff[3];
+  const int gstep = nct * GS, ostep = nct * P4;
+  for (int c = cl; c < nch; c += nct) {
+    float4 o;
+    o.x = wx[0][0] * ga[0]; o.y = wx[1][0] * gb[0]; o.z = wx[2][0] * gc[0]; o.w = wx[3][0] * gd[0];
+#pragma unroll
+    for (int j = 1; j < NT; ++j) {
+      o.x = fmaf(wx[0][j], ga[j], o.x);
+      o.y = fmaf(wx[1][j], gb[j], o.y);
+      o.z = fmaf(wx[2][j], gc[j], o.z);
+      o.w = fmaf(wx[3][j], gd[j], o.w);
+    }
+    *op = o;
+    ga += gstep; gb += gstep; gc += gstep; gd += gstep;
+    op += ostep;
+  }
+}
+
 template <int CH>
-__global__ void __launch_bounds__(kTwoPassThreads, 4)
+__global__ void __launch_bounds__(kTwoPassThreads, 3)
 roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                          float* __restrict__ dst, int H, int W, int C, int outh, int outw,
                          float scale, int sampling_ratio, int groups, int cpc, int n_img) {
   extern __shared__ __align__(16) unsigned char roi_smem[];
   TwoPassSmem* sm = reinterpret_cast<TwoPassSmem*>(roi_smem);
   float* G = reinterpret_cast<float*>(roi_smem + sizeof(TwoPassSmem));
-  const int T = blockDim.x;
+  const int T = blockDim.x, tid = threadIdx.x;
   const int r = blockIdx.x / groups;
   const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
   const int c_end = min(C, c_begin + cpc * CH);
   const int P = outh * outw, P4 = P >> 2;
   const int C4 = C >> 2;
+  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
   const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
-  if (threadIdx.x == 0) sm->ok = 1;
+  if (tid == 0) sm->ok = 1;
   __syncthreads();
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   build_axis_blends(sm->rows, &sm->ok, g.start_h, g.bin_h, g.grid_h, outh, H, 1.0f);
   build_axis_blends(sm->cols, &sm->ok, g.start_w, g.bin_w, g.grid_w, outw, W, inv);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int xf = 1 << 30, xl = -1;
+  if (tid == 0) {
+    int xf = 1 << 30, xl = -1, nxm = 1;
     for (int pw = 0; pw < outw; ++pw) {
       if (sm->cols[pw].n <= 0) continue;
       xf = min(xf, sm->cols[pw].first);
       xl = max(xl, sm->cols[pw].first + sm->cols[pw].n - 1);
+      nxm = max(nxm, sm->cols[pw].n);
     }
     sm->xf = xl >= 0 ? xf : 0;
     sm->ncol = xl >= 0 ? xl - xf + 1 : 1;
+    sm->nx_max = nxm;
   }
+  if (tid < outh) sm->rows[tid].first *= row_bytes;       // byte offset of the first row
   __syncthreads();
-  const int xf = sm->xf, ncol = sm->ncol;
+  const int xf = sm->xf, ncol = sm->ncol, nxm = sm->nx_max;
   const int GS = (outh * ncol) | 1;            // odd plane stride: channels spread over banks
   // channels per round: the largest power of two whose G planes fit
   int che = CH;
   while (che > 4 && che * GS > kTwoPassGFloats) che >>= 1;
   const bool fits = sm->ok != 0 && che * GS <= kTwoPassGFloats;
   float* out_roi = dst + (size_t)r * C * P;
+  const char* img_b = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4);
   if (!fits) {
     // very wide / tall RoI: per-bin evaluation straight from the map (rare, correct, slow)
-    const int row_bytes = W * C4 * 16, px_bytes = C4 * 16;
-    for (int c4 = (c_begin >> 2) + threadIdx.x; c4 < (c_end >> 2); c4 += T) {
-      const char* img = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4 + c4);
+    for (int c4 = (c_begin >> 2) + tid; c4 < (c_end >> 2); c4 += T) {
+      const char* img = img_b + (size_t)c4 * 16;
       for (int p = 0; p < P; ++p) {
         const float4 v = bin_fwd_generic(g, p / outw, p % outw, H, W, img, row_bytes, px_bytes, inv);
         float* o = out_roi + (size_t)(4 * c4) * P + p;
@@ -988,75 +1021,76 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   int lq = 0;
   while ((4 << lq) < che) ++lq;               // che = 4 << lq channels = 1 << lq quads
   const int Qe = 1 << lq;
-  const int M = ncol * Qe;                     // pass A items per output row
+  const int M = ncol * Qe;                     // (column, quad) pairs of one round
+  // pass A: a thread owns one (column, quad) pair and a stride of the output rows
+  const int nsplit = M <= T ? min(outh, T / M) : 1;
+  const int a_k0 = M <= T ? tid % M : tid, a_ph0 = M <= T ? tid / M : 0;
   // pass B: thread = (float4 group p4 of the plane, channel lane); its four bins' merged
-  // column taps live in registers for the whole CTA
+  // column taps (zero-padded to four) live in registers for the whole CTA
   const int nct = T / P4;                      // channel lanes (P4 <= T is a launch condition)
-  const int p4 = threadIdx.x % P4, cl = threadIdx.x / P4;
-  int goff[4], nx[4];
+  const int p4 = tid % P4, cl = tid / P4;
+  int goff[4];
   float wx[4][4];
-  bool narrow = true;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int p = 4 * p4 + e, ph = p / outw, pw = p - ph * outw;
     const AxisBlend& cb = sm->cols[pw];
-    goff[e] = ph * ncol + cb.first - xf;
-    nx[e] = cb.n;
-    if (cb.n <= 0) goff[e] = 0;
-    narrow = narrow && cb.n <= 4;
+    goff[e] = cb.n > 0 ? ph * ncol + cb.first - xf : 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) wx[e][j] = j < cb.n ? cb.w[j] : 0.f;
   }
-  const float4* img0 = src + (size_t)g.batch * H * W * C4;
   for (int c0 = c_begin; c0 < c_end; c0 += che) {
     const int nch = min(che, c_end - c0);
     // ---- pass A
-    {
-      int ph = threadIdx.x / M, k = threadIdx.x - ph * M;
-      while (ph < outh) {
-        const AxisBlend& rbl = sm->rows[ph];
+    if (a_ph0 < nsplit) {
+      for (int k = a_k0; k < M; k += T) {
         const int x = k >> lq, q = k & (Qe - 1);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (4 * q < nch) {
-          const float4* p = img0 + ((size_t)rbl.first * W + xf + x) * C4 + (c0 >> 2) + q;
-          const size_t rs = (size_t)W * C4;
+        if (4 * q >= nch) continue;
+        const char* col = img_b + ((size_t)(xf + x) * C4 + (c0 >> 2) + q) * 16;
+        float* gcol = G + (4 * q) * GS + x;
+        for (int ph = a_ph0; ph < outh; ph += nsplit) {
+          const AxisBlend& rbl = sm->rows[ph];
+          const int n = rbl.n;
+          const char* p = col + rbl.first;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           int j = 0;
-          for (; j + 1 < rbl.n; j += 2, p += 2 * rs) {
-            const float4 v0 = __ldg(p), v1 = __ldg(p + rs);
+          for (; j + 1 < n; j += 2, p += 2 * row_bytes) {
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + row_bytes));
             fma4(acc, rbl.w[j], v0);
             fma4(acc, rbl.w[j + 1], v1);
           }
-          if (j < rbl.n) fma4(acc, rbl.w[j], __ldg(p));
-          float* gp = G + (size_t)(4 * q) * GS + ph * ncol + x;
+          if (j < n) fma4(acc, rbl.w[j], __ldg(reinterpret_cast<const float4*>(p)));
+          float* gp = gcol + ph * ncol;
           gp[0] = acc.x; gp[GS] = acc.y; gp[2 * GS] = acc.z; gp[3 * GS] = acc.w;
         }
-        k += T;
-        while (k >= M) { k -= M; ++ph; }
       }
     }
     __syncthreads();
     // ---- pass B
     if (cl < nct) {
-      float4* outp = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P) + p4;
-      for (int c = cl; c < nch; c += nct) {
-        const float* Gc = G + (size_t)c * GS;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float a = 0.f;
-          const float* gp = Gc + goff[e];
-          if (narrow) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (j < nx[e]) a = fmaf(wx[e][j], gp[j], a);
-          } else {
-            const int p = 4 * p4 + e, pw = p % outw;
+      float4* op = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P) + (size_t)cl * P4 + p4;
+      const float* g0 = G + cl * GS;
+      if (nxm <= 2) {
+        two_pass_b<2>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+      } else if (nxm == 3) {
+        two_pass_b<3>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+      } else if (nxm == 4) {
+        two_pass_b<4>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+      } else {       // bins wider than four columns (explicit sampling_ratio on a small RoI)
+        for (int c = cl; c < nch; c += nct, op += nct * P4) {
+          const float* Gc = G + (size_t)c * GS;
+          float o[4];
+          for (int e = 0; e < 4; ++e) {
+            const int p = 4 * p4 + e, ph = p / outw, pw = p - ph * outw;
             const AxisBlend& cb = sm->cols[pw];
+            const float* gp = Gc + ph * ncol + cb.first - xf;
+            float a = 0.f;
             for (int j = 0; j < cb.n; ++j) a = fmaf(cb.w[j], gp[j], a);
+            o[e] = a;
           }
-          o[e] = a;
+          *op = make_float4(o[0], o[1], o[2], o[3]);
         }
-        outp[(size_t)c * P4] = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
     __syncthreads();
@@ -1306,7 +1340,7 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   CMR_REQUIRE(x_nhwc && rois && y);
   cudaStream_t st = as_stream(stream);
   if (two_pass_ok(outh, outw, y)) {
-    const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * kTwoPassGFloats;
+    const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * (kTwoPassGFloats + kTwoPassGSlack);
     int rc = cl_configure(roi_align_cl2_fwd_kernel<kClChannels>, smem);
     if (rc != CMR_OK) return rc;
     const int chunks = ceil_div(C, kClChannels);

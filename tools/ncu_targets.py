@@ -21,7 +21,7 @@ from chainer_mask_rcnn_b200.models import engine as E  # noqa: E402
 
 what = sys.argv[1] if len(sys.argv) > 1 else 'conv'
 if what not in ('conv1x1', 'wgrad1x1'):
-    what = what.rstrip('0123456789')      # 'roi2' = a second capture of target 'roi'
+    what = what.rstrip('0123456789').rstrip('_') if what[-1].isdigit() else what      # 'roi2' = a second capture of target 'roi'
 dev = 'cuda'
 x = E.round_tf32(torch.randn((1024, 7, 7, 512), device=dev))
 w = E.round_tf32(torch.randn((512, 3, 3, 512), device=dev) / 68.)
@@ -47,7 +47,15 @@ if what == 'roi_cl':
     xm = torch.from_numpy(rs.standard_normal((1, 1024, 50, 68)).astype(np.float32)).cuda()
     xm = xm.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
     rois = torch.from_numpy(synth.rois_xy(rs, 1000, 1, 800, 1088)).cuda()
+if what == 'roi_full':       # the channels-last kernels at the same shape as roi_cl
+    import synth
+    rs = np.random.RandomState(0)
+    featf = torch.from_numpy(rs.standard_normal((1, 50, 68, 1024)).astype(np.float32)).cuda()
+    rois = torch.from_numpy(synth.rois_xy(rs, 1000, 1, 800, 1088)).cuda()
 for _ in range(4):
+    if what == 'roi_full':
+        y = E.roi_align_nhwc(featf, rois, 14, 14, 1, 1. / 16, round_out=False)
+        E.roi_align_nhwc_bwd(y, rois, tuple(featf.shape), 14, 14, 1, 1. / 16)
     if what == 'roi_cl':
         y = functions.roi_align_2d(xm, rois, 14, 14, 1. / 16)
         y.backward(torch.ones_like(y))
