@@ -888,7 +888,8 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 constexpr int kBlendSlots = 8;
 constexpr int kTwoPassThreads = 256;
 constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA: four CTAs per SM
-constexpr int kTwoPassGSlack = 4;               // floats readable past the last plane
+constexpr int kTwoPassGSlack = 4;
+constexpr int kRowBatch = 3;                    // output rows whose loads are in flight together               // floats readable past the last plane
 
 struct AxisBlend {
   int first;                // index of the first feature row / column
@@ -999,10 +1000,24 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   if (tid < outh) sm->rows[tid].first *= row_bytes;       // byte offset of the first row
   __syncthreads();
   const int xf = sm->xf, ncol = sm->ncol, nxm = sm->nx_max;
-  const int GS = (outh * ncol) | 1;            // odd plane stride: channels spread over banks
-  // channels per round: the largest power of two whose G planes fit
-  int che = CH;
-  while (che > 4 && che * GS > kTwoPassGFloats) che >>= 1;
+  // One round = `che` channels x `rs` output rows of G.  Narrow RoIs take all rows and 64
+  // channels in one round; for wide ones the rows are cut first (8, then 4 rows: whole float4
+  // groups and whole 32-byte sectors of every plane), the channels only after that.
+  int rs = outh, che = CH;
+  {
+    const int cand[3] = {outh, 8, 4};
+    bool found = false;
+    for (int i = 0; i < 3 && !found; ++i) {
+      const int c = cand[i];
+      if (c > outh || (i > 0 && (c >= outh || ((c * outw) & 3) || (((outh % c) * outw) & 3)))) continue;
+      if (CH * ((c * ncol) | 1) <= kTwoPassGFloats) { rs = c; found = true; }
+    }
+    if (!found) {
+      rs = (outh > 4 && ((4 * outw) & 3) == 0 && (((outh % 4) * outw) & 3) == 0) ? 4 : outh;
+      while (che > 4 && che * ((rs * ncol) | 1) > kTwoPassGFloats) che >>= 1;
+    }
+  }
+  const int GS = (rs * ncol) | 1;              // odd plane stride: channels spread over banks
   const bool fits = sm->ok != 0 && che * GS <= kTwoPassGFloats;
   float* out_roi = dst + (size_t)r * C * P;
   const char* img_b = reinterpret_cast<const char*>(src + (size_t)g.batch * H * W * C4);
@@ -1018,82 +1033,105 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
     }
     return;
   }
+  // pass B reads up to three floats past a bin's last tap (zero weights): every float of G
+  // must be finite, so the planes start as zeros (once per CTA)
+  for (int i = tid; i < (kTwoPassGFloats + kTwoPassGSlack) / 4; i += T)
+    reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   int lq = 0;
   while ((4 << lq) < che) ++lq;               // che = 4 << lq channels = 1 << lq quads
   const int Qe = 1 << lq;
   const int M = ncol * Qe;                     // (column, quad) pairs of one round
-  // pass A: a thread owns one (column, quad) pair and a stride of the output rows
-  const int nsplit = M <= T ? min(outh, T / M) : 1;
+  // pass A: a thread owns one (column, quad) pair and a stride of the round's output rows
+  const int nsplit = M <= T ? min(rs, T / M) : 1;
   const int a_k0 = M <= T ? tid % M : tid, a_ph0 = M <= T ? tid / M : 0;
-  // pass B: thread = (float4 group p4 of the plane, channel lane); its four bins' merged
-  // column taps (zero-padded to four) live in registers for the whole CTA
-  const int nct = T / P4;                      // channel lanes (P4 <= T is a launch condition)
-  const int p4 = tid % P4, cl = tid / P4;
-  int goff[4];
-  float wx[4][4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int p = 4 * p4 + e, ph = p / outw, pw = p - ph * outw;
-    const AxisBlend& cb = sm->cols[pw];
-    goff[e] = cb.n > 0 ? ph * ncol + cb.first - xf : 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) wx[e][j] = j < cb.n ? cb.w[j] : 0.f;
-  }
+  __syncthreads();                             // G is zero before pass A writes it
   for (int c0 = c_begin; c0 < c_end; c0 += che) {
     const int nch = min(che, c_end - c0);
-    // ---- pass A
-    if (a_ph0 < nsplit) {
-      for (int k = a_k0; k < M; k += T) {
-        const int x = k >> lq, q = k & (Qe - 1);
-        if (4 * q >= nch) continue;
-        const char* col = img_b + ((size_t)(xf + x) * C4 + (c0 >> 2) + q) * 16;
-        float* gcol = G + (4 * q) * GS + x;
-        for (int ph = a_ph0; ph < outh; ph += nsplit) {
-          const AxisBlend& rbl = sm->rows[ph];
-          const int n = rbl.n;
-          const char* p = col + rbl.first;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          int j = 0;
-          for (; j + 1 < n; j += 2, p += 2 * row_bytes) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(p));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(p + row_bytes));
-            fma4(acc, rbl.w[j], v0);
-            fma4(acc, rbl.w[j + 1], v1);
+    for (int pb = 0; pb < outh; pb += rs) {    // the round's rows [pb, pe)
+      const int pe = min(outh, pb + rs);
+      // ---- pass A: kRowBatch output rows per batch, every load of the batch issued before
+      // the first use (the row loop is otherwise one L2 round trip per row: latency-bound)
+      if (a_ph0 < nsplit) {
+        for (int k = a_k0; k < M; k += T) {
+          const int x = k >> lq, q = k & (Qe - 1);
+          if (4 * q >= nch) continue;
+          const char* col = img_b + ((size_t)(xf + x) * C4 + (c0 >> 2) + q) * 16;
+          float* gcol = G + (4 * q) * GS + x - pb * ncol;
+          for (int ph = pb + a_ph0; ph < pe; ph += kRowBatch * nsplit) {
+            float4 v[kRowBatch][3];
+            int nn[kRowBatch];
+#pragma unroll
+            for (int u = 0; u < kRowBatch; ++u) {
+              const int phu = ph + u * nsplit;
+              nn[u] = phu < pe ? sm->rows[phu].n : -1;
+              const char* p = col + sm->rows[phu < pe ? phu : ph].first;
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                if (j < nn[u]) v[u][j] = __ldg(reinterpret_cast<const float4*>(p + j * row_bytes));
+            }
+#pragma unroll
+            for (int u = 0; u < kRowBatch; ++u) {
+              if (nn[u] < 0) continue;
+              const int phu = ph + u * nsplit;
+              const AxisBlend& rbl = sm->rows[phu];
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                if (j < nn[u]) fma4(acc, rbl.w[j], v[u][j]);
+              for (int j = 3; j < nn[u]; ++j)
+                fma4(acc, rbl.w[j],
+                     __ldg(reinterpret_cast<const float4*>(col + rbl.first + j * row_bytes)));
+              float* gp = gcol + phu * ncol;
+              gp[0] = acc.x; gp[GS] = acc.y; gp[2 * GS] = acc.z; gp[3 * GS] = acc.w;
+            }
           }
-          if (j < n) fma4(acc, rbl.w[j], __ldg(reinterpret_cast<const float4*>(p)));
-          float* gp = gcol + ph * ncol;
-          gp[0] = acc.x; gp[GS] = acc.y; gp[2 * GS] = acc.z; gp[3 * GS] = acc.w;
         }
       }
-    }
-    __syncthreads();
-    // ---- pass B
-    if (cl < nct) {
-      float4* op = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P) + (size_t)cl * P4 + p4;
-      const float* g0 = G + cl * GS;
-      if (nxm <= 2) {
-        two_pass_b<2>(g0, op, nch, cl, nct, GS, P4, goff, wx);
-      } else if (nxm == 3) {
-        two_pass_b<3>(g0, op, nch, cl, nct, GS, P4, goff, wx);
-      } else if (nxm == 4) {
-        two_pass_b<4>(g0, op, nch, cl, nct, GS, P4, goff, wx);
-      } else {       // bins wider than four columns (explicit sampling_ratio on a small RoI)
-        for (int c = cl; c < nch; c += nct, op += nct * P4) {
-          const float* Gc = G + (size_t)c * GS;
-          float o[4];
-          for (int e = 0; e < 4; ++e) {
-            const int p = 4 * p4 + e, ph = p / outw, pw = p - ph * outw;
-            const AxisBlend& cb = sm->cols[pw];
-            const float* gp = Gc + ph * ncol + cb.first - xf;
-            float a = 0.f;
-            for (int j = 0; j < cb.n; ++j) a = fmaf(cb.w[j], gp[j], a);
-            o[e] = a;
+      __syncthreads();
+      // ---- pass B: thread = (float4 group of the round's bins, channel lane)
+      const int P4r = ((pe - pb) * outw) >> 2;
+      const int nct = T / P4r;                 // channel lanes (P4r <= P4 <= T)
+      const int p4 = tid % P4r, cl = tid / P4r;
+      if (cl < nct) {
+        // the four bins' merged column taps, zero-padded to four (re-read per round so that
+        // they do not occupy registers during pass A)
+        int goff[4];
+        float wx[4][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int pl = 4 * p4 + e, phl = pl / outw, pw = pl - phl * outw;
+          const AxisBlend& cb = sm->cols[pw];
+          goff[e] = cb.n > 0 ? phl * ncol + cb.first - xf : 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wx[e][j] = j < cb.n ? cb.w[j] : 0.f;
+        }
+        float4* op = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P + (size_t)pb * outw) +
+                     (size_t)cl * P4 + p4;
+        const float* g0 = G + cl * GS;
+        if (nxm <= 2) {
+          two_pass_b<2>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+        } else if (nxm == 3) {
+          two_pass_b<3>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+        } else if (nxm == 4) {
+          two_pass_b<4>(g0, op, nch, cl, nct, GS, P4, goff, wx);
+        } else {     // bins wider than four columns (explicit sampling_ratio on a small RoI)
+          for (int c = cl; c < nch; c += nct, op += nct * P4) {
+            const float* Gc = G + (size_t)c * GS;
+            float o[4];
+            for (int e = 0; e < 4; ++e) {
+              const int pl = 4 * p4 + e, phl = pl / outw, pw = pl - phl * outw;
+              const AxisBlend& cb = sm->cols[pw];
+              const float* gp = Gc + phl * ncol + cb.first - xf;
+              float a = 0.f;
+              for (int j = 0; j < cb.n; ++j) a = fmaf(cb.w[j], gp[j], a);
+              o[e] = a;
+            }
+            *op = make_float4(o[0], o[1], o[2], o[3]);
           }
-          *op = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
