@@ -887,7 +887,7 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 // fewer for wide ones).  Same products as the reference, merged weights (a few ulp).
 constexpr int kBlendSlots = 8;
 constexpr int kTwoPassThreads = 256;
-constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA: four CTAs per SM
+constexpr int kTwoPassGFloats = 10 * 1024;      // 40 KB of G per CTA
 constexpr int kTwoPassGSlack = 4;
 constexpr int kRowBatch = 3;                    // output rows whose loads are in flight together               // floats readable past the last plane
 
@@ -928,6 +928,12 @@ __device__ __forceinline__ void build_axis_blends(AxisBlend* ab, int* ok, float 
     }
   }
 }
+
+struct BinTaps {            // pass B's view of one bin: where its taps start in a G plane
+  int goff;                 // ph * ncol + x0(pw) - xf
+  int pad_[3];
+  float w[4];               // merged column weights x 1 / count, zero-padded
+};
 
 struct TwoPassSmem {
   int ok, xf, ncol, nx_max;
@@ -971,6 +977,7 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   extern __shared__ __align__(16) unsigned char roi_smem[];
   TwoPassSmem* sm = reinterpret_cast<TwoPassSmem*>(roi_smem);
   float* G = reinterpret_cast<float*>(roi_smem + sizeof(TwoPassSmem));
+  BinTaps* bins = reinterpret_cast<BinTaps*>(G + kTwoPassGFloats + kTwoPassGSlack);   // [P]
   const int T = blockDim.x, tid = threadIdx.x;
   const int r = blockIdx.x / groups;
   const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
@@ -1037,6 +1044,12 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   // must be finite, so the planes start as zeros (once per CTA)
   for (int i = tid; i < (kTwoPassGFloats + kTwoPassGSlack) / 4; i += T)
     reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = tid; p < P; p += T) {           // per-bin tap table of pass B
+    const int ph = p / outw, pw = p - ph * outw;
+    const AxisBlend& cb = sm->cols[pw];
+    bins[p].goff = cb.n > 0 ? ph * ncol + cb.first - xf : ph * ncol;
+    for (int j = 0; j < 4; ++j) bins[p].w[j] = j < cb.n ? cb.w[j] : 0.f;
+  }
   int lq = 0;
   while ((4 << lq) < che) ++lq;               // che = 4 << lq channels = 1 << lq quads
   const int Qe = 1 << lq;
@@ -1099,11 +1112,10 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
         float wx[4][4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int pl = 4 * p4 + e, phl = pl / outw, pw = pl - phl * outw;
-          const AxisBlend& cb = sm->cols[pw];
-          goff[e] = cb.n > 0 ? phl * ncol + cb.first - xf : 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) wx[e][j] = j < cb.n ? cb.w[j] : 0.f;
+          const BinTaps& bt = bins[pb * outw + 4 * p4 + e];
+          goff[e] = bt.goff - pb * ncol;
+          const float4 w4 = *reinterpret_cast<const float4*>(bt.w);
+          wx[e][0] = w4.x; wx[e][1] = w4.y; wx[e][2] = w4.z; wx[e][3] = w4.w;
         }
         float4* op = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P + (size_t)pb * outw) +
                      (size_t)cl * P4 + p4;
@@ -1127,201 +1139,6 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
               o[e] = a;
             }
             *op = make_float4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// Backward of the two-pass form, both passes transposed:
-//   pass B'  Hx[c][ph][x] = sum over the bins pw whose taps touch column x of
-//            wx[pw][x - x0(pw)] * gy[c][ph][pw]        (lanes over (ph, x): gy is read in its
-//            reference layout, a column's bins are consecutive, so its taps are contiguous)
-//   pass A'  gx[y][x][c] += sum over the output rows ph whose taps touch feature row y of
-//            wy[ph][y - y0(ph)] * Hx[c][ph][x]         (one vector reduction per feature
-//            pixel and channel quad: the walkers issue one per (output row, tap), ~2.5x more)
-constexpr int kMaxSpan = 256;     // footprint rows / columns the tables hold
-
-struct TwoPassBwdSmem {
-  int ok, xf, ncol, yf, nrow, pad_[3];
-  AxisBlend rows[64];
-  AxisBlend cols[64];
-  int2 col_bins[kMaxSpan];        // per footprint column: first bin, bin count
-  int2 row_bins[kMaxSpan];        // per footprint row: first output row, row count
-};
-
-// bins[i] = {first, count} of the (consecutive) outputs whose merged taps cover index
-// first_index + i.
-__device__ __forceinline__ void build_cover(int2* bins, const AxisBlend* ab, int count, int base,
-                                            int span) {
-  for (int i = threadIdx.x; i < span; i += blockDim.x) {
-    const int idx = base + i;
-    int lo = 1 << 30, hi = -1;
-    for (int o = 0; o < count; ++o) {
-      if (ab[o].n > 0 && ab[o].first <= idx && idx < ab[o].first + ab[o].n) {
-        lo = min(lo, o);
-        hi = max(hi, o);
-      }
-    }
-    bins[i] = hi >= 0 ? make_int2(lo, hi - lo + 1) : make_int2(0, 0);
-  }
-}
-
-template <int CH>
-__global__ void __launch_bounds__(kTwoPassThreads, 3)
-roi_align_cl2_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
-                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
-                         float scale, int sampling_ratio, int groups, int cpc, int n_img) {
-  extern __shared__ __align__(16) unsigned char roi_smem[];
-  TwoPassBwdSmem* sm = reinterpret_cast<TwoPassBwdSmem*>(roi_smem);
-  float* Hx = reinterpret_cast<float*>(roi_smem + sizeof(TwoPassBwdSmem));
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int r = blockIdx.x / groups;
-  const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
-  const int c_end = min(C, c_begin + cpc * CH);
-  const int P = outh * outw;
-  const int C4 = C >> 2;
-  const int px_bytes = C4 * 16, row_bytes = W * px_bytes;
-  const RoiGeom g = roi_geometry(rois + (size_t)r * 5, scale, outh, outw, sampling_ratio, n_img);
-  if (tid == 0) sm->ok = 1;
-  __syncthreads();
-  const float inv = __fdiv_rn(1.0f, g.inv_count_den);
-  build_axis_blends(sm->rows, &sm->ok, g.start_h, g.bin_h, g.grid_h, outh, H, 1.0f);
-  build_axis_blends(sm->cols, &sm->ok, g.start_w, g.bin_w, g.grid_w, outw, W, inv);
-  __syncthreads();
-  if (tid == 0) {
-    int xf = 1 << 30, xl = -1, yf = 1 << 30, yl = -1;
-    for (int pw = 0; pw < outw; ++pw) {
-      if (sm->cols[pw].n <= 0) continue;
-      xf = min(xf, sm->cols[pw].first);
-      xl = max(xl, sm->cols[pw].first + sm->cols[pw].n - 1);
-    }
-    for (int ph = 0; ph < outh; ++ph) {
-      if (sm->rows[ph].n <= 0) continue;
-      yf = min(yf, sm->rows[ph].first);
-      yl = max(yl, sm->rows[ph].first + sm->rows[ph].n - 1);
-    }
-    sm->xf = xl >= 0 ? xf : 0;
-    sm->ncol = xl >= 0 ? xl - xf + 1 : 0;
-    sm->yf = yl >= 0 ? yf : 0;
-    sm->nrow = yl >= 0 ? yl - yf + 1 : 0;
-  }
-  __syncthreads();
-  const int xf = sm->xf, ncol = sm->ncol, yf = sm->yf, nrow = sm->nrow;
-  if (ncol == 0 || nrow == 0) return;           // every sample skipped: no gradient
-  const float* gy_roi = gy + (size_t)r * C * P;
-  char* img_b = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4);
-  // rows per round first, channels second (as in the forward kernel)
-  int rs = outh, che = CH;
-  {
-    const int cand[3] = {outh, 8, 4};
-    bool found = false;
-    for (int i = 0; i < 3 && !found; ++i) {
-      const int c = cand[i];
-      if (c > outh || (i > 0 && c >= outh)) continue;
-      if (CH * ((c * ncol) | 1) <= kTwoPassGFloats) { rs = c; found = true; }
-    }
-    if (!found) {
-      rs = outh > 4 ? 4 : outh;
-      while (che > 4 && che * ((rs * ncol) | 1) > kTwoPassGFloats) che >>= 1;
-    }
-  }
-  const int GS = (rs * ncol) | 1;
-  const bool fits = sm->ok != 0 && che * GS <= kTwoPassGFloats && ncol <= kMaxSpan &&
-                    nrow <= kMaxSpan;
-  if (!fits) {
-    // very wide / tall RoI: per-bin scatter (rare, correct, slow)
-    for (int c4 = (c_begin >> 2) + tid; c4 < (c_end >> 2); c4 += T) {
-      char* img = img_b + (size_t)c4 * 16;
-      const float* gp = gy_roi + (size_t)(4 * c4) * P;
-      for (int p = 0; p < P; ++p)
-        bin_bwd_generic(g, p / outw, p % outw, H, W, img, row_bytes, px_bytes, inv,
-                        make_float4(gp[p], gp[P + p], gp[2 * P + p], gp[3 * P + p]));
-    }
-    return;
-  }
-  build_cover(sm->col_bins, sm->cols, outw, xf, ncol);
-  build_cover(sm->row_bins, sm->rows, outh, yf, nrow);
-  int lq = 0;
-  while ((4 << lq) < che) ++lq;
-  const int Qe = 1 << lq;
-  const int M = ncol * Qe;                     // (column, quad) pairs of one round
-  __syncthreads();
-  for (int c0 = c_begin; c0 < c_end; c0 += che) {
-    const int nch = min(che, c_end - c0);
-    for (int pb = 0; pb < outh; pb += rs) {    // the round's output rows [pb, pe)
-      const int pe = min(outh, pb + rs);
-      // ---- pass B': Hx[c][ph - pb][x]
-      const int items = (pe - pb) * ncol;
-      const int nct = items <= T ? T / items : 1;
-      for (int it = items <= T ? tid % items : tid, cl = items <= T ? tid / items : 0;
-           it < items && cl < nct; it += T) {
-        const int phl = it / ncol, x = it - phl * ncol;
-        const int2 cb = sm->col_bins[x];
-        const float* gp0 = gy_roi + (size_t)c0 * P + (pb + phl) * outw + cb.x;
-        float* hp = Hx + it;
-        if (cb.y <= 4) {
-          float w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const AxisBlend& a = sm->cols[min(cb.x + t, outw - 1)];
-            w[t] = t < cb.y ? a.w[xf + x - a.first] : 0.f;
-          }
-          for (int c = cl; c < nch; c += nct) {
-            const float* gp = gp0 + (size_t)c * P;
-            float a = 0.f;
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (t < cb.y) a = fmaf(w[t], __ldg(gp + t), a);
-            hp[(size_t)c * GS] = a;
-          }
-        } else {
-          for (int c = cl; c < nch; c += nct) {
-            const float* gp = gp0 + (size_t)c * P;
-            float a = 0.f;
-            for (int t = 0; t < cb.y; ++t) {
-              const AxisBlend& ab = sm->cols[cb.x + t];
-              a = fmaf(ab.w[xf + x - ab.first], __ldg(gp + t), a);
-            }
-            hp[(size_t)c * GS] = a;
-          }
-        }
-      }
-      __syncthreads();
-      // ---- pass A': feature rows touched by the round's output rows, one vector reduction
-      // per (row, column, quad)
-      int yb = nrow, ye = -1;                  // footprint rows [yb, ye] of this round
-      for (int ph = pb; ph < pe; ++ph) {
-        const AxisBlend& a = sm->rows[ph];
-        if (a.n <= 0) continue;
-        yb = min(yb, a.first - yf);
-        ye = max(ye, a.first + a.n - 1 - yf);
-      }
-      const int nsplit = M <= T ? max(1, min(ye - yb + 1, T / M)) : 1;
-      const int a_k0 = M <= T ? tid % M : tid, a_y0 = M <= T ? tid / M : 0;
-      if (a_y0 < nsplit) {
-        for (int k = a_k0; k < M; k += T) {
-          const int x = k >> lq, q = k & (Qe - 1);
-          if (4 * q >= nch) continue;
-          char* col = img_b + ((size_t)(xf + x) * C4 + (c0 >> 2) + q) * 16;
-          const float* hcol = Hx + (4 * q) * GS + x - pb * ncol;
-          for (int y = yb + a_y0; y <= ye; y += nsplit) {
-            const int2 rbn = sm->row_bins[y];
-            const int lo = max(rbn.x, pb), hi = min(rbn.x + rbn.y, pe);
-            if (lo >= hi) continue;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int ph = lo; ph < hi; ++ph) {
-              const AxisBlend& a = sm->rows[ph];
-              const float w = a.w[yf + y - a.first];
-              const float* hp = hcol + ph * ncol;
-              acc.x = fmaf(w, hp[0], acc.x);
-              acc.y = fmaf(w, hp[GS], acc.y);
-              acc.z = fmaf(w, hp[2 * GS], acc.z);
-              acc.w = fmaf(w, hp[3 * GS], acc.w);
-            }
-            red_add_f4(reinterpret_cast<float4*>(col + (size_t)(yf + y) * row_bytes), acc);
           }
         }
       }
@@ -1573,7 +1390,8 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   CMR_REQUIRE(x_nhwc && rois && y);
   cudaStream_t st = as_stream(stream);
   if (two_pass_ok(outh, outw, y)) {
-    const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * (kTwoPassGFloats + kTwoPassGSlack);
+    const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * (kTwoPassGFloats + kTwoPassGSlack) +
+                        sizeof(BinTaps) * (size_t)(outh * outw);
     int rc = cl_configure(roi_align_cl2_fwd_kernel<kClChannels>, smem);
     if (rc != CMR_OK) return rc;
     const int chunks = ceil_div(C, kClChannels);
@@ -1601,26 +1419,6 @@ extern "C" int cmr_roi_align_bwd_cl(const float* gy, const float* rois, int R, i
   if (!cl_supported(N, C, H, W, R, outh, outw)) return CMR_ERR_UNSUPPORTED;
   CMR_REQUIRE(R == 0 || (gy && rois));
   cudaStream_t st = as_stream(stream);
-  if (two_pass_ok(outh, outw, gy)) {
-    const size_t smem = sizeof(TwoPassBwdSmem) + sizeof(float) * (kTwoPassGFloats + kTwoPassGSlack);
-    int rc = cl_configure(roi_align_cl2_bwd_kernel<kClChannels>, smem);
-    if (rc != CMR_OK) return rc;
-    prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), st);
-    cudaError_t me = cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, st);
-    if (me != cudaSuccess || R == 0) {
-      prof_end(st);
-      CMR_CUDA_TRY(me);
-      return CMR_OK;
-    }
-    const int chunks = ceil_div(C, kClChannels);
-    const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
-    roi_align_cl2_bwd_kernel<kClChannels><<<R * groups, kTwoPassThreads, smem, st>>>(
-        gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
-        sampling_ratio, groups, cpc, N);
-    prof_end(st);
-    CMR_LAUNCH_CHECK();
-    return CMR_OK;
-  }
   if (cl_vec(outh, outw))
     return launch_cl_bwd<true>(gy, rois, R, N, H, W, C, outh, outw, spatial_scale,
                                sampling_ratio, gx_nhwc, st);
