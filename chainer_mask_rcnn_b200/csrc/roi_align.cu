@@ -887,7 +887,7 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 // fewer for wide ones).  Same products as the reference, merged weights (a few ulp).
 constexpr int kBlendSlots = 8;
 constexpr int kTwoPassThreads = 256;
-constexpr int kTwoPassGFloats = 10 * 1024;      // 40 KB of G per CTA
+constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA; the rest of the SM's 256 KB stays L1 (pass A re-reads rows)
 constexpr int kTwoPassGSlack = 4;
 constexpr int kRowBatch = 3;                    // output rows whose loads are in flight together               // floats readable past the last plane
 
@@ -929,11 +929,10 @@ __device__ __forceinline__ void build_axis_blends(AxisBlend* ab, int* ok, float 
   }
 }
 
-struct BinTaps {            // pass B's view of one bin: where its taps start in a G plane
-  int goff;                 // ph * ncol + x0(pw) - xf
-  int pad_[3];
-  float w[4];               // merged column weights x 1 / count, zero-padded
-};
+// Pass B's view of one float4 group of bins (p = 4 * p4 + e), laid out so that consecutive
+// threads read consecutive 16-byte words: where each bin's taps start in a G plane, and the
+// j-th merged column weight (x 1 / count, zero-padded to four taps) of each bin: bin_goff[P/4]
+// (int4) and bin_w[4][P/4] (float4) behind G in the dynamic shared memory.
 
 struct TwoPassSmem {
   int ok, xf, ncol, nx_max;
@@ -977,7 +976,8 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   extern __shared__ __align__(16) unsigned char roi_smem[];
   TwoPassSmem* sm = reinterpret_cast<TwoPassSmem*>(roi_smem);
   float* G = reinterpret_cast<float*>(roi_smem + sizeof(TwoPassSmem));
-  BinTaps* bins = reinterpret_cast<BinTaps*>(G + kTwoPassGFloats + kTwoPassGSlack);   // [P]
+  int4* bin_goff = reinterpret_cast<int4*>(G + kTwoPassGFloats + kTwoPassGSlack);     // [P / 4]
+  float4* bin_w = reinterpret_cast<float4*>(bin_goff + ((outh * outw) >> 2));          // [4][P / 4]
   const int T = blockDim.x, tid = threadIdx.x;
   const int r = blockIdx.x / groups;
   const int c_begin = (blockIdx.x - r * groups) * cpc * CH;
@@ -1044,11 +1044,12 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
   // must be finite, so the planes start as zeros (once per CTA)
   for (int i = tid; i < (kTwoPassGFloats + kTwoPassGSlack) / 4; i += T)
     reinterpret_cast<float4*>(G)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = tid; p < P; p += T) {           // per-bin tap table of pass B
+  for (int p = tid; p < P; p += T) {           // per-bin tap tables of pass B
     const int ph = p / outw, pw = p - ph * outw;
     const AxisBlend& cb = sm->cols[pw];
-    bins[p].goff = cb.n > 0 ? ph * ncol + cb.first - xf : ph * ncol;
-    for (int j = 0; j < 4; ++j) bins[p].w[j] = j < cb.n ? cb.w[j] : 0.f;
+    reinterpret_cast<int*>(bin_goff)[p] = cb.n > 0 ? ph * ncol + cb.first - xf : ph * ncol;
+    for (int j = 0; j < 4; ++j)
+      reinterpret_cast<float*>(bin_w + j * P4)[p] = j < cb.n ? cb.w[j] : 0.f;
   }
   int lq = 0;
   while ((4 << lq) < che) ++lq;               // che = 4 << lq channels = 1 << lq quads
@@ -1110,12 +1111,16 @@ roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict
         // they do not occupy registers during pass A)
         int goff[4];
         float wx[4][4];
+        {
+          const int g4 = ((pb * outw) >> 2) + p4;
+          const int4 go = bin_goff[g4];
+          goff[0] = go.x - pb * ncol; goff[1] = go.y - pb * ncol;
+          goff[2] = go.z - pb * ncol; goff[3] = go.w - pb * ncol;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const BinTaps& bt = bins[pb * outw + 4 * p4 + e];
-          goff[e] = bt.goff - pb * ncol;
-          const float4 w4 = *reinterpret_cast<const float4*>(bt.w);
-          wx[e][0] = w4.x; wx[e][1] = w4.y; wx[e][2] = w4.z; wx[e][3] = w4.w;
+          for (int j = 0; j < 4; ++j) {
+            const float4 w4 = bin_w[j * P4 + g4];
+            wx[0][j] = w4.x; wx[1][j] = w4.y; wx[2][j] = w4.z; wx[3][j] = w4.w;
+          }
         }
         float4* op = reinterpret_cast<float4*>(out_roi + (size_t)c0 * P + (size_t)pb * outw) +
                      (size_t)cl * P4 + p4;
@@ -1391,7 +1396,7 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
   cudaStream_t st = as_stream(stream);
   if (two_pass_ok(outh, outw, y)) {
     const size_t smem = sizeof(TwoPassSmem) + sizeof(float) * (kTwoPassGFloats + kTwoPassGSlack) +
-                        sizeof(BinTaps) * (size_t)(outh * outw);
+                        20 * (size_t)(outh * outw);      // bin_goff + 4 weights per bin
     int rc = cl_configure(roi_align_cl2_fwd_kernel<kClChannels>, smem);
     if (rc != CMR_OK) return rc;
     const int chunks = ceil_div(C, kClChannels);
