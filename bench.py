@@ -385,7 +385,10 @@ def run_train(args, rank, world, local):
     model = models.MaskRCNNResNet(args.layers, N_FG, anchor_scales=(2, 4, 8, 16, 32), roi_size=14,
                                   min_size=800, max_size=1333, seed=0)
     chain = models.MaskRCNNTrainChain(model)
-    opt = optimizers.MomentumSGD(lr=0.00125 * BS * world, momentum=0.9)
+    # the reference's rule, examples/train_common.py:124-125: lr = 0.00125 x global batch
+    # (CMR_BENCH_LR overrides it: a knob for checking one GPU at the 8-GPU learning rate)
+    lr = float(os.environ.get('CMR_BENCH_LR', 0.00125 * BS * world))
+    opt = optimizers.MomentumSGD(lr=lr, momentum=0.9)
     if world > 1:
         opt = optimizers.create_multi_node_optimizer(opt, optimizers.create_communicator())
     opt.setup(chain)
@@ -522,6 +525,8 @@ def run_train(args, rank, world, local):
             'gpu_launches': int(launches.item()),
             'clocks': clk,
             'loss_first': float(losses[0].item()), 'loss_last': float(losses[-1].item()),
+            'loss_finite': bool(np.isfinite(float(losses[0].item())) and
+                                np.isfinite(float(losses[-1].item()))),
             'host_wall_ms_per_step': wall_total / args.steps,
         }
         if sustained:

@@ -239,6 +239,7 @@ class MaskRCNNResNet(MaskRCNN):
                                'CPU fallback')
         device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.ctx = ctx = Context()
+        self._n_layers = n_layers
         b = base_channels
         extractor = ResNetExtractorBase(ctx, n_layers, base=b)
         rpn = RegionProposalNetwork(ctx, 16 * b, rpn_hidden * b // 64, ratios=ratios,
@@ -320,9 +321,13 @@ class MaskRCNNResNet(MaskRCNN):
             if leaf[-1] == 'b' and not leaf[-2].startswith('bn'):
                 v.zero_()
             elif leaf[-2].startswith('bn'):
-                # slope 0.5 on the two affines feeding each residual sum keeps the
-                # activations O(1) through the 16 blocks of a randomly initialised net
-                gain = 0.5 if leaf[-2] in ('bn3', 'bn4') else 1.0
+                # a slope below one on the two affines feeding each residual sum keeps the
+                # activations O(1) through a randomly initialised net: the variance grows by
+                # (1 + slope^2) per block -- 0.5 for the 16 blocks of R50, 0.3 for the 33 of
+                # R101 (with 0.5 the R101 losses start at ~30 and the reference's learning
+                # rate for 16 images, 0.02, overflows within a few hundred steps)
+                slope = 0.5 if self._n_layers == 50 else 0.3
+                gain = slope if leaf[-2] in ('bn3', 'bn4') else 1.0
                 v.fill_(gain if leaf[-1] == 'W' else 0.0)
             elif name == 'extractor/conv1/W':
                 # inputs are mean-subtracted 8-bit pixels (|x| ~ 128)

@@ -48,6 +48,9 @@ class ProposalTargetCreator(object):
 
     def __call__(self, roi, bbox, label, mask, loc_normalize_mean=(0., 0., 0., 0.),
                  loc_normalize_std=(0.1, 0.1, 0.2, 0.2)):
+        # like the reference (:112-115, :179-183), the work happens on the host and the results
+        # go back to where `roi` lives: NumPy in -> NumPy out, device tensor in -> device tensors
+        device = roi.device if hasattr(roi, 'detach') and roi.is_cuda else None
         roi, bbox, label = _to_host(roi), _to_host(bbox), _to_host(label)
         if bbox.shape[0] == 0:
             raise ValueError('Empty bbox is not supported.')
@@ -78,4 +81,8 @@ class ProposalTargetCreator(object):
                               dtype=np.int32)
         for i, p in enumerate(pos):
             gt_roi_mask[i] = self._mask_target(mask[assigned[p]], sample_roi[i])
-        return sample_roi, gt_roi_loc, gt_roi_label, gt_roi_mask
+        out = (sample_roi, gt_roi_loc, gt_roi_label, gt_roi_mask)
+        if device is not None:
+            import torch
+            out = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in out)
+        return out

@@ -43,6 +43,24 @@ def nchw(t):
     return t.permute(0, 3, 1, 2)
 
 
+def record(name, errs):
+    """Keeps the measured per-layer errors next to the other GPU-run artefacts."""
+    import json
+    import os
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out_dir):
+        path = os.path.join(out_dir, 'config0_errors.json')
+        data = {}
+        if os.path.exists(path):
+            try:
+                data = json.load(open(path))
+            except Exception:
+                data = {}
+        data[name] = {k: float(v) for k, v in errs.items()}
+        data[name + ':max'] = float(max(errs.values()))
+        json.dump(data, open(path, 'w'), indent=1, sort_keys=True)
+
+
 def tie_free(score):
     """Real RPN logits collide (28 728 fp32 values within +-0.3: a few dozen exact ties) and
     NumPy's argsort()[::-1] orders equal keys arbitrarily, so index lists can only be compared
@@ -111,6 +129,7 @@ def test_extractor_every_layer_on_identical_inputs(cfg0):
             _check_block(blk, tape[root], errs, '%s/%s' % (stage, nm))
     assert tape['extractor/res4'].shape == (1, 1024, 38, 63)
     assert len(errs) == 2 + 13 * 4 + 3       # conv1, pool1, 13 blocks x (3 convs + sum), 3 shortcuts
+    record('extractor', errs)
     bad = {k: v for k, v in errs.items() if not v <= TOL}
     assert not bad, bad
     # the whole extractor chained (40 TF32 layers deep) stays within 5e-3
@@ -197,6 +216,7 @@ def test_roi_align_and_head_every_layer_on_identical_inputs(cfg0):
     mk = head.mask.forward(nhwc(tape['head/deconv6']), round_out=False)
     errs['mask'] = rel(nchw(mk), w_mask)
     assert len(errs) == 2 + (5 + 4 + 4) + 5
+    record('head', errs)
     bad = {k: v for k, v in errs.items() if not v <= TOL}
     assert not bad, bad
     # the head chained on the oracle's feature map (13 TF32 layers deep)
@@ -235,6 +255,7 @@ def test_parity_mode_chained_model_matches_fp32_oracle(cfg0):
         errs = dict(feat=e_feat, rpn_locs=e_loc, rpn_scores=e_score, cls_loc=rel(cl, w_cl),
                     score=rel(sc, w_sc), mask=rel(mask, w_mask))
         print('tf32x3 chained errors:', {k: '%.2e' % v for k, v in errs.items()})
+        record('tf32x3_chained', errs)
         bad = {k: v for k, v in errs.items() if not v <= 5e-4}
         assert not bad, bad
         # the chained parity-mode model proposes (as a set: scores 1e-4 apart swap ranks, so
