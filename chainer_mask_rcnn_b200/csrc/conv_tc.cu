@@ -759,13 +759,17 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
   // Tail split: a pair launch whose tiles do not fill its last wave (res5's 392 tiles on 74
   // SM pairs: 6 waves for 5.3 waves of work) runs the whole waves as pairs and hands the
   // images of the partial wave to a second launch with 128 x 128 single-CTA tiles (<= one
-  // wave of 148, a quarter of the work per tile): the tail then costs ~0.4 instead of 1.0
-  // of a wave.  Plain epilogues only; the cut is at an image boundary so that both launches
-  // are ordinary convolutions over a batch.  CMR_CONV_TAIL_SPLIT=0 disables it (A/B runs).
+  // wave of 148, a quarter of the work per tile).  Plain epilogues only; the cut is at an
+  // image boundary so that both launches are ordinary convolutions over a batch.
+  // MEASURED, OFF BY DEFAULT (CMR_CONV_TAIL_SPLIT=1 enables it for A/B runs): a 128 x 128
+  // single-CTA tile ingests 32 KB of operands per 256 MMA cycles -- it is operand-bound and
+  // takes as long as a 256 x 256 pair tile, so the tail wave does not get shorter: two
+  // same-box A/B pairs, tensor-bound launches 616.6 / 619.7 TFLOP/s with the split against
+  // 626.2 / 628.9 without, 13 more launches per step.
   static int tail_ok = -1;
   if (tail_ok < 0) {
     const char* e = getenv("CMR_CONV_TAIL_SPLIT");
-    tail_ok = e ? atoi(e) : 1;
+    tail_ok = e ? atoi(e) : 0;
   }
   if (pair && tail_ok && c->tile_n == 0 && !bcast && p.tap_cols == 0 && p.d_stride == 1 &&
       c->d_h == c->out_h && c->d_w == c->out_w && c->d_oy == 0 && c->d_ox == 0) {
