@@ -316,7 +316,7 @@ def tensor_roofline(prof, pk, tf32, steps, ms_total, measured_in):
     sustained_half = pk['bf16_tflops_sustained'] / 2.0
     burst_half = pk['bf16_tflops'] / 2.0
     achieved = work_k / (ms_k * 1e-3) / 1e12 if ms_k > 0 else 0.0
-    traffic, traffic_src = ncu_traffic('r*_ncu_conv_v*_raw.csv', 'conv_gemm_tc_kernel')
+    traffic, traffic_src = ncu_traffic('r*_ncu_conv_*raw.csv', 'conv_gemm_tc_kernel')
     rl = {
         'bound': 'tensor', 'kernel': 'conv_gemm_tc_kernel (fprop + dgrad implicit GEMM)',
         'achieved': achieved, 'peak': sustained_half, 'unit': 'TFLOP/s',
@@ -815,7 +815,7 @@ def cpu_baseline_roi_nms(budget_s=10.0):
     from oracle import roi_align as ora
     x, rois, boxes = roi_nms_inputs(0)
     with all_host_threads() as pool:
-        R_s, C_s = 64, 64
+        R_s, C_s = 500, 512          # half the RoIs x half the channels: a few seconds
         t0 = time.perf_counter()
         ora.roi_align_forward(x[:, :C_s], rois[1000][:R_s], 14, 14, 1. / 16, 0)
         t_roi = time.perf_counter() - t0
