@@ -73,6 +73,14 @@ _SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    'cmr_conv_wgrad_tc_fixed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
+    'cmr_col_sum_fixed': (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p,
+                                  c_void_p]),
+    'cmr_roi_align_nhwc_bwd_fixed': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                             c_int, c_int, c_int, c_int, c_float, c_int,
+                                             c_void_p, c_void_p]),
+    'cmr_fixed_to_float': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     'cmr_relu_mask': (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'cmr_split_tf32x3': (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
     'cmr_pack_image_nhwc4': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -55,6 +55,20 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // Number of SMs of the current device (148 on B200), cached per process.
 int sm_count();
 
+// Deterministic mode: floating-point reductions whose arrival order is not fixed (split
+// weight gradients, ROIAlign backward, bias column sums) accumulate into 64-bit FIXED-POINT
+// words instead -- integer addition is associative, so the sum does not depend on the order.
+// One unit = 2^-40: +-8.4e6 of range, 9e-13 of resolution (a single fp32 term is converted
+// exactly up to that resolution).
+#ifdef __CUDACC__
+__device__ __forceinline__ long long to_fixed(float v) {
+  return __double2ll_rn((double)v * 1099511627776.0);
+}
+__device__ __forceinline__ void red_fixed(long long* addr, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)to_fixed(v));
+}
+#endif
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) {
   return (a + b - 1) / b;

@@ -67,6 +67,7 @@ struct WgradParams {
   int p_tiled, q_tiled;  // operand is a plain (pixels x channels) matrix: tiled-mode TMA
   int probe;           // timing probes (CMR_WGRAD_PROBE): 1 = loads only for the first ring
                        // fill, 2 = no MMAs; results are garbage, 0 in normal operation
+  int fixed;           // deterministic mode: gw points to int64 fixed-point words (common.cuh)
 };
 
 constexpr int kBM = 128;
@@ -207,7 +208,12 @@ conv_wgrad_tc_kernel(const WgradParams p) {
         for (int g = 0; g < 8; ++g) {
           const int j = jc + g * 4;
           if (j >= p.cols) break;
-          if (vec_ok && j + 3 < p.cols) {
+          if (p.fixed) {
+            long long* frow = reinterpret_cast<long long*>(p.gw) + (size_t)row * p.gw_ld +
+                              p.gw_col0 + tap * p.cols;
+            for (int e = 0; e < 4 && j + e < p.cols; ++e)
+              red_fixed(frow + j + e, __uint_as_float(v[g * 4 + e]) * sc);
+          } else if (vec_ok && j + 3 < p.cols) {
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_row + j),
                          "f"(__uint_as_float(v[g * 4 + 0]) * sc),
                          "f"(__uint_as_float(v[g * 4 + 1]) * sc),
@@ -445,7 +451,12 @@ conv_wgrad_tma_kernel(const __grid_constant__ CUtensorMap tmap_p,
       for (int g = 0; g < 8; ++g) {
         const int j = jc + g * 4;
         if (j >= p.cols) break;
-        if (vec_ok && j + 3 < p.cols) {
+        if (p.fixed) {
+          long long* frow = reinterpret_cast<long long*>(p.gw) + (size_t)row * p.gw_ld +
+                            p.gw_col0 + tap * p.cols;
+          for (int e = 0; e < 4 && j + e < p.cols; ++e)
+            red_fixed(frow + j + e, __uint_as_float(v[g * 4 + e]) * sc);
+        } else if (vec_ok && j + 3 < p.cols) {
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out_row + j),
                        "f"(__uint_as_float(v[g * 4 + 0]) * sc),
                        "f"(__uint_as_float(v[g * 4 + 1]) * sc),
@@ -567,8 +578,25 @@ extern int g_im2col_tma;
 
 using namespace cmr;
 
+namespace {
+int wgrad_impl(const cmr_wgrad_desc* c, const float* gy, const float* x, float* gw, int fixed,
+               const float* row_scale, void* stream);
+}
+
 extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const float* x,
                                  float* gw, const float* row_scale, void* stream) {
+  return wgrad_impl(c, gy, x, gw, 0, row_scale, stream);
+}
+
+extern "C" int cmr_conv_wgrad_tc_fixed(const cmr_wgrad_desc* c, const float* gy, const float* x,
+                                       long long* gw_fixed, const float* row_scale,
+                                       void* stream) {
+  return wgrad_impl(c, gy, x, reinterpret_cast<float*>(gw_fixed), 1, row_scale, stream);
+}
+
+namespace {
+int wgrad_impl(const cmr_wgrad_desc* c, const float* gy, const float* x, float* gw, int fixed,
+               const float* row_scale, void* stream) {
   CMR_REQUIRE(c && gy && x && gw);
   CMR_REQUIRE(c->batch > 0 && c->loop_h > 0 && c->loop_w > 0 && c->rows > 0 && c->cols > 0);
   CMR_REQUIRE(c->gy_h > 0 && c->gy_w > 0 && c->x_h > 0 && c->x_w > 0);
@@ -591,6 +619,7 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   p.div_w = make_fast_div(c->loop_w);
   p.rows = c->rows; p.cols = c->cols;
   p.gw = gw; p.gw_ld = c->gw_ld; p.gw_col0 = c->gw_col0;
+  p.fixed = fixed;
   p.row_scale = row_scale;
   p.num_kb = ceil_div(p.M, kPix);
   {
@@ -676,3 +705,4 @@ extern "C" int cmr_conv_wgrad_tc(const cmr_wgrad_desc* c, const float* gy, const
   if (bn == 128) return launch_wgrad<128, 3>(p, splits, taps, st);
   return launch_wgrad<64, 4>(p, splits, taps, st);
 }
+}  // namespace

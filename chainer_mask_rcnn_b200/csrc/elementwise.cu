@@ -77,10 +77,33 @@ relu_mask_kernel(const float4* __restrict__ g, const float4* __restrict__ mask,
     out[i] = v;
   }
 }
+
+// Fixed-point accumulators (common.cuh) back to fp32: out = (accumulate ? out : 0) +
+// float(in * 2^-40); in is zeroed for the next step when zero_src is set.
+__global__ void __launch_bounds__(256)
+fixed_to_float_kernel(long long* __restrict__ in, float* __restrict__ out, size_t n,
+                      int accumulate, int zero_src) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = (float)((double)in[i] * (1.0 / 1099511627776.0));
+    out[i] = accumulate ? out[i] + v : v;
+    if (zero_src) in[i] = 0;
+  }
+}
 }  // namespace
 }  // namespace cmr
 
 using namespace cmr;
+
+extern "C" int cmr_fixed_to_float(long long* in, float* out, size_t n, int accumulate,
+                                  int zero_src, void* stream) {
+  if (n == 0) return CMR_OK;
+  CMR_REQUIRE(in && out);
+  const int blocks = (int)min((size_t)sm_count() * 8, (n + 255) / 256);
+  fixed_to_float_kernel<<<blocks, 256, 0, as_stream(stream)>>>(in, out, n, accumulate, zero_src);
+  CMR_LAUNCH_CHECK();
+  return CMR_OK;
+}
 
 extern "C" int cmr_relu_mask(const float* g, const float* mask, float* out, size_t n,
                              int round_tf32, void* stream) {

@@ -120,7 +120,7 @@ avg_pool_bwd_accum_kernel(const float4* __restrict__ g, int HW, int C4, float4* 
 // Block = 32 columns x 8 row lanes; grid.y splits the rows.
 __global__ void __launch_bounds__(256)
 col_sum_kernel(const float* __restrict__ g, long long M, int ld, int c0, int n,
-               float* __restrict__ out, int rows_per_block) {
+               float* __restrict__ out, int rows_per_block, int fixed) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -135,7 +135,8 @@ col_sum_kernel(const float* __restrict__ g, long long M, int ld, int c0, int n,
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += part[k][tx];
-    atomicAdd(out + j, t);
+    if (fixed) red_fixed(reinterpret_cast<long long*>(out) + j, t);   // deterministic mode
+    else atomicAdd(out + j, t);
   }
 }
 
@@ -292,11 +293,27 @@ extern "C" int cmr_avg_pool_nhwc_bwd_accum(const float* g, int R, int HW, int C,
   return CMR_OK;
 }
 
+namespace {
+int col_sum_impl(const float* g, long long M, int ld, int c0, int n, float* out, int fixed,
+                 void* stream);
+}
+
 extern "C" int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, float* out,
                            void* stream) {
+  return col_sum_impl(g, M, ld, c0, n, out, 0, stream);
+}
+
+extern "C" int cmr_col_sum_fixed(const float* g, long long M, int ld, int c0, int n,
+                                 long long* out_fixed, void* stream) {
+  return col_sum_impl(g, M, ld, c0, n, reinterpret_cast<float*>(out_fixed), 1, stream);
+}
+
+namespace {
+int col_sum_impl(const float* g, long long M, int ld, int c0, int n, float* out, int fixed,
+                 void* stream) {
   CMR_REQUIRE(M >= 0 && n > 0 && ld >= c0 + n && c0 >= 0 && out);
   cudaStream_t st = as_stream(stream);
-  CMR_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * n, st));
+  CMR_CUDA_TRY(cudaMemsetAsync(out, 0, (fixed ? sizeof(long long) : sizeof(float)) * n, st));
   if (M == 0) return CMR_OK;
   CMR_REQUIRE(g);
   const int col_blocks = ceil_div(n, 32);
@@ -307,10 +324,11 @@ extern "C" int cmr_col_sum(const float* g, long long M, int ld, int c0, int n, f
   if (splits > 65535) splits = 65535;
   const int rows_per_block = (int)((M + splits - 1) / splits);
   dim3 grid(col_blocks, (unsigned)((M + rows_per_block - 1) / rows_per_block));
-  col_sum_kernel<<<grid, 256, 0, st>>>(g, M, ld, c0, n, out, rows_per_block);
+  col_sum_kernel<<<grid, 256, 0, st>>>(g, M, ld, c0, n, out, rows_per_block, fixed);
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
+}  // namespace
 
 extern "C" int cmr_prep_dgrad_weight(const float* w, int O, int T, int I, long long stride_o,
                                      long long stride_t, const float* scale, int flip,

@@ -407,16 +407,26 @@ __device__ __forceinline__ void blend_rows(const RowBlend& rb, const char* __res
   }
 }
 
-template <int NQ>
+// FIXED: the destination is the deterministic mode's int64 fixed-point image (common.cuh):
+// same element order, 8 bytes per element, four scalar 64-bit reductions per quad.
+__device__ __forceinline__ void red_fixed_f4(char* addr, const float4& v) {
+  long long* q = reinterpret_cast<long long*>(addr);
+  red_fixed(q, v.x); red_fixed(q + 1, v.y); red_fixed(q + 2, v.z); red_fixed(q + 3, v.w);
+}
+
+template <int NQ, bool FIXED = false>
 __device__ __forceinline__ void scatter_rows(const RowBlend& rb, char* __restrict__ img, int xoff,
                                              int row_bytes, int qs, const float4 (&h)[NQ]) {
-  char* p = img + rb.first + xoff;
-  for (int k = 0; k < rb.n; ++k, p += row_bytes) {
+  constexpr int kW = FIXED ? 2 : 1;           // bytes per element relative to fp32
+  char* p = img + (size_t)kW * (rb.first + xoff);
+  for (int k = 0; k < rb.n; ++k, p += kW * row_bytes) {
     const float w = rb.w[k];
 #pragma unroll
-    for (int j = 0; j < NQ; ++j)
-      red_add_f4(reinterpret_cast<float4*>(p + j * qs),
-                 make_float4(h[j].x * w, h[j].y * w, h[j].z * w, h[j].w * w));
+    for (int j = 0; j < NQ; ++j) {
+      const float4 v = make_float4(h[j].x * w, h[j].y * w, h[j].z * w, h[j].w * w);
+      if (FIXED) red_fixed_f4(p + kW * j * qs, v);
+      else red_add_f4(reinterpret_cast<float4*>(p + j * qs), v);
+    }
   }
 }
 
@@ -475,7 +485,7 @@ __device__ __forceinline__ void walk_row_fwd(const RowBlend& rb, const float4* _
 }
 
 // Backward of the same walk: fetch(q, j) returns the gradient of bin q of quad j.
-template <int NQ, typename Fetch>
+template <int NQ, bool FIXED = false, typename Fetch>
 __device__ __forceinline__ void walk_row_bwd(const RowBlend& rb, const float4* __restrict__ xt,
                                              int grid_w, int pw0, int pw_step, int npw,
                                              char* __restrict__ img, int row_bytes, int qs,
@@ -502,12 +512,12 @@ __device__ __forceinline__ void walk_row_bwd(const RowBlend& rb, const float4* _
       const int xl = __float_as_int(tx.x), xh = __float_as_int(tx.y);
       if (xl < 0) continue;
       if (xl != lo) {
-        if (lo >= 0) scatter_rows<NQ>(rb, img, lo, row_bytes, qs, hlo);
+        if (lo >= 0) scatter_rows<NQ, FIXED>(rb, img, lo, row_bytes, qs, hlo);
         if (xl == hi) {
 #pragma unroll
           for (int j = 0; j < NQ; ++j) hlo[j] = hhi[j];
         } else {
-          if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+          if (hi >= 0) scatter_rows<NQ, FIXED>(rb, img, hi, row_bytes, qs, hhi);
 #pragma unroll
           for (int j = 0; j < NQ; ++j) hlo[j] = zero;
         }
@@ -523,7 +533,7 @@ __device__ __forceinline__ void walk_row_bwd(const RowBlend& rb, const float4* _
         for (int j = 0; j < NQ; ++j) fma4(hlo[j], tx.z, a[j]);
       } else {
         if (xh != hi) {
-          if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+          if (hi >= 0) scatter_rows<NQ, FIXED>(rb, img, hi, row_bytes, qs, hhi);
           hi = xh;
 #pragma unroll
           for (int j = 0; j < NQ; ++j) hhi[j] = zero;
@@ -533,8 +543,8 @@ __device__ __forceinline__ void walk_row_bwd(const RowBlend& rb, const float4* _
       }
     }
   }
-  if (lo >= 0) scatter_rows<NQ>(rb, img, lo, row_bytes, qs, hlo);
-  if (hi >= 0) scatter_rows<NQ>(rb, img, hi, row_bytes, qs, hhi);
+  if (lo >= 0) scatter_rows<NQ, FIXED>(rb, img, lo, row_bytes, qs, hlo);
+  if (hi >= 0) scatter_rows<NQ, FIXED>(rb, img, hi, row_bytes, qs, hhi);
 }
 
 // Generic (any RoI size) single-bin evaluation on a channels-last map; the rare path for
@@ -560,9 +570,11 @@ __device__ __forceinline__ float4 bin_fwd_generic(const RoiGeom& g, int ph, int 
   return make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
 }
 
+template <bool FIXED = false>
 __device__ __forceinline__ void bin_bwd_generic(const RoiGeom& g, int ph, int pw, int H, int W,
                                                 char* __restrict__ img, int row_bytes,
                                                 int px_bytes, float inv, float4 gv) {
+  constexpr int kW = FIXED ? 2 : 1;
   gv.x *= inv; gv.y *= inv; gv.z *= inv; gv.w *= inv;
   for (int iy = 0; iy < g.grid_h; ++iy) {
     const AxisTap ty = axis_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, H);
@@ -570,17 +582,17 @@ __device__ __forceinline__ void bin_bwd_generic(const RoiGeom& g, int ph, int pw
     for (int ix = 0; ix < g.grid_w; ++ix) {
       const AxisTap tx = axis_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, W);
       if (!tx.valid) continue;
-      char* r0 = img + (size_t)ty.low * row_bytes;
-      char* r1 = img + (size_t)ty.high * row_bytes;
-      const float w1 = ty.h * tx.h, w2 = ty.h * tx.l, w3 = ty.l * tx.h, w4 = ty.l * tx.l;
-      red_add_f4(reinterpret_cast<float4*>(r0 + tx.low * px_bytes),
-                 make_float4(gv.x * w1, gv.y * w1, gv.z * w1, gv.w * w1));
-      red_add_f4(reinterpret_cast<float4*>(r0 + tx.high * px_bytes),
-                 make_float4(gv.x * w2, gv.y * w2, gv.z * w2, gv.w * w2));
-      red_add_f4(reinterpret_cast<float4*>(r1 + tx.low * px_bytes),
-                 make_float4(gv.x * w3, gv.y * w3, gv.z * w3, gv.w * w3));
-      red_add_f4(reinterpret_cast<float4*>(r1 + tx.high * px_bytes),
-                 make_float4(gv.x * w4, gv.y * w4, gv.z * w4, gv.w * w4));
+      char* r0 = img + (size_t)kW * ty.low * row_bytes;
+      char* r1 = img + (size_t)kW * ty.high * row_bytes;
+      const float w[4] = {ty.h * tx.h, ty.h * tx.l, ty.l * tx.h, ty.l * tx.l};
+      char* dst[4] = {r0 + (size_t)kW * tx.low * px_bytes, r0 + (size_t)kW * tx.high * px_bytes,
+                      r1 + (size_t)kW * tx.low * px_bytes, r1 + (size_t)kW * tx.high * px_bytes};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 v = make_float4(gv.x * w[t], gv.y * w[t], gv.z * w[t], gv.w * w[t]);
+        if (FIXED) red_fixed_f4(dst[t], v);
+        else red_add_f4(reinterpret_cast<float4*>(dst[t]), v);
+      }
     }
   }
 }
@@ -641,6 +653,7 @@ roi_align_nhwc_fwd_kernel(const float4* __restrict__ src, const float* __restric
   }
 }
 
+template <bool FIXED>
 __global__ void __launch_bounds__(128, 6)
 roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict__ rois,
                           float4* __restrict__ gx, int H, int W, int C4, int outh, int outw,
@@ -659,24 +672,26 @@ roi_align_nhwc_bwd_kernel(const float4* __restrict__ gy, const float* __restrict
   if (fits) build_col_taps(sm.xt, g, outw, W, px_bytes);
   __syncthreads();
   const bool fast = sm.ok != 0;
-  char* img = reinterpret_cast<char*>(gx + (size_t)g.batch * H * W * C4);
+  // (FIXED: gx is the int64 fixed-point image, two float4 slots per quad)
+  char* img = reinterpret_cast<char*>(gx + (size_t)(FIXED ? 2 : 1) * g.batch * H * W * C4);
   const float4* gyrow = gy + ((size_t)r * oh_s + row) * ow_s * C4;
   const float inv = __fdiv_rn(1.0f, g.inv_count_den);
   const int T = blockDim.x;
   for (int c = threadIdx.x; c < C4; c += 2 * T) {
     const float4* gp = gyrow + c;
     auto fetch = [&](int q, int j) { return __ldg(gp + (size_t)q * C4 + j * T); };
-    char* base = img + (size_t)c * 16;
+    char* base = img + (size_t)(FIXED ? 2 : 1) * c * 16;
     if (!fast) {
       for (int j = 0; j < 2 && c + j * T < C4; ++j)
         for (int q = 0; q < ow_s; ++q)
-          bin_bwd_generic(g, ph, q * bin_stride, H, W, base + (size_t)j * T * 16, row_bytes,
-                          px_bytes, inv, fetch(q, j));
+          bin_bwd_generic<FIXED>(g, ph, q * bin_stride, H, W,
+                                 base + (size_t)(FIXED ? 2 : 1) * j * T * 16, row_bytes,
+                                 px_bytes, inv, fetch(q, j));
     } else if (c + T < C4) {
-      walk_row_bwd<2>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, T * 16, inv,
+      walk_row_bwd<2, FIXED>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, T * 16, inv,
                       fetch);
     } else {
-      walk_row_bwd<1>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, 0, inv, fetch);
+      walk_row_bwd<1, FIXED>(sm.rb, sm.xt, g.grid_w, 0, bin_stride, ow_s, base, row_bytes, 0, inv, fetch);
     }
   }
 }
@@ -865,7 +880,7 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
           walk_row_bwd<1>(rb[ph], sm->xt, g.grid_w, 0, 1, outw, img, row_bytes, 0, inv, fetch);
         } else {
           for (int pw = 0; pw < outw; ++pw)
-            bin_bwd_generic(g, ph, pw, H, W, img, row_bytes, px_bytes, inv, fetch(pw, 0));
+            bin_bwd_generic<>(g, ph, pw, H, W, img, row_bytes, px_bytes, inv, fetch(pw, 0));
         }
       }
     }
@@ -1258,7 +1273,8 @@ extern "C" int cmr_roi_align_nhwc_fwd(const float* x, int N, int H, int W, int C
 namespace {
 int roi_align_nhwc_bwd_impl(const float* gy, const float* rois, int R, int N, int H, int W, int C,
                             int outh, int outw, int bin_stride, float spatial_scale,
-                            int sampling_ratio, float* gx, bool zero_fill, void* stream) {
+                            int sampling_ratio, float* gx, bool zero_fill, void* stream,
+                            bool fixed = false) {
   CMR_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && outh > 0 && outw > 0);
   CMR_REQUIRE(sampling_ratio >= 0 && bin_stride >= 1 && C % 4 == 0 && gx);
   const int oh_s = ceil_div(outh, bin_stride), ow_s = ceil_div(outw, bin_stride);
@@ -1276,14 +1292,29 @@ int roi_align_nhwc_bwd_impl(const float* gy, const float* rois, int R, int N, in
     CMR_CUDA_TRY(me);
     return CMR_OK;
   }
-  roi_align_nhwc_bwd_kernel<<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4, outh,
-      outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, N);
+  if (fixed)
+    roi_align_nhwc_bwd_kernel<true><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4,
+        outh, outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, N);
+  else
+    roi_align_nhwc_bwd_kernel<false><<<R * oh_s, nhwc_threads(C / 4), 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(gy), rois, reinterpret_cast<float4*>(gx), H, W, C / 4,
+        outh, outw, bin_stride, oh_s, ow_s, spatial_scale, sampling_ratio, N);
   prof_end(as_stream(stream));
   CMR_LAUNCH_CHECK();
   return CMR_OK;
 }
 }  // namespace
+
+extern "C" int cmr_roi_align_nhwc_bwd_fixed(const float* gy, const float* rois, int R, int N,
+                                            int H, int W, int C, int outh, int outw,
+                                            int bin_stride, float spatial_scale,
+                                            int sampling_ratio, long long* gx_fixed,
+                                            void* stream) {
+  return roi_align_nhwc_bwd_impl(gy, rois, R, N, H, W, C, outh, outw, bin_stride, spatial_scale,
+                                 sampling_ratio, reinterpret_cast<float*>(gx_fixed), false,
+                                 stream, true);
+}
 
 extern "C" int cmr_roi_align_nhwc_bwd(const float* gy, const float* rois, int R, int N, int H,
                                       int W, int C, int outh, int outw, int bin_stride,

@@ -108,7 +108,9 @@ def wgrad_tap(gy, x, gw, rows, cols, loop_hw, gw_ld, gw_col0=0, gy_stride=1, gy_
     d = _lib.WgradDesc(B, loop_hw[0], loop_hw[1], gh, gww, gld, gy_stride, gy_off[0], gy_off[1],
                        gy_c0, xh, xw, xld, x_stride, x_off[0], x_off[1], x_c0, rows, cols,
                        gw_ld, gw_col0, 0, taps[0], taps[1])
-    grad_side.run(lambda: _lib.call('cmr_conv_wgrad_tc', ctypes.byref(d), _p(gy), _p(x), _p(gw),
+    # an int64 destination is the deterministic mode's fixed-point shadow of the gradient
+    fn = 'cmr_conv_wgrad_tc_fixed' if gw.dtype == torch.int64 else 'cmr_conv_wgrad_tc'
+    grad_side.run(lambda: _lib.call(fn, ctypes.byref(d), _p(gy), _p(x), _p(gw),
                                     _p(row_scale), stream()), gy, x)
 
 
@@ -133,8 +135,16 @@ def column_sums(g, c0, n, out):
     """out[:n] = sum over all leading axes of g[..., c0:c0+n] (g contiguous)."""
     ld = g.shape[-1]
     rows = g.numel() // ld
-    grad_side.run(lambda: _lib.call('cmr_col_sum', _p(g), rows, ld, c0, n, _p(out), stream()), g)
+    fn = 'cmr_col_sum_fixed' if out.dtype == torch.int64 else 'cmr_col_sum'
+    grad_side.run(lambda: _lib.call(fn, _p(g), rows, ld, c0, n, _p(out), stream()), g)
     return out
+
+
+def fixed_to_float(src, dst, accumulate=False, zero_src=True):
+    """Deterministic mode: int64 fixed-point accumulators -> fp32 (cmr_fixed_to_float)."""
+    _lib.call('cmr_fixed_to_float', _p(src), _p(dst), src.numel(), int(accumulate),
+              int(zero_src), stream())
+    return dst
 
 
 _prep_recorder = None   # list collecting descriptors while a batch table is being built
@@ -219,10 +229,19 @@ def roi_align_nhwc(x, rois_xy, outh, outw, bin_stride, spatial_scale, sampling_r
 
 
 def roi_align_nhwc_bwd(gy, rois_xy, x_shape, outh, outw, bin_stride, spatial_scale,
-                       sampling_ratio=0, accum=None):
+                       sampling_ratio=0, accum=None, deterministic=False):
     """-> gx (N,H,W,C); with ``accum`` (N,H,W,C) the RoI gradients are added to it in place
-    (no zero fill)."""
+    (no zero fill).  ``deterministic``: the scatter goes through int64 fixed-point words
+    (order-independent sums), converted to fp32 afterwards."""
     N, H, W, C = x_shape
+    if deterministic:
+        fx = torch.zeros((N, H, W, C), dtype=torch.int64, device=gy.device)
+        _lib.call('cmr_roi_align_nhwc_bwd_fixed', _p(gy), _p(rois_xy), rois_xy.shape[0], N, H, W,
+                  C, outh, outw, bin_stride, float(spatial_scale), sampling_ratio, _p(fx),
+                  stream())
+        out = accum if accum is not None else torch.empty((N, H, W, C), dtype=f32,
+                                                          device=gy.device)
+        return fixed_to_float(fx, out, accumulate=accum is not None, zero_src=False)
     if accum is not None:
         _lib.call('cmr_roi_align_nhwc_bwd_accum', _p(gy), _p(rois_xy), rois_xy.shape[0], N, H,
                   W, C, outh, outw, bin_stride, float(spatial_scale), sampling_ratio, _p(accum),

@@ -37,6 +37,10 @@ class Context(object):
         # the parity mode of SURVEY.md 7.3); forward only.
         self.precision = 'tf32'
         self.version = 0                # bumped whenever parameters change
+        # deterministic mode: weight / bias gradients and the ROIAlign backward accumulate in
+        # int64 fixed point (order-independent), see include/cmr_b200.h
+        self.deterministic = False
+        self.grads_fixed = None
         self._train_dirty = True
         self._frozen_dirty = True
         self._dgrad_dirty = True
@@ -63,7 +67,24 @@ class Context(object):
         return (self.train if name in self.train else self.frozen).view(name)
 
     def grad(self, name):
+        """Where the backward kernels accumulate dL/d(name): the fp32 gradient buffer, or its
+        int64 fixed-point shadow in deterministic mode (``finish_grads`` converts)."""
+        if self.deterministic:
+            if self.grads_fixed is None:
+                self.grads_fixed = torch.zeros(self.grads.shape, dtype=torch.int64,
+                                               device=self.device)
+            return self.train.view(name, self.grads_fixed)
         return self.train.view(name, self.grads)
+
+    def finish_grads(self, lo=0, hi=None):
+        """End of the backward pass (or of the part of it that fills gradients [lo, hi)): in
+        deterministic mode the fixed-point sums become the fp32 gradients (and are zeroed for
+        the next step)."""
+        if self.deterministic and self.grads_fixed is not None:
+            hi = self.grads.numel() if hi is None else hi
+            if hi > lo:
+                E.fixed_to_float(self.grads_fixed[lo:hi], self.grads[lo:hi], accumulate=False,
+                                 zero_src=True)
 
     def fwd(self, name):
         """tf32-rounded copy read by the forward GEMMs."""

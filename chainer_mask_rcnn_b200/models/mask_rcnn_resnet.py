@@ -215,7 +215,8 @@ class ResNetRoIHead(object):
         g_pool = self.res5.backward(g_res5, input_is_relu=False)
         return E.roi_align_nhwc_bwd(g_pool, s['rois_xy'], s['feat_shape'], self.roi_size,
                                     self.roi_size, self.bin_stride, self.spatial_scale,
-                                    accum=accum() if accum is not None else None)
+                                    accum=accum() if accum is not None else None,
+                                    deterministic=self.ctx.deterministic)
 
 
 class MaskRCNNResNet(MaskRCNN):

@@ -66,9 +66,16 @@ def _host(a):
 class MaskRCNNTrainChain(object):
 
     def __init__(self, mask_rcnn, rpn_sigma=3., roi_sigma=1., anchor_target_creator=None,
-                 proposal_target_creator=None, seed=0):
+                 proposal_target_creator=None, seed=0, deterministic=None):
+        """``deterministic=True`` (or CMR_DETERMINISTIC=1): the reductions whose arrival order
+        is not fixed (split weight gradients, ROIAlign backward, bias sums) accumulate in 64-bit
+        fixed point, so two runs of the same steps give bit-identical parameters; ~3 % slower."""
+        import os
         self.mask_rcnn = mask_rcnn
         self.ctx = mask_rcnn.ctx
+        if deterministic is None:
+            deterministic = os.environ.get('CMR_DETERMINISTIC', '0') == '1'
+        self.ctx.deterministic = bool(deterministic)
         self.rpn_sigma = rpn_sigma
         self.roi_sigma = roi_sigma
         self.anchor_target_creator = anchor_target_creator or DeviceAnchorTargetCreator()
@@ -337,5 +344,7 @@ class MaskRCNNTrainChain(object):
                 m.extractor.backward(g_feat)
             finally:
                 E.grad_side.join()
+            if after_head is None:       # (a hook's owner finishes the two parts itself)
+                ctx.finish_grads()
 
         return Loss(loss, backward)

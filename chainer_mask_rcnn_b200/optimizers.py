@@ -107,13 +107,16 @@ class MomentumSGD(object):
             loss = lossfun(*args, **kwds)
         multi = self.comm is not None and self.comm.size > 1
         backbone, heads = self.grad_buckets()
+        split = backbone.numel()
         pending = []
 
         def after_head():
+            self.ctx.finish_grads(split, None)       # (deterministic mode: fixed point -> fp32)
             if multi and heads.numel():
                 pending.append(dist.all_reduce(heads, group=self.comm.group, async_op=True))
 
         loss.backward(after_head=after_head)
+        self.ctx.finish_grads(0, split)
         if multi and backbone.numel():
             pending.append(dist.all_reduce(backbone, group=self.comm.group, async_op=True))
         for work in pending:

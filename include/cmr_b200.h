@@ -273,6 +273,28 @@ typedef struct cmr_wgrad_desc {
 int cmr_conv_wgrad_tc(const cmr_wgrad_desc* desc, const float* gy, const float* x,
                       float* gw, const float* row_scale, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * Deterministic mode.  The three reductions of the train step whose arrival order is not
+ * fixed -- split weight gradients, the ROIAlign backward scatter, bias column sums -- have
+ * `_fixed` forms that accumulate into 64-bit fixed-point words (one unit = 2^-40) instead
+ * of fp32: integer addition is associative, so the replayed step is bit-reproducible.  The
+ * words use the element order of the fp32 tensor they stand for (same shapes, strides and
+ * offsets, 8 bytes per element) and must be zero before the first accumulation.
+ * cmr_fixed_to_float converts them back: out = (accumulate ? out : 0) + in * 2^-40, zeroing
+ * `in` for the next step when zero_src != 0.
+ * ------------------------------------------------------------------------ */
+int cmr_conv_wgrad_tc_fixed(const cmr_wgrad_desc* desc, const float* gy, const float* x,
+                            long long* gw_fixed, const float* row_scale, void* stream);
+int cmr_col_sum_fixed(const float* g, long long M, int ld, int c0, int n,
+                      long long* out_fixed, void* stream);   /* zeroes out_fixed[0..n) first */
+int cmr_roi_align_nhwc_bwd_fixed(const float* gy, const float* rois, int R, int N,
+                                 int H, int W, int C, int outh, int outw,
+                                 int bin_stride, float spatial_scale,
+                                 int sampling_ratio, long long* gx_fixed,
+                                 void* stream);               /* adds to gx_fixed (no zero fill) */
+int cmr_fixed_to_float(long long* in, float* out, size_t n, int accumulate,
+                       int zero_src, void* stream);
+
 /* out[i] = round-to-nearest-tf32(in[i]) (in == out allowed). */
 int cmr_round_tf32(const float* in, float* out, size_t n, void* stream);
 

@@ -44,6 +44,9 @@ class _Ctx(object):
         self.train = store
         self.grads = torch.zeros_like(store.data)
 
+    def finish_grads(self, lo=0, hi=None):      # (deterministic mode only; a no-op here)
+        pass
+
 
 def _make_store():
     s = E.FlatStore()

@@ -571,3 +571,37 @@ def test_rpn_branch_on_side_stream_gives_the_same_step():
                      'extractor/res3/a/conv1/W'):
             a, b = model.ctx.train.view(name, g0), model.ctx.train.view(name, g1)
             assert float((a - b).abs().max()) <= 1e-3 * float(a.abs().max()), (mode, name)
+
+
+def test_deterministic_mode_is_bit_reproducible():
+    """MaskRCNNTrainChain(deterministic=True): split weight gradients, bias sums and the
+    ROIAlign backward accumulate in 64-bit fixed point, so two runs of the same graph-replayed
+    steps from the same initial state end with BIT-IDENTICAL parameters (the default mode's
+    atomic fp32 reductions differ from run to run in the last bits); and the deterministic
+    gradients are the default mode's up to that rounding."""
+    from chainer_mask_rcnn_b200 import optimizers
+    rs = np.random.RandomState(23)
+    imgs, bboxes, labels, masks, scales = _tiny_batch(rs)
+    imgs_t = torch.from_numpy(imgs).cuda()
+    masks_t = torch.from_numpy(np.stack(masks).astype(np.uint8)).cuda()
+
+    def run(deterministic, steps=4):
+        model = models.MaskRCNNResNet(50, N_FG, anchor_scales=SCALES, roi_size=14,
+                                      base_channels=BASE, seed=6)
+        chain = models.MaskRCNNTrainChain(model, seed=10, deterministic=deterministic)
+        opt = optimizers.MomentumSGD(lr=0.002, momentum=0.9).setup(chain)
+        opt.add_hook(optimizers.WeightDecay(1e-4))
+        up = optimizers.GraphedUpdater(opt, chain, max_boxes=8)
+        hist = [up(imgs_t, bboxes, labels, masks_t, scales).item() for _ in range(steps)]
+        torch.cuda.synchronize()
+        return hist, model.ctx.train.data.clone(), model.ctx.grads.clone()
+
+    h1, p1, g1 = run(True)
+    h2, p2, g2 = run(True)
+    assert all(np.isfinite(h1)) and h1[-1] < h1[0]
+    assert torch.equal(p1, p2) and torch.equal(g1, g2)          # bit-identical
+    h0, p0, g0 = run(False, steps=1)
+    hd, pd, gd = run(True, steps=1)
+    np.testing.assert_allclose(hd[0], h0[0], rtol=1e-5)
+    assert float((gd - g0).abs().max()) <= 2e-5 * float(g0.abs().max())
+    assert float((pd - p0).abs().max()) <= 1e-6 * float(p0.abs().max())
