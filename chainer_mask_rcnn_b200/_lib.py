@@ -67,6 +67,8 @@ _SIGNATURES = {
                               c_float, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
     'cmr_set_im2col_tma': (c_int, [c_int]),
+    'cmr_set_conv_variant': (c_int, [c_int]),
+    'cmr_set_conv_debug': (c_int, [c_void_p]),
     'cmr_conv_gemm_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p]),
     'cmr_conv_gemm_tc_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -66,6 +66,8 @@ struct ConvGemmParams {
   int tma_a;   // A tiles by TMA: 1 = im2col-mode map, 2 = tiled-mode map (plain matrix);
                // 0 = cp.async gathers
   int epi_groups;   // epilogue warps per TMEM lane quarter: 3 with TMA A tiles, else 2
+  long long* dbg;   // measurement only: per-CTA wait-cycle counters (cmr_set_conv_debug)
+  int probe;        // measurement only (cmr_set_conv_variant): 1 = the epilogue does not store
   double alg_bytes; // host only: algorithmic HBM bytes of the launch (profiling)
 };
 
@@ -100,6 +102,15 @@ struct SmemLayout {
 // The rare forms are their own instantiations so that the common epilogue keeps its
 // register budget (128 registers, no spills).
 constexpr int kEpiPlain = 0, kEpiBcast = 1, kEpiTaps = 2;
+
+// Wait-cycle counters and probe bits of cmr_set_conv_debug / cmr_set_conv_variant: compiled
+// in only with -DCMR_CONV_INSTRUMENT=1 (build.py: CMR_CONV_INSTRUMENT=1 in the environment);
+// the product kernel carries none of it.
+#ifndef CMR_CONV_INSTRUMENT
+#define CMR_CONV_INSTRUMENT 0
+#endif
+constexpr bool kInstr = CMR_CONV_INSTRUMENT != 0;
+
 
 template <int BN, int STAGES, bool PAIR, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
@@ -210,6 +221,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     // ---------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t it = 0;
+      long long w_empty = 0;
       const int cpt = p.in_c / kBK;  // k-blocks per filter tap
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const int n0 = (tile % p.n_tiles) * BN;
@@ -223,7 +235,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], phase ^ 1);
+          if (kInstr && p.dbg) {
+            const long long c0 = clock64();
+            mbar_wait(&empty_bar[s], phase ^ 1);
+            w_empty += clock64() - c0;
+          } else {
+            mbar_wait(&empty_bar[s], phase ^ 1);
+          }
           if (PAIR) {
             // both CTAs' boxes complete on the leader's barrier, armed with all their bytes
             const uint32_t bar = mapa_cluster(smem_u32(&full_bar[s]), 0);
@@ -266,21 +284,36 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                       n0);
         }
       }
+      if (kInstr && p.dbg) p.dbg[blockIdx.x * 8 + 3] = w_empty;
     }
   } else if (warp == 5) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_tf32(kTileM, BN, 0, 0);
     uint32_t it = 0, tc_ = 0;
+    long long w_tmem = 0, w_full = 0;
+    const long long t_start = (kInstr && p.dbg) ? clock64() : 0;
     if (!PAIR || cta_rank == 0) {   // the leader CTA issues for the pair
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
       const uint32_t buf = tc_ & 1;
-      mbar_wait(&tmem_empty_bar[buf], ((tc_ >> 1) & 1) ^ 1);
+      if (kInstr && p.dbg) {
+        const long long c0 = clock64();
+        mbar_wait(&tmem_empty_bar[buf], ((tc_ >> 1) & 1) ^ 1);
+        w_tmem += clock64() - c0;
+      } else {
+        mbar_wait(&tmem_empty_bar[buf], ((tc_ >> 1) & 1) ^ 1);
+      }
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * BN;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         const uint32_t phase = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], phase);
+        if (kInstr && p.dbg) {
+          const long long c0 = clock64();
+          mbar_wait(&full_bar[s], phase);
+          w_full += clock64() - c0;
+        } else {
+          mbar_wait(&full_bar[s], phase);
+        }
         tc_fence_after();
         if (lane == 0) {
           const uint64_t da = make_smem_desc_sw128(smem_base + L::kAOff + s * kABytes, 16, 1024);
@@ -303,8 +336,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       __syncwarp();
     }
     }
+    if (kInstr && p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 0] = w_tmem;
+      p.dbg[blockIdx.x * 8 + 1] = w_full;
+      p.dbg[blockIdx.x * 8 + 2] = clock64() - t_start;
+      p.dbg[blockIdx.x * 8 + 6] = tc_;
+    }
   } else {
     // ------------------------------------------------------------- epilogue
+    // Written for instruction count: three epilogue warps per SM sub-partition cannot hide
+    // much, so a 32 x 32 chunk is ONE straight-line block -- operand loads, accumulator
+    // load, transpose through shared memory, then the arithmetic of all eight row groups
+    // with every optional step behind a single warp-uniform branch per chunk.
     const int q = warp & 3;                   // TMEM lane quarter this warp may read
     // column group of this warp; n_groups warps share a lane quarter
     const int n_groups = p.epi_groups;
@@ -319,32 +362,44 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     const float* __restrict__ mask_p = p.mask;
     float* __restrict__ d_p = p.d;
     const bool relu = p.relu != 0, round_out = p.round_out != 0;
+    const bool affine = scale_p != nullptr || bias_p != nullptr;
     const bool vec_ok = ((p.d_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(d_p) & 15) == 0) &&
                         (!addend_p || (reinterpret_cast<uintptr_t>(addend_p) & 15) == 0) &&
                         (!mask_p || (reinterpret_cast<uintptr_t>(mask_p) & 15) == 0);
+    // the output tensor is the (M, d_ld) matrix itself: row offsets need no division
+    const bool linear = p.d_stride == 1 && p.d_oy == 0 && p.d_ox == 0 && p.d_h == p.out_h &&
+                        p.d_w == p.out_w;
+    // transpose buffer: this lane writes row `lane` (16-byte slots XOR-swizzled with the
+    // row: conflict-free both ways, no padding) and reads rows 4 i + sub; the slot of an
+    // even / odd row group differs in bit 2 only
+    float4* const xw = xp4 + lane * 8;
+    const float4* const xr0 = xp4 + sub * 8 + ((lane & 7) ^ sub);
+    const float4* const xr1 = xp4 + (4 + sub) * 8 + ((lane & 7) ^ (4 + sub));
     constexpr int kChunks = BN / 32;          // 32-column chunks of the tile
     uint32_t tc_ = 0;
+    long long w_acc = 0;
+    const long long t_start = (kInstr && p.dbg) ? clock64() : 0;
     for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
       const int m0 = (tile / p.n_tiles) * kTileM + (int)cta_rank * kBM;
       const int n0 = (tile % p.n_tiles) * BN;
       const uint32_t buf = tc_ & 1;
-      // output element offsets of this lane's 8 rows (row = 32q + 4i + sub); the host
-      // checks that the output tensor has fewer than 2^31 elements
+      // output element offsets of this lane's 8 rows (row = 32q + 4i + sub); rows past M
+      // read the operands of row M - 1 and store nothing.  The host checks that the output
+      // tensor has fewer than 2^31 elements.
+      const int row0 = m0 + q * 32 + sub;
+      const bool rows_ok = m0 + q * 32 + 32 <= p.M;        // warp-uniform
+      auto row_offset = [&](int row) -> int {
+        if (linear) return row * p.d_ld;
+        const int img = row / ohw;
+        const int rem = row - img * ohw;
+        const int oy = rem / p.out_w;
+        const int ox = rem - oy * p.out_w;
+        return ((img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w + ox * p.d_stride + p.d_ox) *
+               p.d_ld;
+      };
       int doff[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = m0 + q * 32 + 4 * i + sub;
-        if (row < p.M) {
-          const int img = row / ohw;
-          const int rem = row - img * ohw;
-          const int oy = rem / p.out_w;
-          const int ox = rem - oy * p.out_w;
-          doff[i] = ((img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w + ox * p.d_stride +
-                     p.d_ox) * p.d_ld;
-        } else {
-          doff[i] = -1;
-        }
-      }
+      for (int i = 0; i < 8; ++i) doff[i] = row_offset(min(row0 + 4 * i, p.M - 1));
       bool waited = false;
 #pragma unroll 1
       for (int chunk = grp; chunk < kChunks; chunk += n_groups) {
@@ -354,7 +409,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         // pixel-shuffle store of a fused 2x2 stride-2 deconvolution: column block t =
         // ng / tap_cols holds tap (t >> 1, t & 1); n / toff address the output tensor
         const int tap = EPI == kEpiTaps ? (n0 + cbase) / p.tap_cols : 0;
-        const int toff = ((tap >> 1) * p.d_w + (tap & 1)) * p.d_ld;
+        const int cn = ((tap >> 1) * p.d_w + (tap & 1)) * p.d_ld + ng - tap * p.tap_cols;
         const int n = ng - tap * p.tap_cols;              // channel in the output tensor
         const bool full4 = vec_ok && (ng + 3 < p.N);
         // operands of the epilogue are requested before the accumulator is waited for
@@ -365,20 +420,40 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           if (addend_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              ad[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(addend_p + doff[i] + toff + n))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              ad[i] = __ldg(reinterpret_cast<const float4*>(addend_p + doff[i] + cn));
           }
           if (mask_p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              mk[i] = doff[i] >= 0 ? __ldg(reinterpret_cast<const float4*>(mask_p + doff[i] + toff + n))
-                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+              mk[i] = __ldg(reinterpret_cast<const float4*>(mask_p + doff[i] + cn));
+          }
+          if (EPI == kEpiBcast) {
+            // ad[] carries the broadcast rows: raw when there is no addend (scaled below),
+            // else folded into the addend here
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int grp_row = min(row0 + 4 * i, p.M - 1) / p.bcast_group;
+              const float4 bv =
+                  __ldg(reinterpret_cast<const float4*>(p.bcast + (size_t)grp_row * p.N + n));
+              if (addend_p) {
+                ad[i].x = fmaf(bv.x, p.bcast_scale, ad[i].x); ad[i].y = fmaf(bv.y, p.bcast_scale, ad[i].y);
+                ad[i].z = fmaf(bv.z, p.bcast_scale, ad[i].z); ad[i].w = fmaf(bv.w, p.bcast_scale, ad[i].w);
+              } else {
+                ad[i] = bv;
+              }
+            }
           }
           if (scale_p) sc = __ldg(reinterpret_cast<const float4*>(scale_p + n));
           if (bias_p) bi = __ldg(reinterpret_cast<const float4*>(bias_p + n));
         }
         if (!waited) {
-          mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
+          if (kInstr && p.dbg) {
+            const long long c0 = clock64();
+            mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
+            w_acc += clock64() - c0;
+          } else {
+            mbar_wait(&tmem_full_bar[buf], (tc_ >> 1) & 1);
+          }
           tc_fence_after();
           waited = true;
         }
@@ -386,63 +461,88 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)cbase, v);
         tmem_ld_wait();
         __syncwarp();   // previous chunk's reads of the transpose buffer are done
-        // lane = accumulator row: 8 x 16-byte stores into a 32 x 128 B buffer whose 16-byte
-        // slots are XOR-swizzled with the row (conflict-free both ways, no padding)
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          xp4[lane * 8 + (c ^ (lane & 7))] =
+          xw[c ^ (lane & 7)] =
               make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]),
                           __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
         __syncwarp();
         if (full4) {
+          float4 o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (doff[i] < 0) continue;
-            const int r = 4 * i + sub;
-            float4 o = xp4[r * 8 + ((lane & 7) ^ (r & 7))];
-            if (scale_p) { o.x *= sc.x; o.y *= sc.y; o.z *= sc.z; o.w *= sc.w; }
-            if (bias_p) { o.x += bi.x; o.y += bi.y; o.z += bi.z; o.w += bi.w; }
-            if (addend_p) { o.x += ad[i].x; o.y += ad[i].y; o.z += ad[i].z; o.w += ad[i].w; }
-            if (EPI == kEpiBcast) {
-              const int grp_row = (m0 + q * 32 + r) / p.bcast_group;
-              const float4 bv =
-                  __ldg(reinterpret_cast<const float4*>(p.bcast + (size_t)grp_row * p.N + n));
-              o.x += bv.x * p.bcast_scale; o.y += bv.y * p.bcast_scale;
-              o.z += bv.z * p.bcast_scale; o.w += bv.w * p.bcast_scale;
+          for (int i = 0; i < 8; ++i) o[i] = (i & 1) ? xr1[(i - 1) * 32] : xr0[i * 32];
+          if (affine) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = fmaf(o[i].x, sc.x, bi.x); o[i].y = fmaf(o[i].y, sc.y, bi.y);
+              o[i].z = fmaf(o[i].z, sc.z, bi.z); o[i].w = fmaf(o[i].w, sc.w, bi.w);
             }
-            if (relu) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f);
-              o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          if (addend_p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x += ad[i].x; o[i].y += ad[i].y; o[i].z += ad[i].z; o[i].w += ad[i].w;
             }
-            if (mask_p) {
-              o.x = mk[i].x > 0.f ? o.x : 0.f; o.y = mk[i].y > 0.f ? o.y : 0.f;
-              o.z = mk[i].z > 0.f ? o.z : 0.f; o.w = mk[i].w > 0.f ? o.w : 0.f;
+          }
+          if (EPI == kEpiBcast && !addend_p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = fmaf(ad[i].x, p.bcast_scale, o[i].x); o[i].y = fmaf(ad[i].y, p.bcast_scale, o[i].y);
+              o[i].z = fmaf(ad[i].z, p.bcast_scale, o[i].z); o[i].w = fmaf(ad[i].w, p.bcast_scale, o[i].w);
             }
-            if (round_out) {
-              o.x = round_tf32(o.x); o.y = round_tf32(o.y);
-              o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = fmaxf(o[i].x, 0.f); o[i].y = fmaxf(o[i].y, 0.f);
+              o[i].z = fmaxf(o[i].z, 0.f); o[i].w = fmaxf(o[i].w, 0.f);
             }
-            *reinterpret_cast<float4*>(d_p + doff[i] + toff + n) = o;
+          }
+          if (mask_p) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = mk[i].x > 0.f ? o[i].x : 0.f; o[i].y = mk[i].y > 0.f ? o[i].y : 0.f;
+              o[i].z = mk[i].z > 0.f ? o[i].z : 0.f; o[i].w = mk[i].w > 0.f ? o[i].w : 0.f;
+            }
+          }
+          if (round_out) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = round_tf32(o[i].x); o[i].y = round_tf32(o[i].y);
+              o[i].z = round_tf32(o[i].z); o[i].w = round_tf32(o[i].w);
+            }
+          }
+          if (!(kInstr && (p.probe & 1))) {
+            if (rows_ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(d_p + doff[i] + cn) = o[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (row0 + 4 * i < p.M) *reinterpret_cast<float4*>(d_p + doff[i] + cn) = o[i];
+            }
           }
         } else {
           // ragged / unaligned tail columns: scalar path
           const float* xs = reinterpret_cast<const float*>(xp4);
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {
-            if (doff[i] < 0) continue;
+            if (row0 + 4 * i >= p.M) continue;
             const int r = 4 * i + sub;
+            const int off = row_offset(row0 + 4 * i) + cn;
             for (int e = 0; e < 4 && ng + e < p.N; ++e) {
               float x = xs[r * 32 + ((((lane & 7) ^ (r & 7))) << 2) + e];
               if (scale_p) x *= __ldg(scale_p + n + e);
               if (bias_p) x += __ldg(bias_p + n + e);
-              if (addend_p) x += __ldg(addend_p + doff[i] + toff + n + e);
+              if (addend_p) x += __ldg(addend_p + off + e);
               if (EPI == kEpiBcast)
-                x += __ldg(p.bcast + (size_t)((m0 + q * 32 + r) / p.bcast_group) * p.N + n + e) *
+                x += __ldg(p.bcast + (size_t)((row0 + 4 * i) / p.bcast_group) * p.N + n + e) *
                      p.bcast_scale;
               if (relu) x = fmaxf(x, 0.f);
-              if (mask_p) x = __ldg(mask_p + doff[i] + toff + n + e) > 0.f ? x : 0.f;
+              if (mask_p) x = __ldg(mask_p + off + e) > 0.f ? x : 0.f;
               if (round_out) x = round_tf32(x);
-              d_p[doff[i] + toff + n + e] = x;
+              d_p[off + e] = x;
             }
           }
         }
@@ -457,6 +557,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         if (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tmem_empty_bar[buf]), 0));
         else mbar_arrive(&tmem_empty_bar[buf]);
       }
+    }
+    if (kInstr && p.dbg && warp == kEpiWarp0 && lane == 0) {
+      p.dbg[blockIdx.x * 8 + 4] = w_acc;
+      p.dbg[blockIdx.x * 8 + 5] = clock64() - t_start;
     }
     }
   }
@@ -559,6 +663,8 @@ int make_tmap_im2col(CUtensorMap* map, const float* base, int batch, int h, int 
 }
 
 int g_im2col_tma = 1;   // cmr_set_im2col_tma
+int g_conv_variant = 0; // cmr_set_conv_variant
+long long* g_conv_dbg = nullptr;   // cmr_set_conv_debug
 
 namespace {
 
@@ -644,6 +750,17 @@ using namespace cmr;
 extern "C" int cmr_set_im2col_tma(int on) {
   const int old = g_im2col_tma;
   g_im2col_tma = on != 0;
+  return old;
+}
+
+extern "C" int cmr_set_conv_debug(long long* buf) {
+  g_conv_dbg = buf;
+  return CMR_OK;
+}
+
+extern "C" int cmr_set_conv_variant(int v) {
+  const int old = g_conv_variant;
+  g_conv_variant = v;
   return old;
 }
 
@@ -743,7 +860,11 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
   // groups (long reductions: the main loop dominates) or 3 stages and 3 groups (short
   // reductions: the epilogue's HBM traffic dominates).
   p.epi_groups = p.tma_a ? 3 : 2;
-  const bool deep = p.K >= 1024 || !p.tma_a;
+  const int variant = g_conv_variant & 15;
+  p.dbg = g_conv_dbg;
+  p.probe = (g_conv_variant >> 5) & 1;                   // 32: no stores (instrumented builds)
+  if (g_conv_variant & 16) p.addend = p.mask = nullptr;  // 16: no epilogue operand loads
+  const bool deep = p.K >= 1024 || !p.tma_a || variant == 3 || variant == 2;
   if (bn == 256 && deep) p.epi_groups = 2;
   // CTA pairs (tcgen05.mma.cta_group::2) for the long reductions with enough 256-row tiles
   // to fill the 74 SM pairs
@@ -754,7 +875,7 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
   }
   // (128-wide pair tiles were measured on the res3 / res4 3x3 layers: no gain, those
   // single-wave launches are bound by their prologue / epilogue, not by operand delivery)
-  const bool pair = pair_ok && bn == 256 && deep && p.tma_a &&
+  const bool pair = pair_ok && bn == 256 && (deep || variant == 1) && p.tma_a && variant != 3 &&
                     (long long)ceil_div(p.M, 2 * kBM) * ceil_div(p.N, bn) >= sm_count() / 2;
   // Tail split: a pair launch whose tiles do not fill its last wave (res5's 392 tiles on 74
   // SM pairs: 6 waves for 5.3 waves of work) runs the whole waves as pairs and hands the
@@ -810,6 +931,7 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
     case 64: return launch<64, 6, false>(tmap, tmap_a, p, st);
     case 128: return launch<128, 5, false>(tmap, tmap_a, p, st);
     case 256:
+      if (pair && !deep) return launch<256, 5, true>(tmap, tmap_a, p, st);
       if (pair) return launch<256, 6, true>(tmap, tmap_a, p, st);
       return deep ? launch<256, 4, false>(tmap, tmap_a, p, st)
                   : launch<256, 3, false>(tmap, tmap_a, p, st);

@@ -229,6 +229,21 @@ typedef struct cmr_conv_desc {
  * tests).  Process-wide; returns the previous setting. */
 int cmr_set_im2col_tma(int on);
 
+/* Measurement knob: tile-configuration override of cmr_conv_gemm_tc for same-box A/B runs of
+ * single layers (tools/conv_shape_bench.py).  0 = the dispatch described above (default);
+ * 1 = CTA pairs also for short reductions (5 stages, 3 epilogue groups); 2 = the long-reduction
+ * configuration (pairs, 6 stages, 2 groups) for every 256-wide launch; 3 = single CTAs with
+ * 4 stages and 2 groups; + 16 = the epilogue reads no addend / mask; + 32 = the epilogue does not
+ * store (probes: the results are wrong).  Process-wide; returns the previous setting. */
+int cmr_set_conv_variant(int variant);
+
+/* Measurement knob: when `buf` (device memory, 8 int64 per CTA of the launch, i.e. 8 * 148
+ * words) is non-NULL every following cmr_conv_gemm_tc launch writes, per CTA, the SM cycles its
+ * roles spent waiting: [0] MMA issuer for a free accumulator, [1] MMA issuer for operand
+ * stages, [2] MMA issuer total, [3] TMA producer for free stages, [4] first epilogue warp for
+ * finished accumulators, [5] first epilogue warp total, [6] tiles.  NULL switches it off. */
+int cmr_set_conv_debug(long long* buf);
+
 int cmr_conv_gemm_tc(const cmr_conv_desc* desc, const float* a, const float* w,
                      float* d, const float* scale, const float* bias,
                      const float* addend, const float* mask, void* stream);
