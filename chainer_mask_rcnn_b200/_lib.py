@@ -73,6 +73,10 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p]),
     'cmr_conv_gemm_tc_ex': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    'cmr_conv_gemm_ws_bytes': (c_size_t, []),
+    'cmr_conv_gemm_tc_ws': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                    c_size_t, c_void_p]),
     'cmr_conv_wgrad_tc': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'cmr_round_tf32': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     'cmr_conv_wgrad_tc_fixed': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

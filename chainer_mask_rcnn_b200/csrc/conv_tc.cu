@@ -66,9 +66,15 @@ struct ConvGemmParams {
   int tma_a;   // A tiles by TMA: 1 = im2col-mode map, 2 = tiled-mode map (plain matrix);
                // 0 = cp.async gathers
   int epi_groups;   // epilogue warps per TMEM lane quarter: 3 with TMA A tiles, else 2
+  // K-split tail (see cmr_conv_gemm_tc_ws): tiles >= tail_begin (a multiple of the slot
+  // count) are each computed by tail_splits slots, one K-part of tail_kb k-blocks each
+  int tail_begin, tail_rounds, tail_splits, tail_items, tail_kb;
+  float4* ws;       // partial accumulators of the tail parts
   long long* dbg;   // measurement only: per-CTA wait-cycle counters (cmr_set_conv_debug)
   int probe;        // measurement only (cmr_set_conv_variant): 1 = the epilogue does not store
   double alg_bytes; // host only: algorithmic HBM bytes of the launch (profiling)
+  void* ws_base;    // host only: caller's workspace (cmr_conv_gemm_tc_ws), may be NULL
+  size_t ws_bytes;
 };
 
 constexpr int kBM = 128;
@@ -103,6 +109,11 @@ struct SmemLayout {
 // register budget (128 registers, no spills).
 constexpr int kEpiPlain = 0, kEpiBcast = 1, kEpiTaps = 2;
 
+// K-split tail (cmr_conv_gemm_tc_ws): at most kSplitMax parts per tile, only for reductions of
+// at least kSplitMinKb k-blocks
+constexpr int kSplitMax = 4;
+constexpr int kSplitMinKb = 32;
+
 // Wait-cycle counters and probe bits of cmr_set_conv_debug / cmr_set_conv_variant: compiled
 // in only with -DCMR_CONV_INSTRUMENT=1 (build.py: CMR_CONV_INSTRUMENT=1 in the environment);
 // the product kernel carries none of it.
@@ -112,7 +123,9 @@ constexpr int kEpiPlain = 0, kEpiBcast = 1, kEpiTaps = 2;
 constexpr bool kInstr = CMR_CONV_INSTRUMENT != 0;
 
 
-template <int BN, int STAGES, bool PAIR, int EPI>
+// SPLIT: the instantiation with the K-split tail (cmr_conv_gemm_tc_ws); the common one carries
+// none of its code or registers.
+template <int BN, int STAGES, bool PAIR, int EPI, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)   // 4 warps per SM sub-partition: 128 registers
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_a, const ConvGemmParams p) {
@@ -137,6 +150,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0;
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // i-th work item of this CTA (pair): whole tiles tile0 + i * tile_step below tail_begin,
+  // then at most one K-part [kb0, kb1) of a tail tile (part >= 0).  Without a split tail
+  // tail_begin == total_tiles.  Every role walks the same sequence.
+  auto work_item = [&](int i, int& tile, int& kb0, int& kb1, int& part) -> bool {
+    tile = tile0 + i * tile_step;
+    kb0 = 0;
+    kb1 = num_kb;
+    part = -1;
+    if (!SPLIT) return tile < total_tiles;
+    if (tile < p.tail_begin) return true;
+    if (p.tail_splits <= 1 || i != p.tail_rounds || tile0 >= p.tail_items) return false;
+    tile = p.tail_begin + tile0 / p.tail_splits;
+    part = tile0 % p.tail_splits;
+    kb0 = part * p.tail_kb;
+    kb1 = min(num_kb, kb0 + p.tail_kb);
+    return true;
+  };
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap_b);
@@ -223,7 +253,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       uint32_t it = 0;
       long long w_empty = 0;
       const int cpt = p.in_c / kBK;  // k-blocks per filter tap
-      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      int tile, kb0, kb1, part;
+      for (int wi = 0; work_item(wi, tile, kb0, kb1, part); ++wi) {
         const int n0 = (tile % p.n_tiles) * BN;
         // top-left input coordinate of the first convolution position of this CTA's rows
         const int m0 = (tile / p.n_tiles) * kTileM + (int)cta_rank * kBM;
@@ -231,8 +262,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
         const int rem = m0 - img * ohw;
         const int oy = rem / p.out_w;
         const int h0 = oy * p.stride - p.pad, w0 = (rem - oy * p.out_w) * p.stride - p.pad;
-        int fr = 0, fs = 0, cb = 0;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int tap0 = kb0 / cpt;
+        int fr = tap0 / p.kw, fs = tap0 - fr * p.kw, cb = kb0 - tap0 * cpt;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
           if (kInstr && p.dbg) {
@@ -293,7 +325,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     long long w_tmem = 0, w_full = 0;
     const long long t_start = (kInstr && p.dbg) ? clock64() : 0;
     if (!PAIR || cta_rank == 0) {   // the leader CTA issues for the pair
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
+    int tile, kb0, kb1, part;
+    for (int wi = 0; work_item(wi, tile, kb0, kb1, part); ++wi, ++tc_) {
       const uint32_t buf = tc_ & 1;
       if (kInstr && p.dbg) {
         const long long c0 = clock64();
@@ -304,7 +337,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
       }
       tc_fence_after();
       const uint32_t acc = tmem_base + buf * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         const uint32_t phase = (it / STAGES) & 1;
         if (kInstr && p.dbg) {
@@ -321,8 +354,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
               make_smem_desc_sw128(smem_base + L::kBOff + s * L::kBBytes, 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {  // 8 tf32 = 32 bytes per MMA -> +2 (16 B units)
-            if (PAIR) umma_tf32_pair(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t accumulate = (kb != kb0 || k != 0) ? 1u : 0u;
+            if (PAIR) umma_tf32_pair(acc, da + 2 * k, db + 2 * k, idesc, accumulate);
+            else umma_tf32(acc, da + 2 * k, db + 2 * k, idesc, accumulate);
           }
           if (PAIR) umma_commit_pair(&empty_bar[s], (uint16_t)3);
           else umma_commit(&empty_bar[s]);
@@ -379,7 +413,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     uint32_t tc_ = 0;
     long long w_acc = 0;
     const long long t_start = (kInstr && p.dbg) ? clock64() : 0;
-    for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tc_) {
+    int tile, kb0, kb1, part;
+    for (int wi = 0; work_item(wi, tile, kb0, kb1, part); ++wi, ++tc_) {
       const int m0 = (tile / p.n_tiles) * kTileM + (int)cta_rank * kBM;
       const int n0 = (tile % p.n_tiles) * BN;
       const uint32_t buf = tc_ & 1;
@@ -471,6 +506,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
           float4 o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = (i & 1) ? xr1[(i - 1) * 32] : xr0[i * 32];
+          if (SPLIT && part >= 0) {
+            // K-part of a tail tile: the raw partial sums go to the workspace in this layout
+            // ((tail tile, part, CTA of the pair, lane quarter, chunk) blocks of 8 x 32 float4);
+            // conv_tail_finish_kernel adds the parts and runs the epilogue
+            float4* dst = p.ws + ((((size_t)(tile - p.tail_begin) * p.tail_splits + part) *
+                                       (PAIR ? 2 : 1) + cta_rank) * 4 + q) * (kChunks * 256) +
+                          chunk * 256 + lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i * 32] = o[i];
+            continue;
+          }
           if (affine) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -572,6 +618,82 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b,
     if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// K-split tail, second step: adds the K-parts of every tail tile in part order and runs the
+// epilogue of conv_gemm_tc_kernel on the sums (same operations in the same order).  One thread
+// per float4 of the workspace layout written there.
+__global__ void __launch_bounds__(256)
+conv_tail_finish_kernel(const ConvGemmParams p, int bn, int ranks, int n_tail_tiles) {
+  const int chunks = bn / 32;
+  const size_t total = (size_t)n_tail_tiles * ranks * 4 * chunks * 256;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int lane = (int)(e & 31);
+  const int i = (int)((e >> 5) & 7);
+  size_t r = e >> 8;
+  const int chunk = (int)(r % chunks); r /= chunks;
+  const int q = (int)(r & 3); r >>= 2;
+  const int rank = (int)(r % ranks);
+  const int tt = (int)(r / ranks);
+  const int tile = p.tail_begin + tt;
+  const int row = (tile / p.n_tiles) * (kBM * ranks) + rank * kBM + q * 32 + 4 * i + (lane >> 3);
+  const int ng = (tile % p.n_tiles) * bn + chunk * 32 + (lane & 7) * 4;
+  if (row >= p.M || ng >= p.N) return;
+  const size_t part_stride = (size_t)ranks * 4 * chunks * 256;
+  const float4* src = p.ws + (size_t)tt * p.tail_splits * part_stride +
+                      ((size_t)(rank * 4 + q) * chunks + chunk) * 256 + i * 32 + lane;
+  float4 o = __ldcg(src);
+  for (int pp = 1; pp < p.tail_splits; ++pp) {
+    const float4 u = __ldcg(src + pp * part_stride);
+    o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+  }
+  const int tap = p.tap_cols > 0 ? (ng - (lane & 7) * 4) / p.tap_cols : 0;
+  const int n = ng - tap * p.tap_cols;
+  int off;
+  {
+    const int ohw = p.out_h * p.out_w;
+    const int img = row / ohw;
+    const int rem = row - img * ohw;
+    const int oy = rem / p.out_w;
+    const int ox = rem - oy * p.out_w;
+    off = ((img * p.d_h + oy * p.d_stride + p.d_oy) * p.d_w + ox * p.d_stride + p.d_ox) * p.d_ld +
+          ((tap >> 1) * p.d_w + (tap & 1)) * p.d_ld + n;
+  }
+  if (p.scale || p.bias) {
+    const float4 sc = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + n))
+                              : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 bi = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x = fmaf(o.x, sc.x, bi.x); o.y = fmaf(o.y, sc.y, bi.y);
+    o.z = fmaf(o.z, sc.z, bi.z); o.w = fmaf(o.w, sc.w, bi.w);
+  }
+  float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.addend) ad = __ldg(reinterpret_cast<const float4*>(p.addend + off));
+  if (p.bcast) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(
+        p.bcast + (size_t)(row / p.bcast_group) * p.N + n));
+    if (p.addend) {
+      ad.x = fmaf(bv.x, p.bcast_scale, ad.x); ad.y = fmaf(bv.y, p.bcast_scale, ad.y);
+      ad.z = fmaf(bv.z, p.bcast_scale, ad.z); ad.w = fmaf(bv.w, p.bcast_scale, ad.w);
+    } else {
+      o.x = fmaf(bv.x, p.bcast_scale, o.x); o.y = fmaf(bv.y, p.bcast_scale, o.y);
+      o.z = fmaf(bv.z, p.bcast_scale, o.z); o.w = fmaf(bv.w, p.bcast_scale, o.w);
+    }
+  }
+  if (p.addend) { o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w; }
+  if (p.relu) {
+    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+  }
+  if (p.mask) {
+    const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask + off));
+    o.x = mk.x > 0.f ? o.x : 0.f; o.y = mk.y > 0.f ? o.y : 0.f;
+    o.z = mk.z > 0.f ? o.z : 0.f; o.w = mk.w > 0.f ? o.w : 0.f;
+  }
+  if (p.round_out) {
+    o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+  }
+  *reinterpret_cast<float4*>(p.d + off) = o;
 }
 
 // ------------------------------------------------------------------ host ----
@@ -708,6 +830,43 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
   const long long tiles = (long long)q.m_tiles * q.n_tiles;
   const int slots = PAIR ? sm_count() / 2 : sm_count();
   const int grid = (int)(tiles < slots ? tiles : slots) * (PAIR ? 2 : 1);
+  // K-split tail: when the tiles leave a last wave that fills at most half of the slots, each
+  // of its tiles is computed by several slots (a K range each); the partial sums go through
+  // the caller's workspace and conv_tail_finish_kernel adds them and runs the epilogue -- the
+  // partial wave then lasts 1 / splits of a tile (+ the small second launch)
+  q.tail_begin = (int)tiles;
+  q.tail_rounds = 0; q.tail_splits = 1; q.tail_items = 0; q.tail_kb = 0;
+  q.ws = nullptr;
+  static int split_ok = -1;
+  if (split_ok < 0) {
+    const char* e = getenv("CMR_CONV_SPLIT_TAIL");
+    split_ok = e ? atoi(e) : 1;
+  }
+  const int num_kb = p.K / kBK;
+  const bool aligned = (p.d_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
+                       (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0) &&
+                       (!p.mask || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
+  long long rem = 0;
+  constexpr bool kHasSplit = PAIR && STAGES == 6;   // (the long-reduction pair kernels)
+  if (kHasSplit && split_ok && p.ws_base && p.tma_a && aligned && p.N % 32 == 0 &&
+      num_kb >= kSplitMinKb) {
+    const long long full = tiles / slots;
+    rem = tiles % slots;
+    if (full >= 1 && rem > 0 && rem * 2 <= slots) {
+      int splits = (int)(slots / rem) < kSplitMax ? (int)(slots / rem) : kSplitMax;
+      const int tail_kb = ceil_div(num_kb, splits);
+      splits = ceil_div(num_kb, tail_kb);
+      const size_t need = (size_t)rem * splits * (PAIR ? 2 : 1) * kBM * BN * 4;
+      if (splits > 1 && need <= p.ws_bytes) {
+        q.tail_begin = (int)(full * slots);
+        q.tail_rounds = (int)full;
+        q.tail_splits = splits;
+        q.tail_items = (int)rem * splits;
+        q.tail_kb = tail_kb;
+        q.ws = reinterpret_cast<float4*>(p.ws_base);
+      }
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -726,8 +885,32 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
   // (TF32 ~706 TFLOP/s over ~6.45 TB/s measured on this pool: 110 FLOP per byte)
   if (flops >= 110.0 * p.alg_bytes) prof_tag(kProfConvTensorBound, flops);
   else prof_tag(kProfConvHbmBound, p.alg_bytes);
-  cudaError_t e =
-      cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI>, tmap, tmap_a, q);
+  cudaError_t e;
+  if constexpr (kHasSplit) {
+    if (q.tail_splits > 1) {
+      static bool configured_split = false;
+      if (!configured_split) {
+        CMR_CUDA_TRY(cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI, true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          L::dynamic_bytes(3) <= 232448 ? L::dynamic_bytes(3)
+                                                                        : L::dynamic_bytes(2)));
+        configured_split = true;
+      }
+      e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI, true>, tmap, tmap_a,
+                             q);
+    } else {
+      e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI, false>, tmap,
+                             tmap_a, q);
+    }
+  } else {
+    e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, STAGES, PAIR, EPI, false>, tmap, tmap_a,
+                           q);
+  }
+  if (e == cudaSuccess && q.tail_splits > 1) {
+    const int ranks = PAIR ? 2 : 1;
+    const size_t total = (size_t)rem * ranks * 4 * (BN / 32) * 256;
+    conv_tail_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, BN, ranks, (int)rem);
+  }
   prof_end(st);
   CMR_CUDA_TRY(e);
   CMR_LAUNCH_CHECK();
@@ -774,6 +957,19 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
                                    float* d, const float* scale, const float* bias,
                                    const float* addend, const float* mask, const float* bcast,
                                    int bcast_group, float bcast_scale, void* stream) {
+  return cmr_conv_gemm_tc_ws(c, a, w, d, scale, bias, addend, mask, bcast, bcast_group,
+                             bcast_scale, nullptr, 0, stream);
+}
+
+extern "C" size_t cmr_conv_gemm_ws_bytes(void) {
+  return (size_t)sm_count() * kBM * 256 * 4;   // one 128 x 256 partial tile per SM
+}
+
+extern "C" int cmr_conv_gemm_tc_ws(const cmr_conv_desc* c, const float* a, const float* w,
+                                   float* d, const float* scale, const float* bias,
+                                   const float* addend, const float* mask, const float* bcast,
+                                   int bcast_group, float bcast_scale, void* ws, size_t ws_bytes,
+                                   void* stream) {
   CMR_REQUIRE(c && a && w && d);
   CMR_REQUIRE(!bcast || (bcast_group >= 1 && (reinterpret_cast<uintptr_t>(bcast) & 15) == 0 &&
                          c->n % 4 == 0));
@@ -807,6 +1003,8 @@ extern "C" int cmr_conv_gemm_tc_ex(const cmr_conv_desc* c, const float* a, const
                          mn * (1 + (addend != nullptr) + (mask != nullptr)));
   }
   p.bcast = bcast; p.bcast_group = bcast_group; p.bcast_scale = bcast_scale;
+  p.ws_base = ws; p.ws_bytes = ws ? ws_bytes : 0;
+  CMR_REQUIRE(!ws || (reinterpret_cast<uintptr_t>(ws) & 15) == 0);
   p.relu = c->relu; p.round_out = c->round_tf32;
   CMR_REQUIRE(p.d_stride >= 1 && p.tap_cols >= 0);
   if (p.tap_cols > 0) {   // fused 2x2 stride-2 deconvolution: four column blocks of tap_cols

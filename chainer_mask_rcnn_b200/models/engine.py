@@ -44,14 +44,29 @@ def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=N
     desc = _lib.ConvDesc(B, H, W, in_c, in_ld, oh, ow, kh, kw, stride, pad, n, dh, dw, dld,
                          d_stride, d_off[0], d_off[1], int(relu), int(round_out), tile_n,
                          tap_cols)
-    if bcast is None:
-        _lib.call('cmr_conv_gemm_tc', ctypes.byref(desc), _p(x), _p(w), _p(out), _p(scale),
-                  _p(bias), _p(addend), _p(mask), stream())
-    else:       # + row-group broadcast term (see cmr_conv_gemm_tc_ex)
-        _lib.call('cmr_conv_gemm_tc_ex', ctypes.byref(desc), _p(x), _p(w), _p(out), _p(scale),
-                  _p(bias), _p(addend), _p(mask), _p(bcast), int(bcast_group),
-                  float(bcast_scale), stream())
+    ws = conv_workspace(x.device)
+    _lib.call('cmr_conv_gemm_tc_ws', ctypes.byref(desc), _p(x), _p(w), _p(out), _p(scale),
+              _p(bias), _p(addend), _p(mask), _p(bcast), int(bcast_group), float(bcast_scale),
+              _p(ws), ws.numel() if ws is not None else 0, stream())
     return out
+
+
+_conv_ws = {}
+
+
+def conv_workspace(device):
+    """The K-split-tail workspace of cmr_conv_gemm_tc_ws for the current stream (one per
+    stream: launches on different streams may run at the same time).  Allocated
+    on first use -- eagerly, i.e. in the warm-up step that precedes a graph capture."""
+    key = (torch.cuda.current_stream(device).cuda_stream, device.index)
+    ws = _conv_ws.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None         # (never allocate from a graph's private pool: no split here)
+        n = int(_lib.load().cmr_conv_gemm_ws_bytes())
+        ws = torch.empty((n,), dtype=torch.uint8, device=device)
+        _conv_ws[key] = ws
+    return ws
 
 
 class _GradSideStream(object):

@@ -260,6 +260,21 @@ int cmr_conv_gemm_tc_ex(const cmr_conv_desc* desc, const float* a, const float* 
                         const float* addend, const float* mask, const float* bcast,
                         int bcast_group, float bcast_scale, void* stream);
 
+/* Same, with a caller-owned workspace that enables the K-split tail: when the launch's tiles
+ * leave a last wave that fills at most half of the SM pairs (e.g. res5's 392 pair tiles on 74
+ * SM pairs: 5.3 waves; CTA-pair launches with K >= 1024 only), every tile of that wave is
+ * computed by up to 4 CTA pairs, one K range each; the partial sums go through `ws` and a small second kernel adds them in part order (a
+ * fixed sum: results do not depend on timing) and runs the epilogue.  `ws`: device memory of
+ * at least cmr_conv_gemm_ws_bytes() bytes, 16-byte aligned, used by one launch at a time --
+ * one workspace per stream.  ws == NULL (or too small, or a launch the split does not apply
+ * to): exactly cmr_conv_gemm_tc_ex.  CMR_CONV_SPLIT_TAIL=0 in the environment disables it. */
+size_t cmr_conv_gemm_ws_bytes(void);
+int cmr_conv_gemm_tc_ws(const cmr_conv_desc* desc, const float* a, const float* w,
+                        float* d, const float* scale, const float* bias,
+                        const float* addend, const float* mask, const float* bcast,
+                        int bcast_group, float bcast_scale, void* ws, size_t ws_bytes,
+                        void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Weight gradient on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate):
  *   gw[i, gw_col0 + j] += row_scale[i] * sum over pixels (b, oy, ox) of

@@ -240,3 +240,51 @@ def test_split_tf32x3_and_fp32_level_convolution():
     p3 = E.split3(px, c_pad=32)
     assert p3.shape == (5, 7, 96) and float(p3[..., 3:32].abs().max()) == 0.
     assert torch.equal(p3[..., :3], round_tf32(px.clone()))
+
+
+@pytest.mark.parametrize('geom', [
+    # (B, H, W, C, N, k, pad): tiles leave a last wave that fills less than half of the SMs
+    (430, 7, 7, 1024, 256, 1, 0),      # 83 pair tiles of 256 x 256 on 74 SM pairs, 4 K-parts
+    (186, 7, 7, 128, 256, 3, 1),       # 3x3, 36 pair tiles ... single wave: no split (control)
+    (4, 75, 76, 1024, 128, 1, 0),      # 179 single-CTA tiles: not a pair launch, no split (control)
+    (410, 7, 7, 512, 512, 3, 1),       # 79 x 2 pair tiles, im2col K ranges starting mid-filter
+])
+def test_k_split_tail_matches_unsplit(geom, a_operand_path):
+    """cmr_conv_gemm_tc_ws: the tiles of a short last wave computed as K-parts through the
+    workspace give the un-split kernel's result up to the fp32 summation order, for the forward
+    epilogue (affine, residual, ReLU, tf32 rounding) and the backward one (addend, mask)."""
+    B, H, W, C, N, k, pad = geom
+    g = torch.Generator(device='cuda').manual_seed(21)
+    x = round_tf32(torch.randn((B, H, W, C), device='cuda', generator=g))
+    w = round_tf32(torch.randn((N, k, k, C), device='cuda', generator=g) / (k * C ** 0.5))
+    scale = torch.rand((N,), device='cuda', generator=g) + 0.5
+    bias = torch.randn((N,), device='cuda', generator=g)
+    addend = torch.randn((B, H, W, N), device='cuda', generator=g)
+    mask = torch.randn((B, H, W, N), device='cuda', generator=g)
+    ws = torch.empty((int(_lib.load().cmr_conv_gemm_ws_bytes()),), dtype=torch.uint8,
+                     device='cuda')
+
+    def run(ws_t, **kw):
+        d = torch.full((B, H, W, N), float('nan'), device='cuda')
+        desc = _lib.ConvDesc(B, H, W, C, C, H, W, k, k, 1, pad, N, H, W, N, 1, 0, 0,
+                             int(kw.get('relu', False)), int(kw.get('round_out', False)), 0)
+        _lib.call('cmr_conv_gemm_tc_ws', ctypes.byref(desc), _lib.ptr(x), _lib.ptr(w),
+                  _lib.ptr(d), _lib.ptr(kw.get('scale')), _lib.ptr(kw.get('bias')),
+                  _lib.ptr(kw.get('addend')), _lib.ptr(kw.get('mask')), None, 1, 0.0,
+                  _lib.ptr(ws_t), ws_t.numel() if ws_t is not None else 0, _lib.stream_ptr())
+        return d
+
+    base = ref_conv(x, w, 1, pad)
+    for kw, want in ((dict(scale=scale, bias=bias, addend=addend, relu=True),
+                      torch.relu(base * scale + bias + addend)),
+                     (dict(addend=addend, mask=mask), (base + addend) * (mask > 0)),
+                     (dict(), base)):
+        plain = run(None, **kw)
+        split = run(ws, **kw)
+        assert torch.isfinite(split).all()
+        assert rel(split, plain) <= 1e-5      # (the tensor core adds with truncation)
+        assert rel(split, want) <= 1e-4
+        again = run(ws, **kw)
+        assert torch.equal(split, again)          # fixed summation order
+    got = run(ws, round_out=True)
+    assert torch.equal(got, round_tf32(got))
