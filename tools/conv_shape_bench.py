@@ -101,6 +101,68 @@ def run_shape(name, variant, reps=8, iters=5):
             'dbg': dbg, 'us': best * 1e3, 'tflops': flops / best / 1e9, 'gbs': nbytes / best / 1e6}
 
 
+# name: (B, H, W, cout(rows), cin(cols), k, pad)   weight gradient of a stride-1 convolution
+WGRAD_SHAPES = {
+    'w_res5_3x3': (1024, 7, 7, 512, 512, 3, 1),
+    'w_res5_conv3': (1024, 7, 7, 2048, 512, 1, 0),
+    'w_res5_conv1': (1024, 7, 7, 512, 2048, 1, 0),
+    'w_rpn_3x3': (2, 51, 84, 1024, 1024, 3, 1),
+    'w_res4_3x3': (2, 51, 84, 256, 256, 3, 1),
+    'w_res4_conv3': (2, 51, 84, 1024, 256, 1, 0),
+    'w_res4_conv1': (2, 51, 84, 256, 1024, 1, 0),
+    'w_res3_3x3': (2, 101, 167, 128, 128, 3, 1),
+    'w_res3_conv3': (2, 101, 167, 512, 128, 1, 0),
+    'w_res3_conv1': (2, 101, 167, 128, 512, 1, 0),
+    'w_mask_head': (1024, 14, 14, 80, 256, 1, 0),
+}
+
+
+def run_wgrad(name, reps=8, iters=5):
+    B, H, W, rows, cols, k, pad = WGRAD_SHAPES[name]
+    M = B * H * W
+    per_set = 4 * M * (rows + cols)
+    n_sets = max(2, min(reps, -(-(300 << 20) // per_set)))
+    sets = []
+    for _ in range(n_sets):
+        gy = torch.randn((B, H, W, rows), device='cuda')
+        x = torch.randn((B, H, W, cols), device='cuda')
+        E.round_tf32(gy, gy)
+        E.round_tf32(x, x)
+        sets.append((gy, x))
+    gw = torch.zeros((rows, k * k * cols), device='cuda')
+
+    def launch(i):
+        gy, x = sets[i % n_sets]
+        E.wgrad_tap(gy, x, gw, rows, cols, (H, W), k * k * cols, x_off=(-pad, -pad), taps=(k, k))
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(n_sets):
+            launch(i)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            launch(i)
+    g.replay()
+    torch.cuda.synchronize()
+    best = None
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        t = a.elapsed_time(b) / reps
+        best = t if best is None else min(best, t)
+    flops = 2.0 * M * rows * cols * k * k
+    nbytes = per_set + 4 * rows * cols * k * k
+    return {'shape': name, 'variant': 0, 'M': M, 'N': rows, 'K': cols * k * k, 'flags': 'wgrad',
+            'dbg': None, 'us': best * 1e3, 'tflops': flops / best / 1e9, 'gbs': nbytes / best / 1e6}
+
+
 def stream_rates():
     """DRAM rates of plain element-wise passes over res5-sized tensors (the read/write mixes of
     the conv epilogues), for comparison."""
@@ -129,12 +191,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--out', default=None)
     ap.add_argument('--variants', default='0,1,2,3')
-    ap.add_argument('--shapes', default=','.join(SHAPES))
+    ap.add_argument('--shapes', default=','.join(list(SHAPES) + list(WGRAD_SHAPES)))
     ap.add_argument('--reps', type=int, default=8)
     args = ap.parse_args()
     rows = []
     print('stream GB/s:', stream_rates(), flush=True)
     for name in args.shapes.split(','):
+        if name in WGRAD_SHAPES:
+            r = run_wgrad(name, reps=args.reps)
+            rows.append(r)
+            print('%-18s  %7.1f us %5.0f TF %5.0f GB/s' % (name, r['us'], r['tflops'], r['gbs']),
+                  flush=True)
+            continue
         line = '%-18s' % name
         for v in [int(t) for t in args.variants.split(',')]:
             r = run_shape(name, v, reps=args.reps)

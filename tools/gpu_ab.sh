@@ -1,5 +1,7 @@
 #!/bin/bash
-# usage: tools/gpu_ab.sh [bench args]   -- same-box A/B of bench.py: tools/ab/conv_tc_old.cu.txt vs the tree's conv_tc.cu
+# usage: tools/gpu_ab.sh [bench args]   -- same-box A/B of bench.py: an older conv_tc.cu (put it at
+# tools/ab/conv_tc_old.cu.txt first: git show REF:chainer_mask_rcnn_b200/csrc/conv_tc.cu, plus stubs for
+# entry points REF lacks) vs the tree's conv_tc.cu, twice each
 mkdir -p gpurun_out
 run() {
   python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || tail -5 gpurun_out/build.log
