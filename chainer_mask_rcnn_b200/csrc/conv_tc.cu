@@ -837,18 +837,13 @@ int launch_b(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const ConvGemmP
   q.tail_begin = (int)tiles;
   q.tail_rounds = 0; q.tail_splits = 1; q.tail_items = 0; q.tail_kb = 0;
   q.ws = nullptr;
-  static int split_ok = -1;
-  if (split_ok < 0) {
-    const char* e = getenv("CMR_CONV_SPLIT_TAIL");
-    split_ok = e ? atoi(e) : 1;
-  }
   const int num_kb = p.K / kBK;
   const bool aligned = (p.d_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
                        (!p.addend || (reinterpret_cast<uintptr_t>(p.addend) & 15) == 0) &&
                        (!p.mask || (reinterpret_cast<uintptr_t>(p.mask) & 15) == 0);
   long long rem = 0;
   constexpr bool kHasSplit = PAIR && STAGES == 6;   // (the long-reduction pair kernels)
-  if (kHasSplit && split_ok && p.ws_base && p.tma_a && aligned && p.N % 32 == 0 &&
+  if (kHasSplit && p.ws_base && p.tma_a && aligned && p.N % 32 == 0 &&
       num_kb >= kSplitMinKb) {
     const long long full = tiles / slots;
     rem = tiles % slots;

@@ -6,6 +6,7 @@ Everything the network computes runs in libcmr_b200's kernels; torch is used for
 device memory, streams and views only.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -52,17 +53,40 @@ def conv_gemm(x, w, n, kh=1, kw=1, stride=1, pad=0, out=None, scale=None, bias=N
 
 
 _conv_ws = {}
+_ws_slot = [0]
+# off by default: measured 1-4 % faster per launch alone, 0.5 % slower inside the train step
+_split_tail = [os.environ.get('CMR_CONV_SPLIT_TAIL', '0') == '1']
+
+
+class ws_slot(object):
+    """Selects the K-split-tail workspace for the conv_gemm calls inside the block.  A
+    workspace serves one launch at a time, so every chain of convolutions that may run next to
+    another one (the RPN branch on its side stream) uses its own slot; the main chain is slot 0.
+    (Slots rather than stream handles: a CUDA-graph capture runs on its own capture stream.)"""
+
+    def __init__(self, slot):
+        self.slot = slot
+
+    def __enter__(self):
+        self.old = _ws_slot[0]
+        _ws_slot[0] = self.slot
+
+    def __exit__(self, *exc):
+        _ws_slot[0] = self.old
 
 
 def conv_workspace(device):
-    """The K-split-tail workspace of cmr_conv_gemm_tc_ws for the current stream (one per
-    stream: launches on different streams may run at the same time).  Allocated
-    on first use -- eagerly, i.e. in the warm-up step that precedes a graph capture."""
-    key = (torch.cuda.current_stream(device).cuda_stream, device.index)
+    """The K-split-tail workspace of cmr_conv_gemm_tc_ws for the current slot (see ws_slot).
+    None unless CMR_CONV_SPLIT_TAIL=1.  Allocated on first use -- eagerly, i.e. in the warm-up
+    step that precedes a graph capture; never from a graph's private pool (None: no split for
+    that launch)."""
+    if not _split_tail[0]:
+        return None
+    key = (device.index, _ws_slot[0])
     ws = _conv_ws.get(key)
     if ws is None:
         if torch.cuda.is_current_stream_capturing():
-            return None         # (never allocate from a graph's private pool: no split here)
+            return None
         n = int(_lib.load().cmr_conv_gemm_ws_bytes())
         ws = torch.empty((n,), dtype=torch.uint8, device=device)
         _conv_ws[key] = ws

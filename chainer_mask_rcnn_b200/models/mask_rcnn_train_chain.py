@@ -249,7 +249,7 @@ class MaskRCNNTrainChain(object):
         side = self._rpn_stream
         ready = torch.cuda.Event()
         ready.record()
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), E.ws_slot(1):
             side.wait_event(ready)
             gl, glab = self.anchor_target_creator(gt, anchor, img_size, seed,
                                                   seed_dev=self.seed_dev)

@@ -267,7 +267,10 @@ int cmr_conv_gemm_tc_ex(const cmr_conv_desc* desc, const float* a, const float* 
  * fixed sum: results do not depend on timing) and runs the epilogue.  `ws`: device memory of
  * at least cmr_conv_gemm_ws_bytes() bytes, 16-byte aligned, used by one launch at a time --
  * one workspace per stream.  ws == NULL (or too small, or a launch the split does not apply
- * to): exactly cmr_conv_gemm_tc_ex.  CMR_CONV_SPLIT_TAIL=0 in the environment disables it. */
+ * to): exactly cmr_conv_gemm_tc_ex.  (The Python engine passes a workspace only with
+ * CMR_CONV_SPLIT_TAIL=1: the split shortens its launches by 1-4 % when they run alone but
+ * measured 0.5 % slower inside the train step, whose side-stream weight gradients already
+ * fill those tails -- DESIGN.md section 3.) */
 size_t cmr_conv_gemm_ws_bytes(void);
 int cmr_conv_gemm_tc_ws(const cmr_conv_desc* desc, const float* a, const float* w,
                         float* d, const float* scale, const float* bias,
