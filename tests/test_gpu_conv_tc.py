@@ -288,3 +288,30 @@ def test_k_split_tail_matches_unsplit(geom, a_operand_path):
         assert torch.equal(split, again)          # fixed summation order
     got = run(ws, round_out=True)
     assert torch.equal(got, round_tf32(got))
+
+
+def test_engine_hands_out_one_split_tail_workspace_per_slot():
+    """models.engine: with the K-split tail switched on the convolutions of a chain get that
+    chain's workspace (E.ws_slot), results stay those of the un-split launch up to the
+    summation order and are identical from slot to slot."""
+    from chainer_mask_rcnn_b200.models import engine as E
+    g = torch.Generator(device='cuda').manual_seed(33)
+    x = round_tf32(torch.randn((430, 7, 7, 1024), device='cuda', generator=g))
+    w = round_tf32(torch.randn((256, 1, 1, 1024), device='cuda', generator=g) / 32)
+    old, old_ws = E._split_tail[0], dict(E._conv_ws)
+    try:
+        E._split_tail[0] = False
+        assert E.conv_workspace(x.device) is None
+        plain = E.conv_gemm(x, w, 256, relu=True, round_out=False)
+        E._split_tail[0] = True
+        E._conv_ws.clear()
+        split0 = E.conv_gemm(x, w, 256, relu=True, round_out=False)
+        with E.ws_slot(1):
+            split1 = E.conv_gemm(x, w, 256, relu=True, round_out=False)
+        assert sorted(k[1] for k in E._conv_ws) == [0, 1]
+    finally:
+        E._split_tail[0] = old
+        E._conv_ws.clear()
+        E._conv_ws.update(old_ws)
+    assert rel(split0, plain) <= 1e-5
+    assert torch.equal(split0, split1)
