@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '-Xcompiler', '-fPIC', '-shared',
 ]
+NVCC_FLAGS += os.environ.get('CMR_EXTRA_NVCC_FLAGS', '').split()   # (-D... for A/B builds)
 if os.environ.get('CMR_CONV_INSTRUMENT') == '1':     # measurement build (tools/conv_shape_bench.py)
     NVCC_FLAGS.append('-DCMR_CONV_INSTRUMENT=1')
 

@@ -726,6 +726,12 @@ __device__ __forceinline__ int tile_index(int c, int p, int PS) {
 
 // One CTA serves `cpc` consecutive channel chunks of its RoI, so the tap tables are built
 // once per cpc * CH channels (they are 15 % of the instructions when built per chunk).
+// resident CTAs per SM of the backward walker (A/B knob, -DCMR_CL_BWD_CTAS=2 measured: see DESIGN.md)
+#ifndef CMR_CL_BWD_CTAS
+#define CMR_CL_BWD_CTAS 3
+#endif
+constexpr int kClBwdCtas = CMR_CL_BWD_CTAS;
+
 template <int CH, bool kVec>
 __global__ void __launch_bounds__(256, 3)      // the staging tile allows three CTAs per SM
 roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
@@ -810,7 +816,7 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
 }
 
 template <int CH, bool kVec>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, kClBwdCtas)
 roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int groups, int cpc, int n_img) {
@@ -902,9 +908,23 @@ roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ 
 // fewer for wide ones).  Same products as the reference, merged weights (a few ulp).
 constexpr int kBlendSlots = 8;
 constexpr int kTwoPassThreads = 256;
-constexpr int kTwoPassGFloats = 11 * 1024;      // 44 KB of G per CTA; the rest of the SM's 256 KB stays L1 (pass A re-reads rows)
-constexpr int kTwoPassGSlack = 4;
-constexpr int kRowBatch = 3;                    // output rows whose loads are in flight together               // floats readable past the last plane
+// Two CTAs per SM (127 registers, no spills, none of the re-derived addresses of the 80-register
+// build), 60 KB of G, four rows per load batch: same-box A/B at R = 1000, forward GB/s: 3 CTAs /
+// 44 KB / 3 rows 1843, 2 CTAs 1956, + 60 KB 2069 (76 KB: 2070), + 4 rows 2104 (2 rows: 1997).
+// The macros exist for such A/B builds (build.py: CMR_EXTRA_NVCC_FLAGS, tools/roi_ab.sh).
+#ifndef CMR_TWO_PASS_CTAS
+#define CMR_TWO_PASS_CTAS 2
+#endif
+constexpr int kTwoPassCtas = CMR_TWO_PASS_CTAS;
+#ifndef CMR_TWO_PASS_G_KB
+#define CMR_TWO_PASS_G_KB 60
+#endif
+constexpr int kTwoPassGFloats = CMR_TWO_PASS_G_KB * 256;      // G per CTA; the rest of the SM's 256 KB stays L1 (pass A re-reads rows)
+constexpr int kTwoPassGSlack = 4;                             // floats readable past the last plane
+#ifndef CMR_TWO_PASS_ROW_BATCH
+#define CMR_TWO_PASS_ROW_BATCH 4
+#endif
+constexpr int kRowBatch = CMR_TWO_PASS_ROW_BATCH;      // output rows whose loads are in flight together
 
 struct AxisBlend {
   int first;                // index of the first feature row / column
@@ -984,7 +1004,7 @@ __device__ __forceinline__ void two_pass_b(const float* __restrict__ g0, float4*
 }
 
 template <int CH>
-__global__ void __launch_bounds__(kTwoPassThreads, 3)
+__global__ void __launch_bounds__(kTwoPassThreads, kTwoPassCtas)
 roi_align_cl2_fwd_kernel(const float4* __restrict__ src, const float* __restrict__ rois,
                          float* __restrict__ dst, int H, int W, int C, int outh, int outw,
                          float scale, int sampling_ratio, int groups, int cpc, int n_img) {
