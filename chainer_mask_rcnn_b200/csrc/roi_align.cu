@@ -726,11 +726,24 @@ __device__ __forceinline__ int tile_index(int c, int p, int PS) {
 
 // One CTA serves `cpc` consecutive channel chunks of its RoI, so the tap tables are built
 // once per cpc * CH channels (they are 15 % of the instructions when built per chunk).
-// resident CTAs per SM of the backward walker (A/B knob, -DCMR_CL_BWD_CTAS=2 measured: see DESIGN.md)
+// Backward walker: staging tile of 32 channels (128 threads, 64 registers, 29 KB: six to seven
+// CTAs = 24-28 warps per SM) and a grid of at least 96 CTAs per SM.  Same-box A/B at
+// R = 300 / 1000 / 2000 / 6000, GB/s: 64 channels, 3 CTAs of 256 threads, grid >= 8 per SM
+// 1382 / 1490 / 1468 / 1684; 2 CTAs 1107 / 1201 / 1188 / 1309 (it is latency-bound: warps
+// count); 32 channels with the old grid rule 1189 / 1373 / 1593 / 1824; grid >= 48 per SM
+// 1565 / 1716 / 1718 / 1823; >= 96: 1571 / 1736 / 1774 / 1860.  (Macros: A/B builds.)
 #ifndef CMR_CL_BWD_CTAS
-#define CMR_CL_BWD_CTAS 3
+#define CMR_CL_BWD_CTAS 6
 #endif
 constexpr int kClBwdCtas = CMR_CL_BWD_CTAS;
+#ifndef CMR_CL_BWD_CH
+#define CMR_CL_BWD_CH 32
+#endif
+constexpr int kClBwdChannels = CMR_CL_BWD_CH;   // channels per staging tile of the backward walker
+#ifndef CMR_CL_BWD_GRID
+#define CMR_CL_BWD_GRID 96
+#endif
+constexpr int kClBwdGridCtas = CMR_CL_BWD_GRID;  // CTAs per SM the grid should at least have
 
 template <int CH, bool kVec>
 __global__ void __launch_bounds__(256, 3)      // the staging tile allows three CTAs per SM
@@ -816,7 +829,7 @@ roi_align_cl_fwd_kernel(const float4* __restrict__ src, const float* __restrict_
 }
 
 template <int CH, bool kVec>
-__global__ void __launch_bounds__(256, kClBwdCtas)
+__global__ void __launch_bounds__(CH * 4, kClBwdCtas)
 roi_align_cl_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ rois,
                         float4* __restrict__ gx, int H, int W, int C, int outh, int outw,
                         float scale, int sampling_ratio, int groups, int cpc, int n_img) {
@@ -911,11 +924,16 @@ constexpr int kTwoPassThreads = 256;
 // Two CTAs per SM (127 registers, no spills, none of the re-derived addresses of the 80-register
 // build), 60 KB of G, four rows per load batch: same-box A/B at R = 1000, forward GB/s: 3 CTAs /
 // 44 KB / 3 rows 1843, 2 CTAs 1956, + 60 KB 2069 (76 KB: 2070), + 4 rows 2104 (2 rows: 1997).
+// A grid of at least 16 (instead of 8) CTAs per SM: 2138 (2197 at R = 2000, was 2095).
 // The macros exist for such A/B builds (build.py: CMR_EXTRA_NVCC_FLAGS, tools/roi_ab.sh).
 #ifndef CMR_TWO_PASS_CTAS
 #define CMR_TWO_PASS_CTAS 2
 #endif
 constexpr int kTwoPassCtas = CMR_TWO_PASS_CTAS;
+#ifndef CMR_TWO_PASS_GRID
+#define CMR_TWO_PASS_GRID 16
+#endif
+constexpr int kTwoPassGridCtas = CMR_TWO_PASS_GRID;   // CTAs per SM the grid should at least have
 #ifndef CMR_TWO_PASS_G_KB
 #define CMR_TWO_PASS_G_KB 60
 #endif
@@ -1191,24 +1209,23 @@ constexpr int kClChannels = 64;   // channels per CTA of the two kernels above
 
 bool cl_vec(int outh, int outw) { return (outw & 1) == 0 && ((outh * outw) & 3) == 0; }
 
-size_t cl_smem_bytes(int outh, int outw) {
+size_t cl_smem_bytes(int outh, int outw, int ch = kClChannels) {
   const int P = outh * outw;
   const int PS = cl_vec(outh, outw) ? (P + 31) / 32 * 32 : P + 1;
-  return sizeof(RoiTileSmem) + sizeof(float) * (size_t)kClChannels * PS +
-         sizeof(RowBlend) * (size_t)outh;
+  return sizeof(RoiTileSmem) + sizeof(float) * (size_t)ch * PS + sizeof(RowBlend) * (size_t)outh;
 }
 
-int cl_threads(int outh) {
-  int t = outh * (kClChannels / 4);
+int cl_threads(int outh, int ch = kClChannels) {
+  int t = outh * (ch / 4);
   t = (t + 31) / 32 * 32;
-  return t > 256 ? 256 : (t < 64 ? 64 : t);
+  return t > ch * 4 ? ch * 4 : (t < 64 ? 64 : t);
 }
 
 // Chunks per CTA: as many as keep >= 8 CTAs per SM in the grid (a power of two <= 16).
-int cl_chunks_per_cta(int R, int chunks) {
+int cl_chunks_per_cta(int R, int chunks, int ctas_per_sm = 8) {
   int cpc = 1;
   while (cpc < 16 && cpc * 2 <= chunks &&
-         (long long)R * ceil_div(chunks, cpc * 2) >= 8ll * sm_count())
+         (long long)R * ceil_div(chunks, cpc * 2) >= (long long)ctas_per_sm * sm_count())
     cpc *= 2;
   return cpc;
 }
@@ -1414,8 +1431,8 @@ template <bool kVec>
 int launch_cl_bwd(const float* gy, const float* rois, int R, int N, int H, int W, int C, int outh,
                   int outw, float spatial_scale, int sampling_ratio, float* gx_nhwc,
                   cudaStream_t st) {
-  const size_t smem = cl_smem_bytes(outh, outw);
-  int rc = cl_configure(roi_align_cl_bwd_kernel<kClChannels, kVec>, smem);
+  const size_t smem = cl_smem_bytes(outh, outw, kClBwdChannels);
+  int rc = cl_configure(roi_align_cl_bwd_kernel<kClBwdChannels, kVec>, smem);
   if (rc != CMR_OK) return rc;
   prof_begin(kProfRoiAlignApiBwd, roi_align_bytes(R, C, outh, outw, N, H, W), st);
   cudaError_t me = cudaMemsetAsync(gx_nhwc, 0, sizeof(float) * (size_t)N * C * H * W, st);
@@ -1424,9 +1441,10 @@ int launch_cl_bwd(const float* gy, const float* rois, int R, int N, int H, int W
     CMR_CUDA_TRY(me);
     return CMR_OK;
   }
-  const int chunks = ceil_div(C, kClChannels);
-  const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
-  roi_align_cl_bwd_kernel<kClChannels, kVec><<<R * groups, cl_threads(outh), smem, st>>>(
+  const int chunks = ceil_div(C, kClBwdChannels);
+  const int cpc = cl_chunks_per_cta(R, chunks, kClBwdGridCtas), groups = ceil_div(chunks, cpc);
+  roi_align_cl_bwd_kernel<kClBwdChannels, kVec>
+      <<<R * groups, cl_threads(outh, kClBwdChannels), smem, st>>>(
       gy, rois, reinterpret_cast<float4*>(gx_nhwc), H, W, C, outh, outw, spatial_scale,
       sampling_ratio, groups, cpc, N);
   prof_end(st);
@@ -1451,7 +1469,7 @@ extern "C" int cmr_roi_align_fwd_cl(const float* x_nhwc, int N, int H, int W, in
     int rc = cl_configure(roi_align_cl2_fwd_kernel<kClChannels>, smem);
     if (rc != CMR_OK) return rc;
     const int chunks = ceil_div(C, kClChannels);
-    const int cpc = cl_chunks_per_cta(R, chunks), groups = ceil_div(chunks, cpc);
+    const int cpc = cl_chunks_per_cta(R, chunks, kTwoPassGridCtas), groups = ceil_div(chunks, cpc);
     prof_begin(kProfRoiAlignApi, roi_align_bytes(R, C, outh, outw, N, H, W), st);
     roi_align_cl2_fwd_kernel<kClChannels><<<R * groups, kTwoPassThreads, smem, st>>>(
         reinterpret_cast<const float4*>(x_nhwc), rois, y, H, W, C, outh, outw, spatial_scale,
