@@ -112,6 +112,36 @@ def ncu_traffic(pattern, kernel_substr):
     return None, None
 
 
+def ncu_l2_delivery(pattern, kernel_substr):
+    """L2 -> SM bytes per L2 cycle of one launch (l1tex__m_xbar2l1tex_read_bytes.sum /
+    lts__cycles_active.avg) from the newest committed ncu raw page matching `pattern`, next to
+    the chip-wide ceiling /opt/skills/guides/B300_MICROARCH.md measures ("LTS throughput cap
+    ~6300 B/cycle, path-independent").  None when no page is there."""
+    import csv
+    import glob
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    for path in reversed(sorted(glob.glob(os.path.join(ROOT, 'profiles', pattern)))):
+        try:
+            with open(path, newline='') as f:
+                rows = list(csv.reader(f))
+            hdr, units = rows[0], rows[1]
+            ik = hdr.index('Kernel Name')
+            ib = hdr.index('l1tex__m_xbar2l1tex_read_bytes.sum')
+            ic = hdr.index('lts__cycles_active.avg')
+            it = hdr.index('gpu__time_duration.sum')
+            for row in rows[2:]:
+                if kernel_substr in row[ik]:
+                    nbytes = float(row[ib].replace(',', '')) * unit.get(units[ib], 1.0)
+                    cycles = float(row[ic].replace(',', ''))
+                    us = float(row[it].replace(',', ''))
+                    return {'bytes_per_l2_cycle': nbytes / cycles, 'cap_bytes_per_l2_cycle': 6300.0,
+                            'frac': nbytes / cycles / 6300.0, 'tb_per_s': nbytes / us / 1e6,
+                            'source': os.path.basename(path)}
+        except Exception:
+            continue
+    return None
+
+
 def synth_batch(seed, bs=BS):
     """SURVEY.md 8d synthetic inputs: U[0,255) - mean images; 40 instances per image with
     log-uniform sizes, uniform labels and filled-ellipse masks."""
@@ -363,7 +393,12 @@ def tensor_roofline(prof, pk, tf32, steps, ms_total, measured_in):
         'hbm_bound_launches': {'achieved': gb_h, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                'frac': gb_h / pk['hbm_gbs'],
                                'launches_per_step': cnt_h / steps,
-                               'ms_per_step': ms_h / steps},
+                               'ms_per_step': ms_h / steps,
+                               # what binds them after the epilogue rewrite:
+                               # operand delivery from L2, from the committed ncu page of the
+                               # largest such launch (res5 conv3 + residual)
+                               'l2_to_sm': ncu_l2_delivery('r*_ncu_conv1x1_raw.csv',
+                                                           'conv_gemm_tc_kernel')},
     }
     return rl
 
