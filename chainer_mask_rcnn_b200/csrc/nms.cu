@@ -232,6 +232,7 @@ nms_sweep_kernel(const unsigned long long* __restrict__ mask, const int* __restr
       const unsigned int rn_lo = __reduce_or_sync(0xffffffffu, (unsigned int)rn);
       const unsigned int rn_hi = __reduce_or_sync(0xffffffffu, (unsigned int)(rn >> 32));
       rn = ((unsigned long long)rn_hi << 32) | rn_lo;
+      __syncwarp();                 // every lane has read count_s before lane 0 replaces it
       if (lane == 0) {
         if (rn && cb + 1 < nb) or_shared(&remv[cb + 1], rn);
         kept_n[cur] = nk;
