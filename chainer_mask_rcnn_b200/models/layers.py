@@ -312,9 +312,13 @@ class BuildingBlock(object):
             x = b.forward(x)
         return x
 
-    def backward(self, g, input_is_relu):
+    def backward(self, g, input_is_relu, progress=None):
         """input_is_relu: whether the stage input is a ReLU output (False for the RoI
-        pool feeding res5)."""
+        pool feeding res5).  ``progress(block)`` is called after each block's backward pass
+        has been enqueued: the gradients of that block's parameters and of everything created
+        after it are then final once the weight-gradient side stream has drained."""
         for i in range(len(self.blocks) - 1, -1, -1):
             g = self.blocks[i].backward(g, input_is_relu or i > 0)
+            if progress is not None:
+                progress(self.blocks[i])
         return g

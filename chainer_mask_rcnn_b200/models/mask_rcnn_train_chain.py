@@ -40,16 +40,20 @@ class Loss(object):
 
     data = property(lambda self: self.array)
 
-    def backward(self, after_head=None):
+    supports_progress = True
+
+    def backward(self, after_head=None, progress=None):
         """Runs the backward schedule.  ``after_head``: optional callable invoked once the
         gradients of the RPN and RoI-head parameters are final (every kernel that writes them
         has been enqueued and joined onto the current stream) and before the backbone's
         backward pass is enqueued -- the data-parallel optimizer starts the all-reduce of
-        that bucket there, under the backbone's backward pass."""
+        that bucket there, under the backbone's backward pass.  ``progress(block)``: called
+        after each backbone block's backward pass has been enqueued (the optimizer cuts the
+        backbone's gradient exchange into pieces there)."""
         if self._backward_fn is None:
             raise RuntimeError('backward() was already called for this loss')
         fn, self._backward_fn = self._backward_fn, None
-        fn(after_head)
+        fn(after_head, progress)
 
     def item(self):
         return float(self.array.item())
@@ -321,7 +325,7 @@ class MaskRCNNTrainChain(object):
         self.outputs = dict(rpn_locs=rpn_locs, rpn_scores=rpn_scores, roi_cls_locs=cls_locs,
                             roi_scores=scores, roi_masks=masks)
 
-        def backward(after_head=None):
+        def backward(after_head=None, progress=None):
             # weight / bias gradients run on a side stream next to the data-gradient chain
             E.grad_side.begin()
             try:
@@ -341,7 +345,7 @@ class MaskRCNNTrainChain(object):
                     E.grad_side.join()
                     after_head()
                     E.grad_side.begin()
-                m.extractor.backward(g_feat)
+                m.extractor.backward(g_feat, progress)
             finally:
                 E.grad_side.join()
             if after_head is None:       # (a hook's owner finishes the two parts itself)

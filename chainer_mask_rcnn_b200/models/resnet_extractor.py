@@ -142,10 +142,11 @@ class ResNetExtractorBase(object):
         self.ctx.prepare(backward=False)
         return E.as_nchw_view(self.forward_nhwc(as_device_f32(x)))
 
-    def backward(self, g_feat):
-        """g_feat: dL/d(res4 output) * ReLU mask, NHWC, tf32-rounded."""
-        g = self.res4.backward(g_feat, input_is_relu=True)
-        self.res3.backward(g, input_is_relu=True)
+    def backward(self, g_feat, progress=None):
+        """g_feat: dL/d(res4 output) * ReLU mask, NHWC, tf32-rounded.  ``progress``: see
+        BuildingBlock.backward."""
+        g = self.res4.backward(g_feat, input_is_relu=True, progress=progress)
+        self.res3.backward(g, input_is_relu=True, progress=progress)
 
 
 class ResNet50Extractor(ResNetExtractorBase):

@@ -11,6 +11,8 @@ step is: ONE NCCL all-reduce (sum) over the gradient buffer + ONE fused kernel
 (cmr_sgd_momentum) that applies the 1/world_size mean, the weight decay, the
 momentum update and the parameter update.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -52,6 +54,9 @@ class MomentumSGD(object):
         self.target = None
         self.t = 0
         self._needs_broadcast = False
+        # update_overlapped: the backbone's gradient exchange goes in pieces of at least this
+        # many floats (0: one piece after the backward pass, the round-2a scheme)
+        self.backbone_chunk = int(float(os.environ.get('CMR_ALLREDUCE_CHUNK_MB', '16')) * (1 << 18))
 
     def setup(self, link):
         self.target = link
@@ -115,10 +120,42 @@ class MomentumSGD(object):
             if multi and heads.numel():
                 pending.append(dist.all_reduce(heads, group=self.comm.group, async_op=True))
 
-        loss.backward(after_head=after_head)
-        self.ctx.finish_grads(0, split)
-        if multi and backbone.numel():
-            pending.append(dist.all_reduce(backbone, group=self.comm.group, async_op=True))
+        # The backbone's bucket goes in pieces of >= backbone_chunk floats, each issued from the
+        # weight-gradient side stream as soon as the blocks it covers have been enqueued (the
+        # collective then waits for exactly those kernels, and the data-gradient chain on the
+        # main stream is not held up): R101's 108 MB of res4 gradients are exchanged under the
+        # rest of the backward pass instead of after it.
+        store = self.ctx.train
+        state = {'hi': split}
+
+        def exchange(lo, hi, on_side):
+            side = E.grad_side.stream if on_side and E.grad_side.active else None
+            if side is not None:
+                with torch.cuda.stream(side):
+                    self.ctx.finish_grads(lo, hi)
+                    pending.append(dist.all_reduce(self.ctx.grads[lo:hi], group=self.comm.group,
+                                                   async_op=True))
+            else:
+                self.ctx.finish_grads(lo, hi)
+                pending.append(dist.all_reduce(self.ctx.grads[lo:hi], group=self.comm.group,
+                                               async_op=True))
+
+        def progress(block):
+            if not multi or self.backbone_chunk <= 0:
+                return
+            off = store.specs[store.index[block.conv1.W]][2]
+            if state['hi'] - off >= self.backbone_chunk and off > 0:
+                exchange(off, state['hi'], True)
+                state['hi'] = off
+
+        if getattr(loss, 'supports_progress', False):
+            loss.backward(after_head=after_head, progress=progress)
+        else:
+            loss.backward(after_head=after_head)
+        if multi and state['hi'] > 0:
+            exchange(0, state['hi'], False)
+        else:
+            self.ctx.finish_grads(0, state['hi'])
         for work in pending:
             work.wait()                     # the current stream waits; the host does not
         self.apply_update()

@@ -225,3 +225,101 @@ def test_two_rank_bucketed_overlapped_update_and_parameter_broadcast(tmp_path):
     assert np.array_equal(np.load(tmp_path / 'p0_0.npy'), np.load(tmp_path / 'p0_1.npy'))
     assert np.array_equal(np.load(tmp_path / 'f0_1.npy'), np.load(tmp_path / 'f0_0.npy'))
     assert float(np.load(tmp_path / 'f0_1.npy')[0]) == 1.0          # rank 0's value
+
+
+class _Block(object):
+    def __init__(self, root):
+        class _C(object):
+            pass
+        self.conv1 = _C()
+        self.conv1.W = root + '/conv1/W'
+
+
+class _FakeLossWithProgress(_FakeLoss):
+    """Like _FakeLoss, and reports the backbone's blocks in backward order (last created
+    first) through ``progress`` -- what models.layers.BuildingBlock.backward does."""
+    supports_progress = True
+
+    def backward(self, after_head=None, progress=None):
+        store = self.ctx.train
+        full = sum(_fake_grad(store, i) for i in self.ids) / len(self.ids)
+        for n in store.names():
+            if not n.startswith('extractor/'):
+                store.view(n, self.ctx.grads).add_(store.view(n, full))
+        if after_head is not None:
+            after_head()
+        self.reported = []
+        for root in ('extractor/res4/b2', 'extractor/res4/b1', 'extractor/res4/a',
+                     'extractor/res3/a'):
+            for n in store.names():
+                if n.startswith(root + '/'):
+                    store.view(n, self.ctx.grads).add_(store.view(n, full))
+            if progress is not None:
+                progress(_Block(root))
+                self.reported.append(root)
+
+
+def _make_store_blocks():
+    s = E.FlatStore()
+    for root in ('extractor/res3/a', 'extractor/res4/a', 'extractor/res4/b1', 'extractor/res4/b2'):
+        s.add(root + '/conv1/W', (16, 1, 1, 8))
+        s.add(root + '/conv2/W', (16, 3, 3, 16))
+    s.add('rpn/conv1/W', (8, 3, 3, 4))
+    s.add('head/score/W', (5, 7))
+    return s.allocate('cpu')
+
+
+def _worker_chunked(rank, world, port, n_images, out_dir):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        comm = optimizers.create_communicator()
+        opt = optimizers.MomentumSGD(lr=0.005, momentum=0.9)
+        store = _make_store_blocks()
+        ctx = _Ctx(store)
+        ctx.frozen = E.FlatStore()
+        ctx.frozen.add('extractor/conv1/W', (4, 7, 7, 3))
+        ctx.frozen.allocate('cpu')
+        ctx.mark_dirty = lambda frozen=True: None
+
+        class Chain(object):
+            pass
+        chain = Chain()
+        chain.ctx = ctx
+        opt.setup(chain)
+        opt = optimizers.create_multi_node_optimizer(opt, comm)
+        opt.backbone_chunk = 3000          # floats: about one block (2432) -> several pieces
+        calls = []
+        real = dist.all_reduce
+
+        def counting(t, *a, **k):
+            calls.append(t.numel())
+            return real(t, *a, **k)
+        dist.all_reduce = counting
+        mine = list(optimizers.shard_indices(n_images, comm.size, comm.rank))
+        fake = _FakeLossWithProgress(ctx, mine)
+        applied = []
+        opt.apply_update = lambda: applied.append(ctx.grads.clone())
+        opt.update_overlapped(lambda: fake)
+        dist.all_reduce = real
+        assert len(fake.reported) == 4 and len(applied) == 1
+        assert len(calls) >= 3 and sum(calls) == ctx.grads.numel()     # heads + >= 2 backbone pieces
+        np.save(os.path.join(out_dir, 'cg_%d.npy' % rank), applied[0].numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_chunked_backbone_exchange(tmp_path):
+    """update_overlapped with ``backbone_chunk``: the backbone's gradients leave in several
+    all-reduces issued from the ``progress`` hook of the backward pass; together with the head
+    bucket they cover the buffer exactly once and give the sum of one all-reduce."""
+    world, n_images = 2, 4
+    port = _free_port()
+    mp.spawn(_worker_chunked, args=(world, port, n_images, str(tmp_path)), nprocs=world, join=True)
+    g0, g1 = np.load(tmp_path / 'cg_0.npy'), np.load(tmp_path / 'cg_1.npy')
+    assert np.array_equal(g0, g1)
+    store = _make_store_blocks()
+    want = sum(_fake_grad(store, i) for i in range(n_images)).numpy() / n_images
+    np.testing.assert_allclose(g0 / world, want, rtol=1e-6, atol=1e-6)
