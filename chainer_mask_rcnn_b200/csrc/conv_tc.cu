@@ -1053,7 +1053,19 @@ extern "C" int cmr_conv_gemm_tc_ws(const cmr_conv_desc* c, const float* a, const
   // groups (long reductions: the main loop dominates) or 3 stages and 3 groups (short
   // reductions: the epilogue's HBM traffic dominates).
   p.epi_groups = p.tma_a ? 3 : 2;
-  const int variant = g_conv_variant & 15;
+  int variant = g_conv_variant & 15;
+  {
+    // A/B knob (CMR_CONV_PAIR_K512=1): CTA pairs also for the K = 512 layers with at most one
+    // epilogue operand tensor (isolated: res5 conv3 + residual 228 -> 211 us, but 266 -> 304 us
+    // with addend AND mask, hence the condition)
+    static int pair512 = -1;
+    if (pair512 < 0) {
+      const char* e = getenv("CMR_CONV_PAIR_K512");
+      pair512 = e ? atoi(e) : 0;
+    }
+    if (pair512 && variant == 0 && p.K >= 512 && p.K < 1024 && p.N >= 1024 && !(addend && mask))
+      variant = 1;
+  }
   p.dbg = g_conv_dbg;
   p.probe = (g_conv_variant >> 5) & 1;                   // 32: no stores (instrumented builds)
   if (g_conv_variant & 16) p.addend = p.mask = nullptr;  // 16: no epilogue operand loads
