@@ -28,10 +28,12 @@
 //               (2 x BN columns) so tile i+1's MMAs overlap tile i's epilogue
 //   warps 6-13  epilogue (plus warps 0-3 when the A tiles come by TMA: 12 warps, three
 //               per TMEM lane quarter, interleaved over the 32-column chunks):
-//               tcgen05.ld (lane = row) -> per-warp shared-memory transpose of 16
-//               columns at a time -> 64 B row segments written 8 rows per instruction;
-//               the residual addend, the ReLU-mask operand and the affine vectors are
-//               requested the same way before the accumulator is waited for
+//               tcgen05.ld (lane = row) of a 32 x 32 chunk -> per-warp XOR-swizzled
+//               shared-memory transpose -> full 128 B row segments, 4 rows per store
+//               instruction; the residual addend, the ReLU-mask operand and the affine
+//               vectors are requested the same way before the accumulator is waited for.
+//               One straight-line block per chunk, ~300 instructions (DESIGN.md section 3:
+//               the epilogue was instruction-bound at ~850)
 // full/empty mbarrier ring of STAGES k-blocks (32 fp32 = one 128 B swizzle row)
 // shared by all tiles; tmem_full/tmem_empty barriers per accumulator buffer.
 #include <stdlib.h>
