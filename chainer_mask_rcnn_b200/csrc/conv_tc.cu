@@ -1084,52 +1084,10 @@ extern "C" int cmr_conv_gemm_tc_ws(const cmr_conv_desc* c, const float* a, const
   // single-wave launches are bound by their prologue / epilogue, not by operand delivery)
   const bool pair = pair_ok && bn == 256 && (deep || variant == 1) && p.tma_a && variant != 3 &&
                     (long long)ceil_div(p.M, 2 * kBM) * ceil_div(p.N, bn) >= sm_count() / 2;
-  // Tail split: a pair launch whose tiles do not fill its last wave (res5's 392 tiles on 74
-  // SM pairs: 6 waves for 5.3 waves of work) runs the whole waves as pairs and hands the
-  // images of the partial wave to a second launch with 128 x 128 single-CTA tiles (<= one
-  // wave of 148, a quarter of the work per tile).  Plain epilogues only; the cut is at an
-  // image boundary so that both launches are ordinary convolutions over a batch.
-  // MEASURED, OFF BY DEFAULT (CMR_CONV_TAIL_SPLIT=1 enables it for A/B runs): a 128 x 128
-  // single-CTA tile ingests 32 KB of operands per 256 MMA cycles -- it is operand-bound and
-  // takes as long as a 256 x 256 pair tile, so the tail wave does not get shorter: two
-  // same-box A/B pairs, tensor-bound launches 616.6 / 619.7 TFLOP/s with the split against
-  // 626.2 / 628.9 without, 13 more launches per step.
-  static int tail_ok = -1;
-  if (tail_ok < 0) {
-    const char* e = getenv("CMR_CONV_TAIL_SPLIT");
-    tail_ok = e ? atoi(e) : 0;
-  }
-  if (pair && tail_ok && c->tile_n == 0 && !bcast && p.tap_cols == 0 && p.d_stride == 1 &&
-      c->d_h == c->out_h && c->d_w == c->out_w && c->d_oy == 0 && c->d_ox == 0) {
-    const int slots = sm_count() / 2;
-    const int n_tiles = ceil_div(p.N, bn);
-    const long long tiles = (long long)ceil_div(p.M, 2 * kBM) * n_tiles;
-    const long long full = tiles / slots, rem = tiles % slots;
-    const int ohw = c->out_h * c->out_w;
-    if (full >= 1 && rem > 0 && rem * 10 < slots * 6) {
-      // images whose rows fit in the whole waves
-      const long long rows_main = full * slots / n_tiles * (2 * kBM);
-      const int img_main = (int)(rows_main / ohw);
-      const int img_tail = c->batch - img_main;
-      const long long tail_tiles =
-          (long long)ceil_div(img_tail * ohw, kBM) * ceil_div(p.N, 128);
-      if (img_main > 0 && img_tail > 0 && tail_tiles <= sm_count()) {
-        cmr_conv_desc main_d = *c, tail_d = *c;
-        main_d.batch = img_main;
-        main_d.tile_n = 256;           // (an explicit width also stops a second split)
-        tail_d.batch = img_tail;
-        tail_d.tile_n = 128;
-        const size_t a_off = (size_t)img_main * c->in_h * c->in_w * c->in_ld;
-        const size_t d_off = (size_t)img_main * c->d_h * c->d_w * c->d_ld;
-        int rc2 = cmr_conv_gemm_tc_ex(&main_d, a, w, d, scale, bias, addend, mask, nullptr, 1, 0.f,
-                                      stream);
-        if (rc2 != CMR_OK) return rc2;
-        return cmr_conv_gemm_tc_ex(&tail_d, a + a_off, w, d + d_off, scale, bias,
-                                   addend ? addend + d_off : nullptr, mask ? mask + d_off : nullptr,
-                                   nullptr, 1, 0.f, stream);
-      }
-    }
-  }
+  // (A first answer to the partial last wave of the 392-tile pair launches -- its images handed
+  // to a second launch of 128 x 128 single-CTA tiles -- was measured slower, 616.6 / 619.7
+  // against 626.2 / 628.9 TFLOP/s, and removed: such a tile is operand-bound and lasts as long
+  // as a 256 x 256 pair tile.  The K-split tail of launch_b is what replaced it.)
   CUtensorMap tmap;
   int rc = make_tmap_2d(&tmap, w, (uint64_t)p.N, (uint64_t)p.K, (uint32_t)(pair ? bn / 2 : bn));
   if (rc != CMR_OK) return rc;
